@@ -1,0 +1,110 @@
+// Shared device helpers for the fs2_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define FS2_OK 0
+#define FS2_ERR_ARG 1
+#define FS2_ERR_CUDA 2
+#define FS2_ERR_UNSUPPORTED 3
+
+// Activation rows live in one flat "padded row space": every (B, T, C) activation is
+// stored as [B * (T + 2*FS2_PAD), C]; row (b, t) sits at b*(T+2*FS2_PAD) + FS2_PAD + t.
+// The FS2_PAD rows either side hold the reflect halo (conv inputs) or zeros (gradients),
+// which turns every "same"-padded Conv1d into a plain shifted-row GEMM.
+#define FS2_PAD 4
+
+typedef __nv_bfloat16 bf16;
+
+#define CUDA_CHECK_RET(x)                                   \
+  do {                                                      \
+    cudaError_t e__ = (x);                                  \
+    if (e__ != cudaSuccess) { fs2_set_error(cudaGetErrorString(e__)); return FS2_ERR_CUDA; } \
+  } while (0)
+
+void fs2_set_error(const char* msg);
+int fs2_check_launch();
+
+template <typename T> struct ActT;
+template <> struct ActT<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct ActT<bf16> {
+  static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// 4-wide vector access helpers (T = float -> 16 B, T = bf16 -> 8 B)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Counter-based dropout RNG: one 64-bit mix per group of 4 consecutive elements
+// gives four 16-bit uniforms.  keep(i) is reproducible from (seed, stream, index),
+// so backward regenerates the mask instead of storing it.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+struct DropCfg {
+  float p;             // drop probability (0 => disabled)
+  unsigned long long seed;  // already mixed with a per-call stream id
+};
+// returns 4 keep-scales (0 or 1/(1-p)) for elements [4*g, 4*g+4)
+__device__ __forceinline__ float4 drop_scale4(const DropCfg& d, uint64_t group) {
+  if (d.p <= 0.f) return make_float4(1.f, 1.f, 1.f, 1.f);
+  uint64_t r = mix64(d.seed ^ (group * 0xD6E8FEB86659FD93ull));
+  uint32_t thr = (uint32_t)(d.p * 65536.0f);
+  float s = 1.0f / (1.0f - d.p);
+  float4 o;
+  o.x = ((uint32_t)(r & 0xFFFF) >= thr) ? s : 0.f;
+  o.y = ((uint32_t)((r >> 16) & 0xFFFF) >= thr) ? s : 0.f;
+  o.z = ((uint32_t)((r >> 32) & 0xFFFF) >= thr) ? s : 0.f;
+  o.w = ((uint32_t)((r >> 48) & 0xFFFF) >= thr) ? s : 0.f;
+  return o;
+}
+
+// (b, t) <-> flat padded row helpers
+struct RowSpace {
+  int T;      // valid rows per batch item
+  int Tp;     // T + 2*FS2_PAD
+};
+__device__ __forceinline__ bool row_decode(int r, int Tp, int T, int& b, int& t) {
+  b = r / Tp;
+  t = r - b * Tp - FS2_PAD;
+  return t >= 0 && t < T;
+}

@@ -1,0 +1,190 @@
+/* fs2_b200 -- C ABI of the B200-native FastSpeech2 hot path.
+ *
+ * The reference (Orca0917/fine-grained-emotional-control-of-tts) has no FFI: its
+ * "operator API" is the Python class contract of emo_rank_tts/fastspeech2/model.py
+ * (FastSpeech2.forward, :279-441) and loss.py (Loss.forward, :62-186), whose
+ * arithmetic is stock torch ops reached through speechbrain.  Each entry point below
+ * replaces one group of those torch-op call sites (cited per function) and is what a
+ * ctypes binding on the reference side would bind.
+ *
+ * Conventions: all pointers are DEVICE pointers unless named h_*; `stream` is a
+ * cudaStream_t passed as void*; every function returns 0 on success or a non-zero
+ * FS2_ERR_* code (fs2_last_error() gives the message).  Nothing here allocates
+ * persistent device memory; callers own every buffer.  No torch types.
+ *
+ * Activation layout ("padded row space"): a (B, T, C) activation is stored as
+ * [B*(T+8), C]; row (b,t) is at b*(T+8)+4+t.  The 4 rows either side of each item hold
+ * the reflect halo (conv inputs) or zeros (gradients).  `act_bf16` selects the storage
+ * type of GEMM-operand activations: 1 = bf16 (tensor-core path), 0 = fp32 (exact path).
+ */
+#ifndef FS2_B200_H
+#define FS2_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS2_ABI_VERSION 1
+
+const char* fs2_last_error(void);
+int fs2_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long fs2_launch_count(void);
+
+/* ---------------------------------------------------------------- GEMM family --
+ * One descriptor drives both the tcgen05/TMA tensor-core kernel (bf16 operands) and the
+ * exact SIMT kernel (fp32 or bf16 operands).  Replaces: nn.Linear / nn.Conv1d /
+ * baddbmm / bmm call sites of speechbrain's Conv1d, Linear and nn.MultiheadAttention
+ * (reference model.py:199-276 constructors; forward model.py:344-346, 359, 425-431) and
+ * their autograd backward (train.py:80).
+ * mode 0: C[m,n] = sum_{j<taps} sum_{k<K} A[a_row_off+m+j*a_tap_step, k] * B[n, j*b_tap_step+k]
+ * mode 1: C[m,n] = sum_j sum_k A[a_row_off+m+j*a_tap_step, k] * B[b_row_off+k, n+j*b_tap_step]
+ * mode 2: C[m, j*c_tap_stride+n] = sum_{k<K} A[a_row_off+k, m] * B[b_row_off+k+j*b_tap_step, n]
+ * Out-of-range operand coordinates read as zero.
+ */
+typedef struct {
+  int mode, M, N, K, taps, batch1, batch2;
+  const void* A; long long lda, a_s1, a_s2; int a_rows, a_inner, a_row_off, a_tap_step;
+  const void* B; long long ldb, b_s1, b_s2; int b_rows, b_inner, b_row_off, b_tap_step;
+  long long c_tap_stride;
+  void* C; int c_bf16; long long ldc, c_s1, c_s2; int c_row_off, c_col_off;
+  int accumulate;          /* 1: atomically add into fp32 C */
+  int split_k;             /* mode 2 only; >1 implies accumulate */
+  const float* bias; float alpha; int relu;
+  const void* relu_aux;    /* optional, addressed like C: out *= (aux > 0) */
+  int aux_bf16;
+  int rs_T, rs_Tp;         /* row space of the output rows (rs_Tp = 0: every row valid) */
+  const int* lens;         /* optional per-item valid length: rows t >= lens[b] -> 0 */
+  int halo;                /* >0: mirror-write the reflect halo of this width */
+  int ab_bf16;             /* operand storage: 1 = bf16, 0 = fp32 (SIMT only) */
+} Fs2Gemm;
+
+int fs2_gemm_simt(const Fs2Gemm* g, void* stream);
+int fs2_gemm_tc(const Fs2Gemm* g, void* stream);     /* tcgen05 + TMA, bf16 operands */
+/* device-side error word of the tensor-core kernel (non-zero: an mbarrier wait timed out) */
+int fs2_gemm_tc_error_flag(void);
+
+/* ------------------------------------------------------------ row-wise kernels -- */
+/* model.py:335-337  encPreNet embedding + sinusoidal pos-enc + padding mask.
+ * tokens (B,Tp) i64; emb (V,D) f32; pe (>=Tp, D) f32.  out_f32/out_act in padded row space. */
+int fs2_embed_posenc(const int64_t* tokens, const float* emb, const float* pe, int B, int Tp, int D,
+                     int pad_idx, float* out_f32, void* out_act, int act_bf16, int* src_lens, void* stream);
+
+/* LayerNorm family (speechbrain LayerNorm / nn.LayerNorm call sites: TransformerEncoderLayer
+ * norm1/norm2, TransformerEncoder.norm, DurationPredictor ln1/ln2, PostNet ln1-3).
+ *   z = x + drop_b(branch);  u = LN(z)*gamma+beta;  v = tanh?(u);  w = drop_a(v);
+ *   out = w * rowmask?  (+ post_add)          ; optional head: scalar[r] = dot(out, head_w)+head_b */
+typedef struct {
+  int B, T, C;
+  const float* x; const float* branch;     /* padded row space fp32; branch may be NULL */
+  float drop_b_p; unsigned long long drop_b_seed;
+  const float* gamma; const float* beta; float eps;
+  int tanh_act;
+  float drop_a_p; unsigned long long drop_a_seed;
+  const int* lens;                          /* NULL: no row mask */
+  const float* post_add;                    /* NULL or fp32 padded-row tensor added after everything */
+  float* out_f32; void* out_act; int act_bf16; int halo;
+  float* mean; float* rstd;                 /* [rows] saved statistics (may be NULL) */
+  const float* head_w; const float* head_b; float* head_out; float head_scale; /* optional 384->1 head; head_out is (B,T) plain */
+} Fs2LnFwd;
+int fs2_ln_fwd(const Fs2LnFwd* p, void* stream);
+
+typedef struct {
+  int B, T, C;
+  const float* dy; const float* dy2; int dy2_fold;   /* dy2 optional; dy2_fold=p>0: dy2 is a conv-dgrad output to be reflect-folded */
+  const float* dhead; const float* head_w; float head_scale; /* optional: + dhead[b,t]*head_w */
+  const float* x; const float* branch;
+  float drop_b_p; unsigned long long drop_b_seed;
+  const float* gamma; const float* beta; float eps; int tanh_act;
+  float drop_a_p; unsigned long long drop_a_seed;
+  const int* lens;
+  const float* mean; const float* rstd;
+  float* dx_f32;            /* dz (fp32, padded rows; invalid rows zero) */
+  void* dbranch_act; int act_bf16;   /* drop_b-backward of dz, operand storage, zero halo */
+  float* dgamma; float* dbeta;       /* accumulated (+=) */
+  float* dhead_w;                    /* accumulated (+=), optional */
+} Fs2LnBwd;
+int fs2_ln_bwd(const Fs2LnBwd* p, void* stream);
+
+/* model.py:352-360 speaker/intensity conditioning, split-weight form:
+ * y = (G + Ws.spk_emb[spk[b]] + Wi.intensity[b,t]) * mask ; G = token_feats.Wt^T (a GEMM) */
+int fs2_cond_finish(const float* G, const float* Wcat /*(D, 2D+5)*/, const float* spk_emb, const int64_t* speakers,
+                    const float* intensity /*(B,Tp,5)*/, const int* lens, int B, int Tp, int D,
+                    float* y_f32, void* y_act, int act_bf16, int halo, void* stream);
+int fs2_cond_bwd(const float* dy /*padded rows fp32, already masked*/, const float* Wcat, const float* spk_emb,
+                 const int64_t* speakers, const float* intensity, int B, int Tp, int D, int n_speakers,
+                 float* dWcat, float* dspk_emb, void* stream);
+
+/* speechbrain average_over_durations (model.py:383, 397): mean over non-zero frames per phoneme.
+ * values (B,Tm) f32; durs (B,Tp) i64 -> avg (B,Tp) f32; also emits starts/ends (B,Tp) i32 and nz counts. */
+int fs2_avg_over_durations(const float* values, const int64_t* durs, int B, int Tp, int Tm,
+                           float* avg, int* starts, int* ends, int* nz, void* stream);
+
+/* pitchEmbed / energyEmbed: Conv1d(1->D,k,reflect) over the phoneme axis + add (model.py:384-389, 398-403).
+ * contour (B,Tp) f32 plain.  y_f32 (unmasked) and y_act (masked copy = predictor input). */
+int fs2_embed_add(const float* x, const float* contour, const float* w /*(D,1,k)*/, const float* bias, int ksize,
+                  const int* lens, int B, int Tp, int D, float* y_f32, void* y_act, int act_bf16, int halo, void* stream);
+int fs2_embed_add_bwd(const float* dy /*padded rows*/, const float* contour, int ksize, int B, int Tp, int D,
+                      float* dw, float* dbias, void* stream);
+
+/* LengthRegulator = speechbrain upsample (model.py:406-410) + get_mask_from_lengths + decoder
+ * pos-enc + mask (model.py:411-423).
+ * fs2_lr_prepare: frames[b,p] = (long)(pace * dur[b,p]) (fdur != NULL: float durations, inference),
+ *                 ends = inclusive cumsum (i32), mel_lens[b].
+ * fs2_lr_expand:  out[b,f,:] = (in[b, idx(f), :] + pe[f,:]) for f < mel_lens[b], else 0;
+ *                 frame2ph[b,f] = idx(f) or -1.  in/out row pitch + offset let the same kernel serve
+ *                 plain (B,T,D) tensors (pitch=T, off=0) and the padded row space. */
+int fs2_lr_prepare(const int64_t* dur, const float* fdur, float pace, int B, int Tp, int* ends, int* mel_lens, void* stream);
+int fs2_lr_expand(const float* in, int in_pitch, int in_off, const int* ends, const int* mel_lens, const float* pe,
+                  int B, int Tp, int Tm, int D, float* out_f32, void* out_act, int act_bf16,
+                  int out_pitch, int out_off, int* frame2ph, void* stream);
+/* backward: dphon[b,p,:] = sum over the phoneme's frames of dframes (segment sum, no atomics) */
+int fs2_lr_bwd(const float* dframes, int f_pitch, int f_off, const int* ends, const int* mel_lens,
+               int B, int Tp, int Tm, int D, float* dphon, int p_pitch, int p_off, void* stream);
+
+/* softmax over keys with the reference's attn_mask quirk (model.py:338-343, 414-419):
+ * keys valid for (b,h) are [0, min(len[b], len[(b*H+h) % B])).  S (B*H, T, ldk) fp32 -> P, Pd. */
+int fs2_softmax_fwd(const float* S, const int* lens, int B, int H, int T, int ldk, float scale,
+                    float drop_p, unsigned long long seed, void* P, void* Pd, int act_bf16, void* stream);
+int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens, int B, int H, int T, int ldk, float scale,
+                    float drop_p, unsigned long long seed, void* dS, int act_bf16, void* stream);
+
+/* misc row-space utilities */
+int fs2_fold_halo(const float* src, int B, int T, int C, int p, const float* add, const int* lens,
+                  float* out_f32, void* out_act, int act_bf16, void* stream);
+int fs2_colsum(const void* x, int x_bf16, long long rows, int C, long long ld, float* out /* += */, void* stream);
+int fs2_unpad_mask(const float* src, const int* lens, int B, int T, int C, float* out_plain, void* out_act,
+                   int act_bf16, int halo, void* stream);
+int fs2_pad_rows(const float* src_plain, int B, int T, int C, float scale, float* out_f32, void* out_act, int act_bf16, void* stream);
+int fs2_embedding_bwd(const float* dx /*padded rows*/, const int64_t* tokens, int B, int Tp, int D, int pad_idx,
+                      float* demb /* += */, void* stream);
+int fs2_cast_bf16(const float* src, void* dst, long long n, void* stream);
+int fs2_add_(float* dst, const float* src, long long n, void* stream);
+
+/* ---------------------------------------------------------------------- losses -- */
+/* loss.py:101-160 per-sample sliced MSE x5, mean over B; fused forward + gradient.
+ * out[0..4] = mel, postnet, dur, pitch, energy (un-weighted).  Gradients are scaled by w[i]. */
+int fs2_mse_losses(const float* mel_out, const float* post_out, const float* mel_tgt, const float* log_dur_pred,
+                   const int64_t* dur_tgt, const float* pitch_pred, const float* pitch_tgt,
+                   const float* energy_pred, const float* energy_tgt, const int64_t* mel_len, const int64_t* phon_len,
+                   int B, int Tp, int Tm, int n_mels, const float* w /*5 weights (device)*/,
+                   float* out, float* dmel, float* dpost, float* ddur, float* dpitch, float* denergy, void* stream);
+/* speechbrain SSIMLoss (loss.py:155): masked per-sample min-max norm + 11x11 gaussian SSIM.
+ * out[0] = clamped loss; dmel_out += weight * dL/dmel_out.  ws: scratch, fs2_ssim_ws_floats() floats. */
+long long fs2_ssim_ws_floats(int B, int Tm, int n_mels);
+int fs2_ssim_loss(const float* mel_out, const float* mel_tgt, const int64_t* mel_len, int B, int Tm, int n_mels,
+                  const float* weight /*device scalar*/, float* out, float* dmel_out /* += , may be NULL */,
+                  float* ws, void* stream);
+
+/* train.py:81 AdamW (torch defaults) over one flat buffer; also refreshes the bf16 shadow. */
+int fs2_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+              float beta2, float eps, float wd, int step, float grad_scale, void* stream);
+
+/* train.py:16-51 duration-segment mean of frame intensities ("next" row f-1) */
+int fs2_intensity_segment_mean(const float* I /*(B,Tm,D)*/, const int64_t* dur, const int64_t* phon_len,
+                               int B, int Tp, int Tm, int D, float* out /*(B,Tp,D)*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

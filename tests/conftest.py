@@ -1,0 +1,23 @@
+import importlib
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return importlib.import_module("fine-grained-emotional-control-of-tts_b200")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    return importlib.import_module("fine-grained-emotional-control-of-tts_b200._lib")
