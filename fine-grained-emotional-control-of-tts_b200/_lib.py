@@ -18,6 +18,40 @@ PAD = 4  # FS2_PAD: halo rows either side of every batch item in the padded row 
 
 _lib = None
 
+# argument codes of every entry point in include/fs2_b200.h that returns a status
+# (p = pointer, i = int, f = float, q = long long, Q = unsigned long long); the trailing p is the stream
+SIGNATURES = {
+    "fs2_gemm_simt": "pp",
+    "fs2_gemm_tc": "pp",
+    "fs2_embed_posenc": "pppiiiippipp",
+    "fs2_embedding_bwd": "ppiiiipp",
+    "fs2_ln_fwd": "pp",
+    "fs2_ln_bwd": "pp",
+    "fs2_softmax_fwd": "ppiiiiffQppip",
+    "fs2_softmax_bwd": "pppiiiiffQpip",
+    "fs2_cond_finish": "ppppppiiipppiip",
+    "fs2_cond_bwd": "pppppiiipppp",
+    "fs2_avg_over_durations": "ppiiippppp",
+    "fs2_embed_add": "ppppipiiippiip",
+    "fs2_embed_add_bwd": "ppiiiippp",
+    "fs2_dur_decode": "pqpp",
+    "fs2_lr_prepare": "ppfiippp",
+    "fs2_lr_expand": "piipppiiiippiiipp",
+    "fs2_lr_bwd": "ppiippiiiipiip",
+    "fs2_fold_halo": "piiiipppppip",
+    "fs2_colsum": "piqiqpp",
+    "fs2_unpad_mask": "ppiiippiip",
+    "fs2_pad_rows": "ppiiifppip",
+    "fs2_pack_weights": "pippip",
+    "fs2_cast_bf16": "ppqp",
+    "fs2_add_": "ppqp",
+    "fs2_memset": "piqp",
+    "fs2_mse_losses": "pppppppppppiiiippppppppp",
+    "fs2_ssim_loss": "pppiiifpppp",
+    "fs2_adamw": "ppppqfffffifp",
+    "fs2_intensity_segment_mean": "pppiiiipp",
+}
+
 
 class Fs2Gemm(C.Structure):
     _fields_ = [
@@ -27,7 +61,7 @@ class Fs2Gemm(C.Structure):
         ("a_rows", C.c_int), ("a_inner", C.c_int), ("a_row_off", C.c_int), ("a_tap_step", C.c_int),
         ("B", C.c_void_p), ("ldb", C.c_longlong), ("b_s1", C.c_longlong), ("b_s2", C.c_longlong),
         ("b_rows", C.c_int), ("b_inner", C.c_int), ("b_row_off", C.c_int), ("b_tap_step", C.c_int),
-        ("c_tap_stride", C.c_longlong),
+        ("c_tap_stride", C.c_longlong), ("c_col_stride", C.c_longlong),
         ("C", C.c_void_p), ("c_bf16", C.c_int), ("ldc", C.c_longlong), ("c_s1", C.c_longlong),
         ("c_s2", C.c_longlong), ("c_row_off", C.c_int), ("c_col_off", C.c_int),
         ("accumulate", C.c_int), ("split_k", C.c_int),
@@ -70,6 +104,11 @@ class Fs2LnBwd(C.Structure):
     ]
 
 
+class Fs2PackItem(C.Structure):
+    _fields_ = [("src_off", C.c_longlong), ("dst_off", C.c_longlong), ("src_ld", C.c_longlong),
+                ("cout", C.c_int), ("cin", C.c_int), ("k", C.c_int), ("pad_", C.c_int)]
+
+
 def load():
     """Load the C-ABI library (once).  Fails loudly when it has not been built."""
     global _lib
@@ -83,8 +122,13 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.fs2_last_error.restype = C.c_char_p
     lib.fs2_launch_count.restype = C.c_longlong
-    if hasattr(lib, 'fs2_ssim_ws_floats'):
-        lib.fs2_ssim_ws_floats.restype = C.c_longlong
+    lib.fs2_ssim_ws_floats.restype = C.c_longlong
+    lib.fs2_ssim_ws_floats.argtypes = [C.c_int, C.c_int, C.c_int]
+    codes = {"p": C.c_void_p, "i": C.c_int, "f": C.c_float, "q": C.c_longlong, "Q": C.c_ulonglong}
+    for name, sig in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly
+        fn.argtypes = [codes[c] for c in sig]
+        fn.restype = C.c_int
     _lib = lib
     return lib
 
@@ -113,15 +157,18 @@ def launch_count():
 
 
 def call(name, *args):
+    """Call an entry point on torch's current stream.  Tensors become device pointers, None becomes NULL."""
     lib = load()
-    rc = getattr(lib, name)(*args)
-    check(rc, name)
+    conv = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
+    rc = getattr(lib, name)(*conv, torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        check(rc, name)
 
 
 # ---------------------------------------------------------------------------- GEMM
 def gemm(*, mode, M, N, K, A, lda, a_rows, a_inner, B, ldb, b_rows, b_inner, Cout, ldc, c_bf16,
          ab_bf16, taps=1, batch1=1, batch2=1, a_s1=0, a_s2=0, a_row_off=0, a_tap_step=0,
-         b_s1=0, b_s2=0, b_row_off=0, b_tap_step=0, c_tap_stride=0, c_s1=0, c_s2=0, c_row_off=0,
+         b_s1=0, b_s2=0, b_row_off=0, b_tap_step=0, c_tap_stride=0, c_col_stride=0, c_s1=0, c_s2=0, c_row_off=0,
          c_col_off=0, accumulate=0, split_k=1, bias=None, alpha=1.0, relu=0, relu_aux=None,
          aux_bf16=0, rs_T=0, rs_Tp=0, lens=None, halo=0, use_tc=None, A_off=0, B_off=0, C_off=0):
     """Thin wrapper over fs2_gemm_tc / fs2_gemm_simt.  A_off/B_off/C_off are element offsets
@@ -136,6 +183,7 @@ def gemm(*, mode, M, N, K, A, lda, a_rows, a_inner, B, ldb, b_rows, b_inner, Cou
     g.ldb, g.b_s1, g.b_s2 = ldb, b_s1, b_s2
     g.b_rows, g.b_inner, g.b_row_off, g.b_tap_step = b_rows, b_inner, b_row_off, b_tap_step
     g.c_tap_stride = c_tap_stride
+    g.c_col_stride = c_col_stride
     g.C = Cout.data_ptr() + C_off * (2 if c_bf16 else 4)
     g.c_bf16, g.ldc, g.c_s1, g.c_s2 = int(c_bf16), ldc, c_s1, c_s2
     g.c_row_off, g.c_col_off = c_row_off, c_col_off
@@ -150,7 +198,7 @@ def gemm(*, mode, M, N, K, A, lda, a_rows, a_inner, B, ldb, b_rows, b_inner, Cou
     if use_tc is None:
         use_tc = bool(ab_bf16)
     fn = "fs2_gemm_tc" if use_tc else "fs2_gemm_simt"
-    call(fn, C.byref(g), stream())
+    call(fn, C.addressof(g))
 
 
 def gemm_tc_error_flag():

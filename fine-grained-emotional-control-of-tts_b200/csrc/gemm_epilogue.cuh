@@ -5,7 +5,8 @@
 
 struct EpiRow {
   long long base;      // element offset of (row, c_col_off) in C
-  long long mirror;    // element offset delta of the reflect-halo mirror row (0 = none)
+  long long mirror;    // element offset delta of the reflect-halo mirror row at the item's start (0 = none)
+  long long mirror2;   // ... and at the item's end (a short item can need both)
   bool in_rect;        // row is a real (b,t) row of the rectangle
   bool live;           // in_rect and t < lens[b]
   bool skip;           // do not write this row at all
@@ -15,6 +16,7 @@ __device__ __forceinline__ void epi_row_setup(const Fs2Gemm& g, int i1, int i2, 
   long long r = (long long)g.c_row_off + m;
   er.base = (long long)i1 * g.c_s1 + (long long)i2 * g.c_s2 + r * g.ldc + g.c_col_off;
   er.mirror = 0;
+  er.mirror2 = 0;
   er.in_rect = true;
   er.live = true;
   er.skip = false;
@@ -25,8 +27,10 @@ __device__ __forceinline__ void epi_row_setup(const Fs2Gemm& g, int i1, int i2, 
     er.live = er.in_rect && (g.lens == nullptr || t < g.lens[b]);
     if (g.halo > 0) {
       if (!er.in_rect) er.skip = true;
-      else if (t >= 1 && t <= g.halo) er.mirror = -2LL * t * g.ldc;
-      else if (t >= g.rs_T - 1 - g.halo && t <= g.rs_T - 2) er.mirror = 2LL * (g.rs_T - 1 - t) * g.ldc;
+      else {
+        if (t >= 1 && t <= g.halo) er.mirror = -2LL * t * g.ldc;
+        if (t >= g.rs_T - 1 - g.halo && t <= g.rs_T - 2) er.mirror2 = 2LL * (g.rs_T - 1 - t) * g.ldc;
+      }
     }
   }
 }
@@ -53,10 +57,12 @@ __device__ __forceinline__ void epi_store(const Fs2Gemm& g, const EpiRow& er, lo
     bf16 h = __float2bfloat16_rn(v);
     ((bf16*)g.C)[o] = h;
     if (er.mirror) ((bf16*)g.C)[o + er.mirror] = h;
+    if (er.mirror2) ((bf16*)g.C)[o + er.mirror2] = h;
   } else if (atomic || g.accumulate) {
     atomicAdd(((float*)g.C) + o, v);
   } else {
     ((float*)g.C)[o] = v;
     if (er.mirror) ((float*)g.C)[o + er.mirror] = v;
+    if (er.mirror2) ((float*)g.C)[o + er.mirror2] = v;
   }
 }

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Fs2Gemm g) {
       if (n >= Ntot) continue;
       long long col;
       int nb;
-      if (g.mode == 2) { int j = n / g.N; nb = n - j * g.N; col = (long long)j * g.c_tap_stride + nb; }
+      if (g.mode == 2) { int j = n / g.N; nb = n - j * g.N; col = (long long)j * g.c_tap_stride + (long long)nb * (g.c_col_stride > 1 ? g.c_col_stride : 1); }
       else { nb = n; col = n; }
       epi_store(g, er, col, nb, acc[i][jj], nsplit > 1);
     }

@@ -259,10 +259,11 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
     const bool row_ok = ok && (m < g.M);
     if (row_ok) epi_row_setup(g, i1, i2, m, er);
     const bool atomic = p.nsplit > 1 || g.accumulate;
-    const long long colbase = (MODE == 2) ? (long long)tapN * g.c_tap_stride + n0 : n0;
-    const bool vec_f32 = !g.c_bf16 && !atomic && ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2 | colbase) % 4 == 0) &&
+    const long long cstr = (MODE == 2 && g.c_col_stride > 1) ? g.c_col_stride : 1;
+    const long long colbase = (MODE == 2) ? (long long)tapN * g.c_tap_stride + n0 * cstr : n0;
+    const bool vec_f32 = cstr == 1 && !g.c_bf16 && !atomic && ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2 | colbase) % 4 == 0) &&
                          (((uintptr_t)g.C) % 16 == 0);
-    const bool vec_bf16 = g.c_bf16 && ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2 | colbase) % 8 == 0) &&
+    const bool vec_bf16 = cstr == 1 && g.c_bf16 && ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2 | colbase) % 8 == 0) &&
                           (((uintptr_t)g.C) % 16 == 0);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
       }
       if (!row_ok || er.skip) continue;
       const int nb0 = n0 + c * 32;
-      const long long col0 = colbase + c * 32;
+      const long long col0 = colbase + c * 32 * cstr;
       const bool full = (nb0 + 32 <= g.N);
       if (full && (vec_f32 || vec_bf16)) {
         float v[32];
@@ -286,25 +287,33 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
           float* dst = (float*)g.C + er.base + col0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-          if (er.mirror) {
-            dst += er.mirror;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+          for (int mi = 0; mi < 2; ++mi) {
+            const long long mo = mi ? er.mirror2 : er.mirror;
+            if (mo) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                st4(dst + mo + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+            }
           }
         } else {
           bf16* dst = (bf16*)g.C + er.base + col0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-          if (er.mirror) {
-            dst += er.mirror;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+          for (int mi = 0; mi < 2; ++mi) {
+            const long long mo = mi ? er.mirror2 : er.mirror;
+            if (mo) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                st4(dst + mo + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+            }
           }
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (nb0 + i < g.N) epi_store(g, er, col0 + i, nb0 + i, __uint_as_float(r[i]), atomic);
+          if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
       }
     }
   }

@@ -1,0 +1,1132 @@
+// Memory-bound row kernels of the FastSpeech2 path (everything that is not a GEMM or a loss):
+// embedding + positional encoding, the LayerNorm family (residual / dropout / tanh / mask / scalar head fused,
+// forward and backward), masked softmax with the reference's attn_mask quirk, speaker/intensity conditioning,
+// average_over_durations, pitch/energy embed-add, the LengthRegulator (scan, expand, segment-sum backward),
+// halo folding, column sums, weight packing and the fused AdamW.
+//
+// All activations live in the padded row space of common.cuh.  Rule for every producer: rect rows get values,
+// halo rows get the reflect mirror (when `halo` > 0, width `halo`) and zeros otherwise, so GEMMs that sweep
+// whole row ranges never meet stale data.
+#include <math.h>
+#include "common.cuh"
+#include "../../include/fs2_b200.h"
+
+namespace {
+
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr int MAXV = 4;  // float4 per lane: C <= 512
+
+inline int grid_for_rows(long long rows) {
+  long long b = (rows + WARPS - 1) / WARPS;
+  const long long cap = 148 * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <typename T>
+__device__ __forceinline__ void store_act4(void* base, long long off, float4 v) {
+  st4(reinterpret_cast<T*>(base) + off, v);
+}
+
+// write one row (and its reflect mirrors) to the fp32 and act copies
+template <typename TA>
+__device__ __forceinline__ void store_row4(float* of, TA* oa, long long rowoff, int c, float4 v, int t, int T, int C,
+                                           int halo) {
+  if (of) st4(of + rowoff + c, v);
+  if (oa) st4(oa + rowoff + c, v);
+  if (halo > 0) {
+    if (t >= 1 && t <= halo) {
+      long long m = rowoff - 2LL * t * C;
+      if (of) st4(of + m + c, v);
+      if (oa) st4(oa + m + c, v);
+    }
+    if (t >= T - 1 - halo && t <= T - 2) {
+      long long m = rowoff + 2LL * (T - 1 - t) * C;
+      if (of) st4(of + m + c, v);
+      if (oa) st4(oa + m + c, v);
+    }
+  }
+}
+
+// halo rows that no mirror write reaches are zeroed (callers guarantee T > halo)
+__device__ __forceinline__ bool halo_row_needs_zero(int t, int T, int halo) {
+  if (t >= 0 && t < T) return false;
+  const int d = (t < 0) ? -t : (t - (T - 1));
+  return !(halo > 0 && d <= halo && d < T);
+}
+
+// ------------------------------------------------------------------ embedding + posenc --
+__global__ void count_nonpad_kernel(const int64_t* tokens, int B, int Tp, int pad_idx, int* lens) {
+  int b = blockIdx.x;
+  int cnt = 0;
+  for (int t = threadIdx.x; t < Tp; t += 32) cnt += (tokens[(long long)b * Tp + t] != pad_idx) ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (threadIdx.x == 0) lens[b] = cnt;
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) embed_posenc_kernel(const int64_t* tokens, const float* emb, const float* pe,
+                                                               int B, int Tp, int D, int pad_idx, float* of, TA* oa) {
+  const int lane = threadIdx.x & 31;
+  const int TP = Tp + 2 * FS2_PAD;
+  const long long rows = (long long)B * TP;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
+    const bool in = t >= 0 && t < Tp;
+    int64_t tok = in ? tokens[(long long)b * Tp + t] : 0;
+    const bool live = in && tok != pad_idx;
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        float4 e = ld4(emb + tok * D + c), p = ld4(pe + (long long)t * D + c);
+        v = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+      }
+      if (of) st4(of + r * D + c, v);
+      if (oa) st4(oa + r * D + c, v);
+    }
+  }
+}
+
+__global__ void embedding_bwd_kernel(const float* dx, const int64_t* tokens, int B, int Tp, int D, int pad_idx,
+                                     float* demb) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * Tp;
+  const int TP = Tp + 2 * FS2_PAD;
+  for (long long i = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); i < rows; i += (long long)gridDim.x * WARPS) {
+    int b = (int)(i / Tp), t = (int)(i - (long long)b * Tp);
+    int64_t tok = tokens[i];
+    if (tok == pad_idx) continue;
+    const float* src = dx + ((long long)b * TP + FS2_PAD + t) * D;
+    for (int c = lane; c < D; c += 32) atomicAdd(demb + tok * D + c, src[c]);
+  }
+}
+
+// ----------------------------------------------------------------------- LayerNorm fwd --
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p) {
+  const int lane = threadIdx.x & 31;
+  const int T = p.T, C = p.C, TP = T + 2 * FS2_PAD;
+  const long long rows = (long long)p.B * TP;
+  const float invC = 1.0f / (float)C;
+  TA* oa = (TA*)p.out_act;
+  const DropCfg db{p.drop_b_p, p.drop_b_seed}, da{p.drop_a_p, p.drop_a_seed};
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
+    const long long ro = r * C;
+    if (t < 0 || t >= T) {
+      if (halo_row_needs_zero(t, T, p.halo)) {
+        for (int c = lane * 4; c < C; c += 128) {
+          if (p.out_f32) st4(p.out_f32 + ro + c, make_float4(0.f, 0.f, 0.f, 0.f));
+          if (oa) st4(oa + ro + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      }
+      continue;
+    }
+    float4 z[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane * 4 + i * 128;
+      z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C) {
+        z[i] = ld4(p.x + ro + c);
+        if (p.branch) {
+          float4 br = ld4(p.branch + ro + c);
+          float4 k = drop_scale4(db, (uint64_t)(ro + c) >> 2);
+          z[i].x += br.x * k.x; z[i].y += br.y * k.y; z[i].z += br.z * k.z; z[i].w += br.w * k.w;
+        }
+        s += z[i].x + z[i].y + z[i].z + z[i].w;
+      }
+    }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane * 4 + i * 128;
+      if (c < C) {
+        float a = z[i].x - mean, bq = z[i].y - mean, cq = z[i].z - mean, d = z[i].w - mean;
+        q += a * a + bq * bq + cq * cq + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invC + p.eps);
+    if (lane == 0) {
+      if (p.mean) p.mean[r] = mean;
+      if (p.rstd) p.rstd[r] = rstd;
+    }
+    const bool live = (p.lens == nullptr) || (t < p.lens[b]);
+    float hd = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane * 4 + i * 128;
+      if (c < C) {
+        float4 g = ld4(p.gamma + c), be = ld4(p.beta + c);
+        float4 u;
+        u.x = (z[i].x - mean) * rstd * g.x + be.x;
+        u.y = (z[i].y - mean) * rstd * g.y + be.y;
+        u.z = (z[i].z - mean) * rstd * g.z + be.z;
+        u.w = (z[i].w - mean) * rstd * g.w + be.w;
+        if (p.tanh_act) { u.x = tanhf(u.x); u.y = tanhf(u.y); u.z = tanhf(u.z); u.w = tanhf(u.w); }
+        float4 k = drop_scale4(da, (uint64_t)(ro + c) >> 2);
+        u.x *= k.x; u.y *= k.y; u.z *= k.z; u.w *= k.w;
+        if (!live) u = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.post_add) {
+          float4 a = ld4(p.post_add + ro + c);
+          u.x += a.x; u.y += a.y; u.z += a.z; u.w += a.w;
+        }
+        if (p.head_w) {
+          float4 hw = ld4(p.head_w + c);
+          hd += u.x * hw.x + u.y * hw.y + u.z * hw.z + u.w * hw.w;
+        }
+        store_row4<TA>(p.out_f32, oa, ro, c, u, t, T, C, p.halo);
+      }
+    }
+    if (p.head_w) {
+      hd = warp_sum(hd);
+      if (lane == 0) p.head_out[(long long)b * T + t] = (hd + p.head_b[0]) * p.head_scale;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------- LayerNorm bwd --
+__device__ __forceinline__ void block_reduce_cols(float4 (&a)[MAXV], float* out, int C, float (*red)[128], int warp,
+                                                  int lane) {
+  if (!out) return;   // uniform across the block
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    __syncthreads();
+    red[warp][lane * 4 + 0] = a[i].x;
+    red[warp][lane * 4 + 1] = a[i].y;
+    red[warp][lane * 4 + 2] = a[i].z;
+    red[warp][lane * 4 + 3] = a[i].w;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      int c = i * 128 + threadIdx.x;
+      if (c < C) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) v += red[w][threadIdx.x];
+        atomicAdd(out + c, v);
+      }
+    }
+  }
+}
+
+// grad wrt the kernel's `out` for row (b,t): dy + fold(dy2) + dhead*head_w*scale, then back through
+// mask, drop_a, tanh, affine, normalisation, (ReLU of x), and the branch dropout.
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
+  __shared__ float red[WARPS][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int T = p.T, C = p.C, TP = T + 2 * FS2_PAD;
+  const long long rows = (long long)p.B * TP;
+  const float invC = 1.0f / (float)C;
+  TA* da_out = (TA*)p.dact;
+  const DropCfg db{p.drop_b_p, p.drop_b_seed}, da{p.drop_a_p, p.drop_a_seed};
+  float4 dg[MAXV], dbt[MAXV], dhw[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) dg[i] = dbt[i] = dhw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float dhb = 0.f;
+  for (long long r = (long long)blockIdx.x * WARPS + warp; r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
+    const long long ro = r * C;
+    if (t < 0 || t >= T) {
+      for (int c = lane * 4; c < C; c += 128) {
+        if (p.dx_f32) st4(p.dx_f32 + ro + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (da_out) st4(da_out + ro + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+      continue;
+    }
+    const bool live = (p.lens == nullptr) || (t < p.lens[b]);
+    const float mean = p.mean[r], rstd = p.rstd[r];
+    const float dh = p.dhead ? p.dhead[(long long)b * T + t] * p.head_scale : 0.f;
+    const int f = p.dy2_fold;
+    const long long m1 = (f > 0 && t >= 1 && t <= f) ? -2LL * t * C : 0;
+    const long long m2 = (f > 0 && t >= T - 1 - f && t <= T - 2) ? 2LL * (T - 1 - t) * C : 0;
+    float4 xh[MAXV], gx[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane * 4 + i * 128;
+      xh[i] = gx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < C) {
+        float4 z = ld4(p.x + ro + c);
+        if (p.branch) {
+          float4 br = ld4(p.branch + ro + c);
+          float4 k = drop_scale4(db, (uint64_t)(ro + c) >> 2);
+          z.x += br.x * k.x; z.y += br.y * k.y; z.z += br.z * k.z; z.w += br.w * k.w;
+        }
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.dy) g = ld4(p.dy + ro + c);
+        if (p.dy2) {
+          float4 a = ld4(p.dy2 + ro + c);
+          g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+          if (m1) { a = ld4(p.dy2 + ro + m1 + c); g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
+          if (m2) { a = ld4(p.dy2 + ro + m2 + c); g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
+        }
+        float4 gam = ld4(p.gamma + c), bet = ld4(p.beta + c);
+        float4 h;
+        h.x = (z.x - mean) * rstd; h.y = (z.y - mean) * rstd; h.z = (z.z - mean) * rstd; h.w = (z.w - mean) * rstd;
+        float4 u = make_float4(h.x * gam.x + bet.x, h.y * gam.y + bet.y, h.z * gam.z + bet.z, h.w * gam.w + bet.w);
+        if (p.tanh_act) { u.x = tanhf(u.x); u.y = tanhf(u.y); u.z = tanhf(u.z); u.w = tanhf(u.w); }
+        float4 k = drop_scale4(da, (uint64_t)(ro + c) >> 2);
+        if (p.head_w) {
+          float4 hw = ld4(p.head_w + c);
+          g.x += dh * hw.x; g.y += dh * hw.y; g.z += dh * hw.z; g.w += dh * hw.w;
+          if (live) {   // d head_w = dhead * out, out = u * drop_a (masked rows contribute 0)
+            dhw[i].x += dh * u.x * k.x; dhw[i].y += dh * u.y * k.y; dhw[i].z += dh * u.z * k.z; dhw[i].w += dh * u.w * k.w;
+          }
+        }
+        if (!live) g = make_float4(0.f, 0.f, 0.f, 0.f);
+        g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
+        if (p.tanh_act) {
+          g.x *= (1.f - u.x * u.x); g.y *= (1.f - u.y * u.y); g.z *= (1.f - u.z * u.z); g.w *= (1.f - u.w * u.w);
+        }
+        dg[i].x += g.x * h.x; dg[i].y += g.y * h.y; dg[i].z += g.z * h.z; dg[i].w += g.w * h.w;
+        dbt[i].x += g.x; dbt[i].y += g.y; dbt[i].z += g.z; dbt[i].w += g.w;
+        g.x *= gam.x; g.y *= gam.y; g.z *= gam.z; g.w *= gam.w;
+        s1 += g.x + g.y + g.z + g.w;
+        s2 += g.x * h.x + g.y * h.y + g.z * h.z + g.w * h.w;
+        xh[i] = h;
+        gx[i] = g;
+      }
+    }
+    if (p.head_w && lane == 0) dhb += dh;
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = lane * 4 + i * 128;
+      if (c < C) {
+        float4 dz;
+        dz.x = rstd * (gx[i].x - s1 - xh[i].x * s2);
+        dz.y = rstd * (gx[i].y - s1 - xh[i].y * s2);
+        dz.z = rstd * (gx[i].z - s1 - xh[i].z * s2);
+        dz.w = rstd * (gx[i].w - s1 - xh[i].w * s2);
+        if (p.relu_x) {
+          float4 x = ld4(p.x + ro + c);
+          if (!(x.x > 0.f)) dz.x = 0.f;
+          if (!(x.y > 0.f)) dz.y = 0.f;
+          if (!(x.z > 0.f)) dz.z = 0.f;
+          if (!(x.w > 0.f)) dz.w = 0.f;
+        }
+        if (p.dx_f32) st4(p.dx_f32 + ro + c, dz);
+        if (da_out) {
+          if (p.branch) {
+            float4 k = drop_scale4(db, (uint64_t)(ro + c) >> 2);
+            dz.x *= k.x; dz.y *= k.y; dz.z *= k.z; dz.w *= k.w;
+          }
+          st4(da_out + ro + c, dz);
+        }
+      }
+    }
+  }
+  // block reduction of the parameter gradients, one atomicAdd per column per block
+  block_reduce_cols(dg, p.dgamma, C, red, warp, lane);
+  block_reduce_cols(dbt, p.dbeta, C, red, warp, lane);
+  block_reduce_cols(dhw, p.dhead_w, C, red, warp, lane);
+  if (p.dhead_b) {
+    __syncthreads();
+    if (lane == 0) red[warp][0] = dhb;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = 0.f;
+      for (int w = 0; w < WARPS; ++w) v += red[w][0];
+      atomicAdd(p.dhead_b, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ softmax --
+__device__ __forceinline__ int quirk_kv(const int* lens, int B, int H, int bh) {
+  // model.py:338-343 / 414-419: the (h*B+b)-ordered attn_mask is read as (b*H+h) by nn.MultiheadAttention,
+  // so (b,h) masks pad[b] U pad[(b*H+h) % B]; with tail padding that is a min of two lengths.
+  int b = bh / H;
+  int o = bh % B;
+  return min(lens[b], lens[o]);
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) softmax_fwd_kernel(const float* S, const int* lens, int B, int H, int T,
+                                                              int ldk, float scale, DropCfg dc, TA* P, TA* Pd) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * H * T;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    const int bh = (int)(r / T);
+    const int kv = quirk_kv(lens, B, H, bh);
+    const float* s = S + r * ldk;
+    float mx = -INFINITY;
+    for (int c = lane * 4; c < kv; c += 128) {
+      float4 v = ld4(s + c);
+      mx = fmaxf(mx, v.x);
+      if (c + 1 < kv) mx = fmaxf(mx, v.y);
+      if (c + 2 < kv) mx = fmaxf(mx, v.z);
+      if (c + 3 < kv) mx = fmaxf(mx, v.w);
+    }
+    mx = warp_max(mx) * scale;
+    float sum = 0.f;
+    for (int c = lane * 4; c < kv; c += 128) {
+      float4 v = ld4(s + c);
+      sum += __expf(v.x * scale - mx);
+      if (c + 1 < kv) sum += __expf(v.y * scale - mx);
+      if (c + 2 < kv) sum += __expf(v.z * scale - mx);
+      if (c + 3 < kv) sum += __expf(v.w * scale - mx);
+    }
+    const float inv = 1.0f / warp_sum(sum);
+    for (int c = lane * 4; c < ldk; c += 128) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < kv) {
+        float4 v = ld4(s + c);
+        o.x = __expf(v.x * scale - mx) * inv;
+        if (c + 1 < kv) o.y = __expf(v.y * scale - mx) * inv;
+        if (c + 2 < kv) o.z = __expf(v.z * scale - mx) * inv;
+        if (c + 3 < kv) o.w = __expf(v.w * scale - mx) * inv;
+      }
+      st4(P + r * ldk + c, o);
+      if (Pd) {
+        float4 k = drop_scale4(dc, (uint64_t)(r * ldk + c) >> 2);
+        st4(Pd + r * ldk + c, make_float4(o.x * k.x, o.y * k.y, o.z * k.z, o.w * k.w));
+      }
+    }
+  }
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) softmax_bwd_kernel(const TA* P, const float* dPd, const int* lens, int B,
+                                                              int H, int T, int ldk, float scale, DropCfg dc, TA* dS) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * H * T;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    const int bh = (int)(r / T);
+    const int kv = quirk_kv(lens, B, H, bh);
+    const long long ro = r * ldk;
+    float dot = 0.f;
+    for (int c = lane * 4; c < kv; c += 128) {
+      float4 pv = ld4(P + ro + c), g = ld4(dPd + ro + c);
+      float4 k = drop_scale4(dc, (uint64_t)(ro + c) >> 2);
+      dot += pv.x * g.x * k.x + pv.y * g.y * k.y + pv.z * g.z * k.z + pv.w * g.w * k.w;   // P is 0 beyond kv
+    }
+    dot = warp_sum(dot);
+    for (int c = lane * 4; c < ldk; c += 128) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < kv) {
+        float4 pv = ld4(P + ro + c), g = ld4(dPd + ro + c);
+        float4 k = drop_scale4(dc, (uint64_t)(ro + c) >> 2);
+        o.x = scale * pv.x * (g.x * k.x - dot);
+        o.y = scale * pv.y * (g.y * k.y - dot);
+        o.z = scale * pv.z * (g.z * k.z - dot);
+        o.w = scale * pv.w * (g.w * k.w - dot);
+      }
+      st4(dS + ro + c, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------- speaker / intensity cond --
+__global__ void spk_proj_kernel(const float* Wcat, const float* spk_emb, const int64_t* speakers, int B, int D,
+                                float* sp) {
+  // sp[b, c] = sum_e Wcat[c, D + e] * spk_emb[speakers[b], e]; one warp per (b, c)
+  const int lane = threadIdx.x & 31;
+  const long long n = (long long)B * D;
+  const int ldw = 2 * D + 5;
+  for (long long i = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); i < n; i += (long long)gridDim.x * WARPS) {
+    int b = (int)(i / D), c = (int)(i - (long long)b * D);
+    const float* w = Wcat + (long long)c * ldw + D;
+    const float* e = spk_emb + speakers[b] * D;
+    float s = 0.f;
+    for (int k = lane; k < D; k += 32) s += w[k] * e[k];
+    s = warp_sum(s);
+    if (lane == 0) sp[i] = s;
+  }
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) cond_finish_kernel(const float* G, const float* Wcat, const float* sp,
+                                                              const float* intensity, const int* lens, int B, int Tp,
+                                                              int D, float* yf, TA* ya, int halo) {
+  const int lane = threadIdx.x & 31;
+  const int TP = Tp + 2 * FS2_PAD;
+  const long long rows = (long long)B * TP;
+  const int ldw = 2 * D + 5;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
+    const long long ro = r * D;
+    if (t < 0 || t >= Tp) {
+      if (halo_row_needs_zero(t, Tp, halo))
+        for (int c = lane * 4; c < D; c += 128) {
+          if (yf) st4(yf + ro + c, make_float4(0.f, 0.f, 0.f, 0.f));
+          if (ya) st4(ya + ro + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+      continue;
+    }
+    const bool live = t < lens[b];
+    float iv[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) iv[i] = intensity[((long long)b * Tp + t) * 5 + i];
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        float4 g = ld4(G + ro + c), s = ld4(sp + (long long)b * D + c);
+        float o[4] = {g.x + s.x, g.y + s.y, g.z + s.z, g.w + s.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* wi = Wcat + (long long)(c + q) * ldw + 2 * D;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) o[q] += wi[i] * iv[i];
+        }
+        v = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      store_row4<TA>(yf, ya, ro, c, v, t, Tp, D, halo);
+    }
+  }
+}
+
+// dsum[b,c] = sum_t dy[b,t,c];  dWi[c,i] += sum_{b,t} dy[b,t,c] * int[b,t,i]     (dy already masked)
+__global__ void cond_bwd_rows_kernel(const float* dy, const float* intensity, int B, int Tp, int D, float* dsum,
+                                     float* dWcat) {
+  const int b = blockIdx.x;
+  const int TP = Tp + 2 * FS2_PAD;
+  const int ldw = 2 * D + 5;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f, wi[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < Tp; ++t) {
+      float g = dy[((long long)b * TP + FS2_PAD + t) * D + c];
+      s += g;
+      const float* iv = intensity + ((long long)b * Tp + t) * 5;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) wi[i] += g * iv[i];
+    }
+    dsum[(long long)b * D + c] = s;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) atomicAdd(dWcat + (long long)c * ldw + 2 * D + i, wi[i]);
+  }
+}
+// dWs[c,e] += sum_b dsum[b,c]*emb[spk[b],e];   dspk_emb[spk[b],e] += sum_c Ws[c,e]*dsum[b,c]
+__global__ void cond_bwd_spk_kernel(const float* dsum, const float* Wcat, const float* spk_emb, const int64_t* speakers,
+                                    int B, int D, float* dWcat, float* dspk_emb) {
+  const int ldw = 2 * D + 5;
+  const long long n = (long long)D * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i / D), e = (int)(i - (long long)c * D);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dsum[(long long)b * D + c] * spk_emb[speakers[b] * D + e];
+    atomicAdd(dWcat + (long long)c * ldw + D + e, s);
+  }
+  const long long m = (long long)B * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(i / D), e = (int)(i - (long long)b * D);
+    float s = 0.f;
+    for (int c = 0; c < D; ++c) s += Wcat[(long long)c * ldw + D + e] * dsum[(long long)b * D + c];
+    atomicAdd(dspk_emb + speakers[b] * D + e, s);
+  }
+}
+
+// ------------------------------------------------------------- average_over_durations --
+// Restates speechbrain's prefix-sum formulation on torch's CPU semantics: cumsum accumulates in double and
+// rounds every prefix to fp32; segment sum = difference of two fp32 prefixes; mean over non-zero frames.
+__global__ void avg_over_durations_kernel(const float* values, const int64_t* durs, int B, int Tp, int Tm, float* avg,
+                                          int* starts, int* ends, int* nz) {
+  extern __shared__ unsigned char smraw[];
+  float* vc = (float*)smraw;            // Tm+1 prefix sums
+  int* nc = (int*)(vc + Tm + 1);        // Tm+1 non-zero counts
+  int* de = nc + Tm + 1;                // Tp inclusive duration ends
+  const int b = blockIdx.x;
+  const float* v = values + (long long)b * Tm;
+  for (int i = threadIdx.x; i < Tm; i += blockDim.x) vc[i + 1] = v[i];
+  for (int i = threadIdx.x; i < Tp; i += blockDim.x) de[i] = (int)durs[(long long)b * Tp + i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    int cnt = 0;
+    vc[0] = 0.f;
+    nc[0] = 0;
+    for (int i = 1; i <= Tm; ++i) {
+      float x = vc[i];
+      acc += (double)x;
+      cnt += (x != 0.0f) ? 1 : 0;
+      vc[i] = (float)acc;
+      nc[i] = cnt;
+    }
+  } else if (threadIdx.x == 32) {
+    int acc = 0;
+    for (int i = 0; i < Tp; ++i) { acc += de[i]; de[i] = acc; }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < Tp; p += blockDim.x) {
+    int e = de[p], s = p ? de[p - 1] : 0;
+    int ec = min(max(e, 0), Tm), sc = min(max(s, 0), Tm);
+    float sum = vc[ec] - vc[sc];
+    int n = nc[ec] - nc[sc];
+    long long o = (long long)b * Tp + p;
+    avg[o] = (n == 0) ? 0.f : sum / (float)n;
+    if (starts) starts[o] = s;
+    if (ends) ends[o] = e;
+    if (nz) nz[o] = n;
+  }
+}
+
+// ----------------------------------------------------------------- pitch/energy embed-add --
+__device__ __forceinline__ int reflect_idx(int i, int T) {
+  if (i < 0) i = -i;
+  if (i >= T) i = 2 * (T - 1) - i;
+  return i;
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) embed_add_kernel(const float* x, const float* contour, const float* w,
+                                                            const float* bias, int ksize, const int* lens, int B, int Tp,
+                                                            int D, float* yf, TA* ya, int halo) {
+  const int lane = threadIdx.x & 31;
+  const int TP = Tp + 2 * FS2_PAD;
+  const long long rows = (long long)B * TP;
+  const int pad = (ksize - 1) / 2;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
+    const long long ro = r * D;
+    if (t < 0 || t >= Tp) {
+      for (int c = lane * 4; c < D; c += 128) {
+        if (yf) st4(yf + ro + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (ya && halo_row_needs_zero(t, Tp, halo)) st4(ya + ro + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+      continue;
+    }
+    float cv[9];
+    for (int j = 0; j < ksize; ++j) cv[j] = contour[(long long)b * Tp + reflect_idx(t + j - pad, Tp)];
+    const bool live = t < lens[b];
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 xv = ld4(x + ro + c), bv = ld4(bias + c);
+      float o[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        for (int j = 0; j < ksize; ++j) o[q] += w[(long long)(c + q) * ksize + j] * cv[j];
+      float4 y = make_float4(xv.x + o[0], xv.y + o[1], xv.z + o[2], xv.w + o[3]);
+      if (yf) st4(yf + ro + c, y);
+      if (ya) store_row4<TA>(nullptr, ya, ro, c, live ? y : make_float4(0.f, 0.f, 0.f, 0.f), t, Tp, D, halo);
+    }
+  }
+}
+
+// dw[c,j] += sum_{b,t} dy[b,t,c]*contour_r[b,t+j-p]; dbias[c] += sum dy   (all rect rows, unmasked)
+__global__ void embed_add_bwd_kernel(const float* dy, const float* contour, int ksize, int B, int Tp, int D, float* dw,
+                                     float* dbias) {
+  const int TP = Tp + 2 * FS2_PAD;
+  const int pad = (ksize - 1) / 2;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float sb = 0.f;
+  const long long total = (long long)B * Tp;
+  for (long long i = blockIdx.y; i < total; i += gridDim.y) {
+    int b = (int)(i / Tp), t = (int)(i - (long long)b * Tp);
+    float g = dy[((long long)b * TP + FS2_PAD + t) * D + c];
+    sb += g;
+    for (int j = 0; j < ksize; ++j) acc[j] += g * contour[(long long)b * Tp + reflect_idx(t + j - pad, Tp)];
+  }
+  for (int j = 0; j < ksize; ++j) atomicAdd(dw + (long long)c * ksize + j, acc[j]);
+  atomicAdd(dbias + c, sb);
+}
+
+// ---------------------------------------------------------------------- LengthRegulator --
+__global__ void dur_decode_kernel(const float* log_dur, long long n, float* fdur) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fdur[i] = fmaxf(expm1f(log_dur[i]), 0.f);   // model.py:372-375
+}
+
+__global__ void lr_prepare_kernel(const int64_t* dur, const float* fdur, float pace, int B, int Tp, int* ends,
+                                  int* mel_lens) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int carry = 0;
+  for (int base = 0; base < Tp; base += 32) {
+    int p = base + lane;
+    int fr = 0;
+    if (p < Tp) {
+      // speechbrain upsample: (pace * durs).long() -- fp32 product, truncation toward zero
+      float d = fdur ? fdur[(long long)b * Tp + p] : (float)dur[(long long)b * Tp + p];
+      fr = (int)(long long)__fmul_rn(pace, d);
+      if (fr < 0) fr = 0;   // repeat_interleave rejects negatives; durations are >= 0 by construction
+    }
+    int s = fr;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += n;
+    }
+    if (p < Tp) ends[(long long)b * Tp + p] = carry + s;
+    carry += __shfl_sync(0xffffffffu, s, 31);
+  }
+  if (lane == 0) mel_lens[b] = carry;
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) lr_expand_kernel(const float* in, int in_pitch, int in_off, const int* ends,
+                                                            const int* mel_lens, const float* pe, int B, int Tp, int Tm,
+                                                            int D, float* of, TA* oa, int out_pitch, int out_off,
+                                                            int* frame2ph) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * out_pitch;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / out_pitch), f = (int)(r - (long long)b * out_pitch) - out_off;
+    const long long ro = r * D;
+    int idx = -1;
+    if (f >= 0 && f < Tm && f < mel_lens[b]) {
+      const int* e = ends + (long long)b * Tp;
+      int lo = 0, hi = Tp - 1;           // first p with ends[p] > f
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (e[mid] > f) hi = mid; else lo = mid + 1;
+      }
+      idx = lo;
+    }
+    if (frame2ph && f >= 0 && f < Tm && lane == 0) frame2ph[(long long)b * Tm + f] = idx;
+    const float* src = idx >= 0 ? in + ((long long)b * in_pitch + in_off + idx) * D : nullptr;
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src) {
+        v = ld4(src + c);
+        if (pe) {
+          float4 pv = ld4(pe + (long long)f * D + c);
+          v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+        }
+      }
+      if (of) st4(of + ro + c, v);
+      if (oa) st4(oa + ro + c, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) lr_bwd_kernel(const float* df, const float* df2, int f_pitch, int f_off,
+                                                         const int* ends, const int* mel_lens, int B, int Tp, int Tm,
+                                                         int D, float* dphon, int p_pitch, int p_off) {
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * p_pitch;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / p_pitch), p = (int)(r - (long long)b * p_pitch) - p_off;
+    int s = 0, e = 0;
+    if (p >= 0 && p < Tp) {
+      e = min(ends[(long long)b * Tp + p], Tm);
+      s = p ? min(ends[(long long)b * Tp + p - 1], Tm) : 0;
+    }
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int f = s; f < e; ++f) {
+        long long o = ((long long)b * f_pitch + f_off + f) * D + c;
+        float4 v = ld4(df + o);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        if (df2) { v = ld4(df2 + o); a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+      }
+      st4(dphon + r * D + c, a);
+    }
+  }
+}
+
+// -------------------------------------------------------------------- row-space utilities --
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) fold_halo_kernel(const float* src, int B, int T, int C, int pw,
+                                                            const float* add, const float* add2, const int* lens,
+                                                            float* of, TA* oa) {
+  const int lane = threadIdx.x & 31;
+  const int TP = T + 2 * FS2_PAD;
+  const long long rows = (long long)B * TP;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
+    const long long ro = r * C;
+    const bool in = t >= 0 && t < T;
+    const bool live = in && (lens == nullptr || t < lens[b]);
+    const long long m1 = (in && pw > 0 && t >= 1 && t <= pw) ? -2LL * t * C : 0;
+    const long long m2 = (in && pw > 0 && t >= T - 1 - pw && t <= T - 2) ? 2LL * (T - 1 - t) * C : 0;
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        if (src) {
+          v = ld4(src + ro + c);
+          if (m1) { float4 a = ld4(src + ro + m1 + c); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+          if (m2) { float4 a = ld4(src + ro + m2 + c); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+        }
+        if (add) { float4 a = ld4(add + ro + c); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+        if (add2) { float4 a = ld4(add2 + ro + c); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+      }
+      if (of) st4(of + ro + c, v);
+      if (oa) st4(oa + ro + c, v);
+    }
+  }
+}
+
+template <typename TX>
+__global__ void colsum_kernel(const TX* x, long long rows, int C, long long ld, float* out) {
+  __shared__ float4 red[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+      float4 v = ld4(x + r * ld + c);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) { float4 v = red[i][threadIdx.x]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    atomicAdd(out + c, a.x);
+    atomicAdd(out + c + 1, a.y);
+    atomicAdd(out + c + 2, a.z);
+    atomicAdd(out + c + 3, a.w);
+  }
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) unpad_mask_kernel(const float* src, const int* lens, int B, int T, int C,
+                                                             float* plain, TA* oa, int halo) {
+  const int lane = threadIdx.x & 31;
+  const int TP = T + 2 * FS2_PAD;
+  const long long rows = (long long)B * TP;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
+    const long long ro = r * C;
+    if (t < 0 || t >= T) {
+      if (oa && halo_row_needs_zero(t, T, halo))
+        for (int c = lane * 4; c < C; c += 128) st4(oa + ro + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    const bool live = (lens == nullptr) || (t < lens[b]);
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 v = live ? ld4(src + ro + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (plain) st4(plain + ((long long)b * T + t) * C + c, v);
+      if (oa) store_row4<TA>(nullptr, oa, ro, c, v, t, T, C, halo);
+    }
+  }
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) pad_rows_kernel(const float* a, const float* a2, int B, int T, int C,
+                                                           float scale, float* of, TA* oa) {
+  const int lane = threadIdx.x & 31;
+  const int TP = T + 2 * FS2_PAD;
+  const long long rows = (long long)B * TP;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
+    const bool in = t >= 0 && t < T;
+    for (int c = lane * 4; c < C; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in) {
+        long long o = ((long long)b * T + t) * C + c;
+        v = ld4(a + o);
+        if (a2) { float4 w = ld4(a2 + o); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      }
+      if (of) st4(of + r * C + c, v);
+      if (oa) st4(oa + r * C + c, v);
+    }
+  }
+}
+
+// Weight packing: dst[co, j, ci] = src[co*src_ld + ci*k + j]  (torch Conv1d (Cout,Cin,k) -> tap-major K),
+// one launch for the whole parameter set driven by a device-side table.
+template <typename TD>
+__global__ void pack_weights_kernel(const Fs2PackItem* items, const float* src_base, TD* dst_base) {
+  const Fs2PackItem it = items[blockIdx.y];
+  const long long n = (long long)it.cout * it.cin * it.k;
+  const float* src = src_base + it.src_off;
+  TD* dst = dst_base + it.dst_off;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int ci = (int)(i % it.cin);
+    long long q = i / it.cin;
+    int j = (int)(q % it.k);
+    long long co = q / it.k;
+    ActT<TD>::st(dst + i, src[co * it.src_ld + (long long)ci * it.k + j]);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* s, bf16* d, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) st4(d + i, ld4(s + i));
+  else for (; i < n; ++i) d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void add_kernel(float* d, const float* s, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 a = ld4(d + i), b = ld4(s + i);
+    st4(d + i, make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w));
+  } else for (; i < n; ++i) d[i] += s[i];
+}
+
+__global__ void adamw_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                             float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (i + 3 < n) {
+    float4 P = ld4(p + i), G = ld4(g + i), M = ld4(m + i), V = ld4(v + i);
+    float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float gr = gg[q] * gscale;
+      pp[q] *= (1.f - lr * wd);
+      mm[q] = b1 * mm[q] + (1.f - b1) * gr;
+      vv[q] = b2 * vv[q] + (1.f - b2) * gr * gr;
+      float denom = sqrtf(vv[q]) / bc2_sqrt + eps;
+      pp[q] -= (lr / bc1) * (mm[q] / denom);
+    }
+    st4(p + i, P); st4(m + i, M); st4(v + i, V);
+  } else {
+    for (; i < n; ++i) {
+      float gr = g[i] * gscale;
+      float P = p[i] * (1.f - lr * wd);
+      float M = b1 * m[i] + (1.f - b1) * gr;
+      float V = b2 * v[i] + (1.f - b2) * gr * gr;
+      P -= (lr / bc1) * (M / (sqrtf(V) / bc2_sqrt + eps));
+      p[i] = P; m[i] = M; v[i] = V;
+    }
+  }
+}
+
+// train.py:16-51: per-phoneme mean of frame intensities (plain mean, zero-duration phonemes -> 0)
+__global__ void intensity_segment_mean_kernel(const float* I, const int64_t* dur, const int64_t* phon_len, int B, int Tp,
+                                              int Tm, int D, float* out) {
+  extern __shared__ int ends_s[];
+  const int b = blockIdx.x;
+  const int pl = (int)phon_len[b];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int p = 0; p < Tp; ++p) { if (p < pl) acc += (int)dur[(long long)b * Tp + p]; ends_s[p] = acc; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Tp * D; i += blockDim.x) {
+    int p = i / D, d = i - p * D;
+    float r = 0.f;
+    if (p < pl) {
+      int e = min(ends_s[p], Tm), s = p ? min(ends_s[p - 1], Tm) : 0;
+      float acc = 0.f;
+      for (int f = s; f < e; ++f) acc += I[((long long)b * Tm + f) * D + d];
+      float den = fmaxf((float)dur[(long long)b * Tp + p], 1.0f);
+      r = acc / den;
+    }
+    out[((long long)b * Tp + p) * D + d] = r;
+  }
+}
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+#define REQUIRE(cond, msg) do { if (!(cond)) { fs2_set_error(msg); return FS2_ERR_ARG; } } while (0)
+
+extern "C" int fs2_embed_posenc(const int64_t* tokens, const float* emb, const float* pe, int B, int Tp, int D,
+                                int pad_idx, float* out_f32, void* out_act, int act_bf16, int* src_lens, void* stream) {
+  REQUIRE(tokens && emb && pe && src_lens && D % 4 == 0, "fs2_embed_posenc: bad arguments");
+  count_nonpad_kernel<<<B, 32, 0, ST>>>(tokens, B, Tp, pad_idx, src_lens);
+  int rc = fs2_check_launch();
+  if (rc) return rc;
+  const long long rows = (long long)B * (Tp + 2 * FS2_PAD);
+  if (act_bf16) embed_posenc_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(tokens, emb, pe, B, Tp, D, pad_idx, out_f32, (bf16*)out_act);
+  else embed_posenc_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(tokens, emb, pe, B, Tp, D, pad_idx, out_f32, (float*)out_act);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_embedding_bwd(const float* dx, const int64_t* tokens, int B, int Tp, int D, int pad_idx, float* demb,
+                                 void* stream) {
+  REQUIRE(dx && tokens && demb, "fs2_embedding_bwd: null pointer");
+  embedding_bwd_kernel<<<grid_for_rows((long long)B * Tp), THREADS, 0, ST>>>(dx, tokens, B, Tp, D, pad_idx, demb);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_ln_fwd(const Fs2LnFwd* p, void* stream) {
+  REQUIRE(p && p->x && p->gamma && p->beta, "fs2_ln_fwd: null pointer");
+  REQUIRE(p->C % 4 == 0 && p->C <= 128 * MAXV, "fs2_ln_fwd: C must be a multiple of 4 and <= 512");
+  REQUIRE(p->halo <= FS2_PAD && (p->halo == 0 || p->T > p->halo), "fs2_ln_fwd: halo too wide for T");
+  const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
+  if (p->act_bf16) ln_fwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(*p);
+  else ln_fwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(*p);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
+  REQUIRE(p && p->x && p->gamma && p->beta && p->mean && p->rstd, "fs2_ln_bwd: null pointer");
+  REQUIRE(p->C % 4 == 0 && p->C <= 128 * MAXV, "fs2_ln_bwd: C must be a multiple of 4 and <= 512");
+  const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
+  int grid = grid_for_rows(rows);
+  if (grid > 148 * 4) grid = 148 * 4;
+  if (p->act_bf16) ln_bwd_kernel<bf16><<<grid, THREADS, 0, ST>>>(*p);
+  else ln_bwd_kernel<float><<<grid, THREADS, 0, ST>>>(*p);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_softmax_fwd(const float* S, const int* lens, int B, int H, int T, int ldk, float scale, float drop_p,
+                               unsigned long long seed, void* P, void* Pd, int act_bf16, void* stream) {
+  REQUIRE(S && lens && P && ldk % 4 == 0 && ldk >= T, "fs2_softmax_fwd: bad arguments");
+  DropCfg dc{drop_p, seed};
+  if (drop_p <= 0.f) Pd = nullptr;
+  const long long rows = (long long)B * H * T;
+  if (act_bf16) softmax_fwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(S, lens, B, H, T, ldk, scale, dc, (bf16*)P, (bf16*)Pd);
+  else softmax_fwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(S, lens, B, H, T, ldk, scale, dc, (float*)P, (float*)Pd);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens, int B, int H, int T, int ldk,
+                               float scale, float drop_p, unsigned long long seed, void* dS, int act_bf16, void* stream) {
+  REQUIRE(P && dPd && lens && dS && ldk % 4 == 0, "fs2_softmax_bwd: bad arguments");
+  DropCfg dc{drop_p, seed};
+  const long long rows = (long long)B * H * T;
+  if (act_bf16) softmax_bwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>((const bf16*)P, dPd, lens, B, H, T, ldk, scale, dc, (bf16*)dS);
+  else softmax_bwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>((const float*)P, dPd, lens, B, H, T, ldk, scale, dc, (float*)dS);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_cond_finish(const float* G, const float* Wcat, const float* spk_emb, const int64_t* speakers,
+                               const float* intensity, const int* lens, int B, int Tp, int D, float* sp_ws, float* y_f32,
+                               void* y_act, int act_bf16, int halo, void* stream) {
+  REQUIRE(G && Wcat && spk_emb && speakers && intensity && lens && sp_ws && D % 4 == 0, "fs2_cond_finish: bad arguments");
+  spk_proj_kernel<<<grid_for_rows((long long)B * D), THREADS, 0, ST>>>(Wcat, spk_emb, speakers, B, D, sp_ws);
+  int rc = fs2_check_launch();
+  if (rc) return rc;
+  const long long rows = (long long)B * (Tp + 2 * FS2_PAD);
+  if (act_bf16) cond_finish_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(G, Wcat, sp_ws, intensity, lens, B, Tp, D, y_f32, (bf16*)y_act, halo);
+  else cond_finish_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(G, Wcat, sp_ws, intensity, lens, B, Tp, D, y_f32, (float*)y_act, halo);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_cond_bwd(const float* dy, const float* Wcat, const float* spk_emb, const int64_t* speakers,
+                            const float* intensity, int B, int Tp, int D, float* dsum_ws, float* dWcat, float* dspk_emb,
+                            void* stream) {
+  REQUIRE(dy && Wcat && spk_emb && speakers && intensity && dsum_ws && dWcat && dspk_emb, "fs2_cond_bwd: null pointer");
+  cond_bwd_rows_kernel<<<B, 128, 0, ST>>>(dy, intensity, B, Tp, D, dsum_ws, dWcat);
+  int rc = fs2_check_launch();
+  if (rc) return rc;
+  cond_bwd_spk_kernel<<<148, 256, 0, ST>>>(dsum_ws, Wcat, spk_emb, speakers, B, D, dWcat, dspk_emb);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_avg_over_durations(const float* values, const int64_t* durs, int B, int Tp, int Tm, float* avg,
+                                      int* starts, int* ends, int* nz, void* stream) {
+  REQUIRE(values && durs && avg, "fs2_avg_over_durations: null pointer");
+  size_t smem = (size_t)(Tm + 1) * 8 + (size_t)Tp * 4;
+  REQUIRE(smem <= 48 * 1024, "fs2_avg_over_durations: Tm too large for the shared-memory scan");
+  avg_over_durations_kernel<<<B, 128, smem, ST>>>(values, durs, B, Tp, Tm, avg, starts, ends, nz);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_embed_add(const float* x, const float* contour, const float* w, const float* bias, int ksize,
+                             const int* lens, int B, int Tp, int D, float* y_f32, void* y_act, int act_bf16, int halo,
+                             void* stream) {
+  REQUIRE(x && contour && w && bias && lens && ksize >= 1 && ksize <= 9 && (ksize & 1) && Tp > (ksize - 1) / 2,
+          "fs2_embed_add: bad arguments");
+  const long long rows = (long long)B * (Tp + 2 * FS2_PAD);
+  if (act_bf16) embed_add_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(x, contour, w, bias, ksize, lens, B, Tp, D, y_f32, (bf16*)y_act, halo);
+  else embed_add_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(x, contour, w, bias, ksize, lens, B, Tp, D, y_f32, (float*)y_act, halo);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_embed_add_bwd(const float* dy, const float* contour, int ksize, int B, int Tp, int D, float* dw,
+                                 float* dbias, void* stream) {
+  REQUIRE(dy && contour && dw && dbias && ksize <= 9, "fs2_embed_add_bwd: bad arguments");
+  dim3 grid((D + 127) / 128, 64);
+  embed_add_bwd_kernel<<<grid, 128, 0, ST>>>(dy, contour, ksize, B, Tp, D, dw, dbias);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_dur_decode(const float* log_dur, long long n, float* fdur, void* stream) {
+  REQUIRE(log_dur && fdur, "fs2_dur_decode: null pointer");
+  dur_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST>>>(log_dur, n, fdur);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_lr_prepare(const int64_t* dur, const float* fdur, float pace, int B, int Tp, int* ends, int* mel_lens,
+                              void* stream) {
+  REQUIRE((dur || fdur) && ends && mel_lens, "fs2_lr_prepare: null pointer");
+  lr_prepare_kernel<<<B, 32, 0, ST>>>(dur, fdur, pace, B, Tp, ends, mel_lens);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_lr_expand(const float* in, int in_pitch, int in_off, const int* ends, const int* mel_lens,
+                             const float* pe, int B, int Tp, int Tm, int D, float* out_f32, void* out_act, int act_bf16,
+                             int out_pitch, int out_off, int* frame2ph, void* stream) {
+  REQUIRE(in && ends && mel_lens && D % 4 == 0, "fs2_lr_expand: bad arguments");
+  const long long rows = (long long)B * out_pitch;
+  if (act_bf16) lr_expand_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (bf16*)out_act, out_pitch, out_off, frame2ph);
+  else lr_expand_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (float*)out_act, out_pitch, out_off, frame2ph);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pitch, int f_off, const int* ends,
+                          const int* mel_lens, int B, int Tp, int Tm, int D, float* dphon, int p_pitch, int p_off,
+                          void* stream) {
+  REQUIRE(dframes && ends && dphon && D % 4 == 0, "fs2_lr_bwd: bad arguments");
+  lr_bwd_kernel<<<grid_for_rows((long long)B * p_pitch), THREADS, 0, ST>>>(dframes, dframes2, f_pitch, f_off, ends, mel_lens, B, Tp, Tm, D, dphon, p_pitch, p_off);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_fold_halo(const float* src, int B, int T, int C, int p, const float* add, const float* add2,
+                             const int* lens, float* out_f32, void* out_act, int act_bf16, void* stream) {
+  REQUIRE(C % 4 == 0 && p <= FS2_PAD, "fs2_fold_halo: bad arguments");
+  const long long rows = (long long)B * (T + 2 * FS2_PAD);
+  if (act_bf16) fold_halo_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(src, B, T, C, p, add, add2, lens, out_f32, (bf16*)out_act);
+  else fold_halo_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(src, B, T, C, p, add, add2, lens, out_f32, (float*)out_act);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_colsum(const void* x, int x_bf16, long long rows, int C, long long ld, float* out, void* stream) {
+  REQUIRE(x && out && C % 4 == 0 && ld % 4 == 0, "fs2_colsum: bad arguments");
+  long long gy = (rows + 63) / 64;
+  if (gy > 296) gy = 296;
+  if (gy < 1) gy = 1;
+  dim3 grid((C + 127) / 128, (unsigned)gy), block(32, 8);
+  if (x_bf16) colsum_kernel<bf16><<<grid, block, 0, ST>>>((const bf16*)x, rows, C, ld, out);
+  else colsum_kernel<float><<<grid, block, 0, ST>>>((const float*)x, rows, C, ld, out);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_unpad_mask(const float* src, const int* lens, int B, int T, int C, float* out_plain, void* out_act,
+                              int act_bf16, int halo, void* stream) {
+  REQUIRE(src && C % 4 == 0, "fs2_unpad_mask: bad arguments");
+  const long long rows = (long long)B * (T + 2 * FS2_PAD);
+  if (act_bf16) unpad_mask_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(src, lens, B, T, C, out_plain, (bf16*)out_act, halo);
+  else unpad_mask_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(src, lens, B, T, C, out_plain, (float*)out_act, halo);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_pad_rows(const float* src_plain, const float* src2_plain, int B, int T, int C, float scale,
+                            float* out_f32, void* out_act, int act_bf16, void* stream) {
+  REQUIRE(src_plain && C % 4 == 0, "fs2_pad_rows: bad arguments");
+  const long long rows = (long long)B * (T + 2 * FS2_PAD);
+  if (act_bf16) pad_rows_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(src_plain, src2_plain, B, T, C, scale, out_f32, (bf16*)out_act);
+  else pad_rows_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(src_plain, src2_plain, B, T, C, scale, out_f32, (float*)out_act);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_pack_weights(const Fs2PackItem* items_dev, int n_items, const float* src_base, void* dst_base,
+                                int dst_bf16, void* stream) {
+  REQUIRE(items_dev && src_base && dst_base && n_items > 0, "fs2_pack_weights: bad arguments");
+  dim3 grid(64, n_items);
+  if (dst_bf16) pack_weights_kernel<bf16><<<grid, 256, 0, ST>>>(items_dev, src_base, (bf16*)dst_base);
+  else pack_weights_kernel<float><<<grid, 256, 0, ST>>>(items_dev, src_base, (float*)dst_base);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_cast_bf16(const float* src, void* dst, long long n, void* stream) {
+  REQUIRE(src && dst, "fs2_cast_bf16: null pointer");
+  cast_bf16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ST>>>(src, (bf16*)dst, n);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_add_(float* dst, const float* src, long long n, void* stream) {
+  REQUIRE(src && dst, "fs2_add_: null pointer");
+  add_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ST>>>(dst, src, n);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_memset(void* dst, int value, long long nbytes, void* stream) {
+  CUDA_CHECK_RET(cudaMemsetAsync(dst, value, (size_t)nbytes, ST));
+  return FS2_OK;
+}
+
+extern "C" int fs2_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                         float eps, float wd, int step, float grad_scale, void* stream) {
+  REQUIRE(p && g && m && v && step >= 1, "fs2_adamw: bad arguments");
+  float bc1 = 1.0f - powf(beta1, (float)step);
+  float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
+  adamw_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_intensity_segment_mean(const float* I, const int64_t* dur, const int64_t* phon_len, int B, int Tp,
+                                          int Tm, int D, float* out, void* stream) {
+  REQUIRE(I && dur && phon_len && out, "fs2_intensity_segment_mean: null pointer");
+  intensity_segment_mean_kernel<<<B, 256, (size_t)Tp * 4, ST>>>(I, dur, phon_len, B, Tp, Tm, D, out);
+  return fs2_check_launch();
+}

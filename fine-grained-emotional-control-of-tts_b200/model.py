@@ -1,0 +1,816 @@
+"""Drop-in `FastSpeech2` for `/root/reference/emo_rank_tts/fastspeech2/model.py:149-441`.
+
+Same constructor kwargs (parameter.yaml:62-90 + n_speakers), same forward signature and 8-tuple, same
+state_dict keys -- but every numeric op of the forward AND the backward is a hand-written sm_100a kernel
+reached through the C ABI of include/fs2_b200.h (libfs2_b200.so).  torch is used for device memory,
+streams and autograd wiring only.  There is no CPU path.
+
+Layout: activations live in a "padded row space" (B items x (T+8) rows, 4 halo rows either side of every
+item) so that every reflect-"same"-padded Conv1d of the reference becomes a shifted-row implicit GEMM, and
+its dgrad / wgrad are the same GEMM kernel in its other two operand modes.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .params import ParamStore
+
+PAD = L.PAD
+_M64 = (1 << 64) - 1
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+class Arena:
+    """Bump allocator over a zero-initialised device buffer of ONE dtype (stale rows that a sweep-style GEMM
+    may touch are then always finite values of the right type, never reinterpreted bits)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+        self.buf = None
+        self.off = 0
+        self.extra = []
+        self.high = 0
+
+    def reset(self, device):
+        need = self.high
+        if self.buf is None or self.buf.device != device or self.extra:
+            size = max(int(need * 1.25), 1 << 20)
+            if self.buf is None or self.buf.device != device or size > self.buf.numel():
+                self.buf = torch.zeros(size, dtype=self.dtype, device=device)
+        self.extra = []
+        self.off = 0
+        self.high = 0
+
+    def alloc(self, *shape):
+        n = int(math.prod(shape))
+        es = self.buf.element_size()
+        n_al = _rup(n * es, 256) // es
+        if self.off + n_al <= self.buf.numel():
+            t = self.buf[self.off:self.off + n]
+            self.off += n_al
+        else:
+            chunk = torch.zeros(n_al, dtype=self.dtype, device=self.buf.device)
+            self.extra.append(chunk)
+            t = chunk[:n]
+        self.high += n_al
+        return t.view(*shape)
+
+
+class _Saved:
+    pass
+
+
+class FastSpeech2(nn.Module):
+    """B200-native FastSpeech2 with speaker + emotion-intensity conditioning (reference model.py:30-441).
+
+    Extra keyword (not in the reference): `precision` = "bf16" (tcgen05 tensor-core GEMMs, bf16 operands,
+    fp32 accumulation / residual stream / LayerNorm statistics) or "fp32" (exact SIMT GEMMs).
+    """
+
+    def __init__(
+        self, enc_num_layers, enc_num_head, enc_d_model, enc_ffn_dim, enc_k_dim, enc_v_dim, enc_dropout,
+        dec_num_layers, dec_num_head, dec_d_model, dec_ffn_dim, dec_k_dim, dec_v_dim, dec_dropout,
+        normalize_before, ffn_type, ffn_cnn_kernel_size_list, n_char, n_mels, postnet_embedding_dim,
+        postnet_kernel_size, postnet_n_convolutions, postnet_dropout, padding_idx, dur_pred_kernel_size,
+        pitch_pred_kernel_size, energy_pred_kernel_size, variance_predictor_dropout, n_speakers,
+        precision="bf16",
+    ):
+        super().__init__()
+        if ffn_type != "1dcnn":
+            raise NotImplementedError("fs2_b200: only ffn_type='1dcnn' (the reference's parameter.yaml:78)")
+        if normalize_before:
+            raise NotImplementedError("fs2_b200: only normalize_before=False (the reference's parameter.yaml:77)")
+        if enc_d_model != dec_d_model:
+            raise ValueError("enc_d_model must equal dec_d_model (the length regulator feeds one into the other)")
+        if enc_k_dim != enc_d_model or enc_v_dim != enc_d_model or dec_k_dim != dec_d_model or dec_v_dim != dec_d_model:
+            raise NotImplementedError("fs2_b200: kdim/vdim must equal d_model (packed in_proj_weight, as the reference)")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        D = enc_d_model
+        self.D, self.n_mels, self.n_char, self.n_speakers = D, n_mels, n_char, n_speakers
+        self.padding_idx = padding_idx
+        self.precision = precision
+        self.enc = dict(name="encoder", nl=enc_num_layers, H=enc_num_head, F=enc_ffn_dim, p=float(enc_dropout))
+        self.dec = dict(name="decoder", nl=dec_num_layers, H=dec_num_head, F=dec_ffn_dim, p=float(dec_dropout))
+        self.k0, self.k1 = int(ffn_cnn_kernel_size_list[0]), int(ffn_cnn_kernel_size_list[1])
+        self.kd = int(dur_pred_kernel_size)          # all three predictors use it (model.py:211,217,223; quirk Q4)
+        self.kp, self.ke = int(pitch_pred_kernel_size), int(energy_pred_kernel_size)
+        self.var_p = float(variance_predictor_dropout)
+        self.E, self.kpn, self.npn, self.pn_p = postnet_embedding_dim, int(postnet_kernel_size), int(postnet_n_convolutions), float(postnet_dropout)
+        for k in (self.k0, self.k1, self.kd, self.kp, self.ke, self.kpn):
+            if k % 2 != 1 or k > 2 * PAD + 1:
+                raise ValueError("kernel sizes must be odd and <= 9")
+        if D % 8 or enc_ffn_dim % 8 or dec_ffn_dim % 8 or n_mels % 8 or self.E % 8 or D > 512 or self.E > 512:
+            raise ValueError("fs2_b200: channel sizes must be multiples of 8; d_model and postnet dim <= 512")
+        if D % enc_num_head or D % dec_num_head:
+            raise ValueError("d_model must be divisible by the number of heads")
+        if self.npn < 2:
+            raise ValueError("postnet_n_convolutions must be >= 2")
+
+        st = ParamStore(self)
+        self.store = st
+        st.add("speaker_emb.Embedding.weight", (n_speakers, D), ("normal",))
+        st.add("concat_proj.w.weight", (D, 2 * D + 5), ("kaiming_uniform", 2 * D + 5))
+        st.add_packed("concat_proj.w.weight", D, D, 1, src_ld=2 * D + 5, src_col0=0, name="concat_proj.tok")
+        st.add("encPreNet.token_embedding.Embedding.weight", (n_char, D), ("normal",))
+        for pred in ("durPred", "pitchPred", "energyPred"):
+            st.conv(f"{pred}.conv1.conv", D, D, self.kd)
+            st.conv(f"{pred}.conv2.conv", D, D, self.kd)
+            st.add(f"{pred}.linear.w.weight", (1, D), ("kaiming_uniform", D))
+            st.add(f"{pred}.linear.w.bias", (1,), ("uniform_fan", D))
+            st.layernorm(f"{pred}.ln1.norm", D)
+            st.layernorm(f"{pred}.ln2.norm", D)
+        st.conv("pitchEmbed.conv", D, 1, self.kp, pack=False)
+        st.conv("energyEmbed.conv", D, 1, self.ke, pack=False)
+        for cfg in (self.enc, self.dec):
+            for l in range(cfg["nl"]):
+                pre = f"{cfg['name']}.layers.{l}"
+                st.add(f"{pre}.self_att.att.in_proj_weight", (3 * D, D), ("xavier_uniform",))
+                st.add(f"{pre}.self_att.att.in_proj_bias", (3 * D,), ("zeros",))
+                st.add_packed(f"{pre}.self_att.att.in_proj_weight", 3 * D, D, 1)
+                st.add(f"{pre}.self_att.att.out_proj.weight", (D, D), ("kaiming_uniform", D))
+                st.add(f"{pre}.self_att.att.out_proj.bias", (D,), ("zeros",))
+                st.add_packed(f"{pre}.self_att.att.out_proj.weight", D, D, 1)
+                st.conv(f"{pre}.pos_ffn.0.conv", cfg["F"], D, self.k0)
+                st.conv(f"{pre}.pos_ffn.2.conv", D, cfg["F"], self.k1)
+                st.layernorm(f"{pre}.norm1.norm", D)
+                st.layernorm(f"{pre}.norm2.norm", D)
+            st.layernorm(f"{cfg['name']}.norm.norm", D)
+        st.linear("linear.w", n_mels, D)
+        st.conv("postnet.conv_pre.conv", self.E, n_mels, self.kpn)
+        for i in range(self.npn - 2):
+            st.conv(f"postnet.convs_intermedite.{i}.conv", self.E, self.E, self.kpn)
+        st.conv("postnet.conv_post.conv", n_mels, self.E, self.kpn)
+        st.layernorm("postnet.ln1", self.E)
+        st.layernorm("postnet.ln2", self.E)
+        st.layernorm("postnet.ln3", n_mels)
+        st.build()
+
+        # persistent sinusoid buffers, same keys as speechbrain PositionalEncoding (model.py:187-192)
+        pe = torch.zeros(2500, D)
+        pos = torch.arange(0, 2500).unsqueeze(1).float()
+        den = torch.exp(torch.arange(0, D, 2).float() * -(math.log(10000.0) / D))
+        pe[:, 0::2] = torch.sin(pos * den)
+        pe[:, 1::2] = torch.cos(pos * den)
+        for nm in ("sinusoidal_positional_embed_encoder", "sinusoidal_positional_embed_decoder"):
+            m = nn.Module()
+            m.register_buffer("pe", pe.unsqueeze(0).clone())
+            self.add_module(nm, m)
+
+        self._anchor = torch.zeros(1, requires_grad=True)   # lets autograd reach our backward; never a parameter
+        self._arenas = None
+        self._seed_base = 0x1234
+        self._generation = 0
+        self.trace = None        # set to a dict to collect unpadded intermediates (debug / parity tests)
+        self._pin_lens = None
+
+    # ------------------------------------------------------------------ nn.Module plumbing
+    def _apply(self, fn, *a, **kw):
+        super()._apply(fn, *a, **kw)
+        self.store.reflatten()
+        self._anchor = torch.zeros(1, device=self.store.flat.device, requires_grad=True)
+        return self
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        sd = dict(state_dict)
+        for i in (1, 2, 3):     # accept speechbrain-LayerNorm style keys for the PostNet norms
+            for leaf in ("weight", "bias"):
+                alt = f"postnet.ln{i}.norm.{leaf}"
+                if alt in sd:
+                    sd[f"postnet.ln{i}.{leaf}"] = sd.pop(alt)
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def manual_seed(self, seed):
+        """Seed of the counter-based dropout masks."""
+        self._seed_base = int(seed) & _M64
+
+    # --------------------------------------------------------------------------- helpers
+    @property
+    def _bf16(self):
+        return self.precision == "bf16"
+
+    def _P(self, key):
+        return self.store.params[key]
+
+    def _G(self, key):
+        return self.store.grad(key)
+
+    def _f32(self, *shape):
+        return self._arenas[0].alloc(*shape)
+
+    def _act(self, *shape):
+        return self._arenas[1].alloc(*shape)
+
+    def _i32(self, *shape):
+        return self._arenas[2].alloc(*shape)
+
+    def _tr(self, name, t, B, T, C):
+        if self.trace is not None:
+            self.trace[name] = t.view(B, T + 2 * PAD, C)[:, PAD:PAD + T].float().clone()
+
+    @staticmethod
+    def _site_seed(base, site):
+        return (base * 0x9E3779B97F4A7C15 + site * 0xD1B54A32D192ED03 + 0x2545F4914F6CDD1D) & _M64
+
+    def _conv(self, x, B, T, wname, out, *, c_bf16, bias=None, relu=0, lens=None, halo=0):
+        """y[r] = sum_j x[r + j - p] . W_j (+bias, ReLU, row mask, reflect-halo mirror): model.py Conv1d/Linear sites."""
+        w = self.store.pw(wname)
+        rows = B * (T + 2 * PAD)
+        p = (w.k - 1) // 2
+        L.gemm(mode=0, M=rows, N=w.cout, K=w.cin, taps=w.k, A=x, lda=w.cin, a_rows=rows, a_inner=w.cin,
+               a_row_off=-p, a_tap_step=1, B=self.store.packed_buf, B_off=w.off, ldb=w.k * w.cin, b_rows=w.cout,
+               b_inner=w.k * w.cin, b_tap_step=w.cin, Cout=out, ldc=w.cout, c_bf16=c_bf16, ab_bf16=self._bf16,
+               bias=bias, relu=relu, rs_T=T, rs_Tp=T + 2 * PAD, lens=lens, halo=halo)
+
+    def _conv_dgrad(self, dy, B, T, wname, out, *, c_bf16=False, relu_aux=None):
+        """dx[r] = sum_j dy[r + p - j] . W_j  (gradient wrt the padded input, halo rows included)."""
+        w = self.store.pw(wname)
+        rows = B * (T + 2 * PAD)
+        p = (w.k - 1) // 2
+        L.gemm(mode=1, M=rows, N=w.cin, K=w.cout, taps=w.k, A=dy, lda=w.cout, a_rows=rows, a_inner=w.cout,
+               a_row_off=p, a_tap_step=-1, B=self.store.packed_buf, B_off=w.off, ldb=w.k * w.cin, b_rows=w.cout,
+               b_inner=w.k * w.cin, b_tap_step=w.cin, Cout=out, ldc=w.cin, c_bf16=c_bf16, ab_bf16=self._bf16,
+               relu_aux=relu_aux, aux_bf16=int(self._bf16))
+
+    def _conv_wgrad(self, dy, x, B, T, wname, wkey, bkey=None):
+        """dW[co, ci, j] += sum_r dy[r, co] * x[r + j - p, ci];  db[co] += sum_r dy[r, co]."""
+        w = self.store.pw(wname)
+        rows = B * (T + 2 * PAD)
+        p = (w.k - 1) // 2
+        tiles = ((w.cin + 127) // 128) * w.k * ((w.cout + 127) // 128)
+        split = max(1, min((rows + 63) // 64, 1184 // max(tiles, 1)))
+        o, _ = self.store.offsets[wkey]
+        src_ld = w.src_ld
+        L.gemm(mode=2, M=w.cout, N=w.cin, K=rows, taps=w.k, A=dy, lda=w.cout, a_rows=rows, a_inner=w.cout,
+               B=x, ldb=w.cin, b_rows=rows, b_inner=w.cin, b_row_off=-p, b_tap_step=1,
+               Cout=self.store.flat_grad, C_off=o + w.src_col0, ldc=src_ld, c_tap_stride=1, c_col_stride=w.k,
+               c_bf16=False, ab_bf16=self._bf16, accumulate=1, split_k=split)
+        if bkey is not None:
+            L.call("fs2_colsum", dy, int(self._bf16), rows, w.cout, w.cout, self._G(bkey))
+
+    def _ln_fwd(self, B, T, C, x, gamma, beta, eps, *, branch=None, drop_b=(0.0, 0), tanh=0, drop_a=(0.0, 0),
+                lens=None, post_add=None, out_f32=None, out_act=None, halo=0, mean=None, rstd=None, head=None):
+        p = L.Fs2LnFwd()
+        p.B, p.T, p.C = B, T, C
+        p.x = x.data_ptr()
+        p.branch = branch.data_ptr() if branch is not None else None
+        p.drop_b_p, p.drop_b_seed = drop_b
+        p.gamma, p.beta, p.eps = gamma.data_ptr(), beta.data_ptr(), eps
+        p.tanh_act = tanh
+        p.drop_a_p, p.drop_a_seed = drop_a
+        p.lens = lens.data_ptr() if lens is not None else None
+        p.post_add = post_add.data_ptr() if post_add is not None else None
+        p.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+        p.out_act = out_act.data_ptr() if out_act is not None else None
+        p.act_bf16, p.halo = int(self._bf16), halo
+        p.mean = mean.data_ptr() if mean is not None else None
+        p.rstd = rstd.data_ptr() if rstd is not None else None
+        if head is not None:
+            hw, hb, hout, hs = head
+            p.head_w, p.head_b, p.head_out, p.head_scale = hw.data_ptr(), hb.data_ptr(), hout.data_ptr(), hs
+        L.call("fs2_ln_fwd", L.C.addressof(p))
+
+    def _ln_bwd(self, B, T, C, x, gamma, beta, eps, mean, rstd, *, dy=None, dy2=None, dy2_fold=0, dhead=None,
+                head_w=None, head_scale=1.0, branch=None, drop_b=(0.0, 0), tanh=0, drop_a=(0.0, 0), lens=None,
+                relu_x=0, dx_f32=None, dact=None, dgamma=None, dbeta=None, dhead_w=None, dhead_b=None):
+        p = L.Fs2LnBwd()
+        p.B, p.T, p.C = B, T, C
+        p.dy = dy.data_ptr() if dy is not None else None
+        p.dy2 = dy2.data_ptr() if dy2 is not None else None
+        p.dy2_fold = dy2_fold
+        p.dhead = dhead.data_ptr() if dhead is not None else None
+        p.head_w = head_w.data_ptr() if head_w is not None else None
+        p.head_scale = head_scale
+        p.x = x.data_ptr()
+        p.branch = branch.data_ptr() if branch is not None else None
+        p.drop_b_p, p.drop_b_seed = drop_b
+        p.gamma, p.beta, p.eps, p.tanh_act = gamma.data_ptr(), beta.data_ptr(), eps, tanh
+        p.drop_a_p, p.drop_a_seed = drop_a
+        p.lens = lens.data_ptr() if lens is not None else None
+        p.mean, p.rstd = mean.data_ptr(), rstd.data_ptr()
+        p.relu_x = relu_x
+        p.dx_f32 = dx_f32.data_ptr() if dx_f32 is not None else None
+        p.dact = dact.data_ptr() if dact is not None else None
+        p.act_bf16 = int(self._bf16)
+        p.dgamma = dgamma.data_ptr() if dgamma is not None else None
+        p.dbeta = dbeta.data_ptr() if dbeta is not None else None
+        p.dhead_w = dhead_w.data_ptr() if dhead_w is not None else None
+        p.dhead_b = dhead_b.data_ptr() if dhead_b is not None else None
+        L.call("fs2_ln_bwd", L.C.addressof(p))
+
+    # ------------------------------------------------------------------- FFT block stack
+    def _attn_gemms_fwd(self, qkv, B, T, H, S, lens, P, Pd, O, p_drop, seed):
+        D = self.D
+        hd = D // H
+        TP = T + 2 * PAD
+        ld = 3 * D
+        ldk = S.shape[-1]
+        bf = self._bf16
+        # S[b,h] = Q K^T
+        L.gemm(mode=0, M=T, N=T, K=hd, A=qkv, A_off=PAD * ld, lda=ld, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * ld,
+               B=qkv, B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
+               Cout=S, ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=bf)
+        L.call("fs2_softmax_fwd", S, lens, B, H, T, ldk, 1.0 / math.sqrt(hd), p_drop, seed, P,
+               Pd if p_drop > 0 else None, int(bf))
+        # O[b,:,h] = Pd V
+        L.gemm(mode=1, M=T, N=hd, K=T, A=Pd, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
+               B=qkv, B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
+               Cout=O, C_off=PAD * D, ldc=D, c_s1=hd, c_s2=TP * D, c_bf16=bf, ab_bf16=bf)
+
+    def _stack_fwd(self, cfg, x_f32, x_act, B, T, lens, final_lens, final_halo, base_seed, site0, training):
+        D, F, H, nl = self.D, cfg["F"], cfg["H"], cfg["nl"]
+        name = cfg["name"]
+        rows = B * (T + 2 * PAD)
+        ldk = _rup(T, 8)
+        bf = self._bf16
+        p = cfg["p"] if training else 0.0
+        S = self._f32(B * H, T, ldk)          # scratch, shared by all layers of this stack
+        saves = []
+        h1, h2 = (self.k0 - 1) // 2, (self.k1 - 1) // 2
+        for l in range(nl):
+            pre = f"{name}.layers.{l}"
+            sv = _Saved()
+            sv.x_f32, sv.x_act = x_f32, x_act
+            sv.seeds = [self._site_seed(base_seed, site0 + 3 * l + i) for i in range(3)]
+            sv.qkv = self._act(rows, 3 * D)
+            self._conv(x_act, B, T, f"{pre}.self_att.att.in_proj_weight", sv.qkv, c_bf16=bf,
+                       bias=self._P(f"{pre}.self_att.att.in_proj_bias"))
+            sv.P = self._act(B * H, T, ldk)
+            sv.Pd = self._act(B * H, T, ldk) if p > 0 else sv.P
+            sv.O = self._act(rows, D)
+            self._attn_gemms_fwd(sv.qkv, B, T, H, S, lens, sv.P, sv.Pd, sv.O, p, sv.seeds[0])
+            sv.proj = self._f32(rows, D)
+            self._conv(sv.O, B, T, f"{pre}.self_att.att.out_proj.weight", sv.proj, c_bf16=False,
+                       bias=self._P(f"{pre}.self_att.att.out_proj.bias"))
+            sv.x1_f32, sv.x1_act = self._f32(rows, D), self._act(rows, D)
+            sv.mean1, sv.rstd1 = self._f32(rows), self._f32(rows)
+            self._ln_fwd(B, T, D, x_f32, self._P(f"{pre}.norm1.norm.weight"), self._P(f"{pre}.norm1.norm.bias"), 1e-6,
+                         branch=sv.proj, drop_b=(p, sv.seeds[1]), out_f32=sv.x1_f32, out_act=sv.x1_act, halo=h1,
+                         mean=sv.mean1, rstd=sv.rstd1)
+            sv.Hh = self._act(rows, F)
+            self._conv(sv.x1_act, B, T, f"{pre}.pos_ffn.0.conv.weight", sv.Hh, c_bf16=bf,
+                       bias=self._P(f"{pre}.pos_ffn.0.conv.bias"), relu=1, halo=h2)
+            sv.Fo = self._f32(rows, D)
+            self._conv(sv.Hh, B, T, f"{pre}.pos_ffn.2.conv.weight", sv.Fo, c_bf16=False,
+                       bias=self._P(f"{pre}.pos_ffn.2.conv.bias"))
+            y_f32, y_act = self._f32(rows, D), self._act(rows, D)
+            sv.mean2, sv.rstd2 = self._f32(rows), self._f32(rows)
+            self._ln_fwd(B, T, D, sv.x1_f32, self._P(f"{pre}.norm2.norm.weight"), self._P(f"{pre}.norm2.norm.bias"), 1e-6,
+                         branch=sv.Fo, drop_b=(p, sv.seeds[2]), out_f32=y_f32, out_act=y_act, mean=sv.mean2,
+                         rstd=sv.rstd2)
+            saves.append(sv)
+            x_f32, x_act = y_f32, y_act
+            self._tr(f"{name}.layer{l}", y_f32, B, T, D)
+        fin = _Saved()
+        fin.x_f32 = x_f32
+        fin.mean, fin.rstd = self._f32(rows), self._f32(rows)
+        out_f32, out_act = self._f32(rows, D), self._act(rows, D)
+        self._ln_fwd(B, T, D, x_f32, self._P(f"{name}.norm.norm.weight"), self._P(f"{name}.norm.norm.bias"), 1e-6,
+                     lens=final_lens, out_f32=out_f32, out_act=out_act, halo=final_halo, mean=fin.mean, rstd=fin.rstd)
+        fin.p = p
+        return out_f32, out_act, saves, fin
+
+    def _stack_bwd(self, cfg, saves, fin, dout, dout2, B, T, lens, final_lens):
+        """dout (+dout2): fp32 padded-row gradient wrt the stack output.  Returns (dx_a, dx_b): the gradient wrt
+        the stack input is their sum."""
+        D, F, H, nl = self.D, cfg["F"], cfg["H"], cfg["nl"]
+        name = cfg["name"]
+        hd = D // H
+        rows = B * (T + 2 * PAD)
+        TP = T + 2 * PAD
+        ldk = _rup(T, 8)
+        bf = self._bf16
+        p = fin.p
+        ld = 3 * D
+        h1, h2 = (self.k0 - 1) // 2, (self.k1 - 1) // 2
+        scale = 1.0 / math.sqrt(hd)
+        # scratch shared by all layers
+        dPd = self._f32(B * H, T, ldk)
+        dS = self._act(B * H, T, ldk)
+        dqkv = self._act(rows, ld)
+        dF_act, dH_act = self._act(rows, D), self._act(rows, F)
+        dHc = self._f32(rows, F) if h2 > 0 else None
+        dX1c, dz2, dz1, dXa = self._f32(rows, D), self._f32(rows, D), self._f32(rows, D), self._f32(rows, D)
+        dProj_act, dO_act = self._act(rows, D), self._act(rows, D)
+        dy_a, dy_b = self._f32(rows, D), None
+        self._ln_bwd(B, T, D, fin.x_f32, self._P(f"{name}.norm.norm.weight"), self._P(f"{name}.norm.norm.bias"), 1e-6,
+                     fin.mean, fin.rstd, dy=dout, dy2=dout2, lens=final_lens, dx_f32=dy_a,
+                     dgamma=self._G(f"{name}.norm.norm.weight"), dbeta=self._G(f"{name}.norm.norm.bias"))
+        for l in reversed(range(nl)):
+            pre = f"{name}.layers.{l}"
+            sv = saves[l]
+            # ---- LN2 + FFN
+            self._ln_bwd(B, T, D, sv.x1_f32, self._P(f"{pre}.norm2.norm.weight"), self._P(f"{pre}.norm2.norm.bias"), 1e-6,
+                         sv.mean2, sv.rstd2, dy=dy_a, dy2=dy_b, branch=sv.Fo, drop_b=(p, sv.seeds[2]),
+                         dx_f32=dz2, dact=dF_act, dgamma=self._G(f"{pre}.norm2.norm.weight"),
+                         dbeta=self._G(f"{pre}.norm2.norm.bias"))
+            self._conv_wgrad(dF_act, sv.Hh, B, T, f"{pre}.pos_ffn.2.conv.weight", f"{pre}.pos_ffn.2.conv.weight",
+                             f"{pre}.pos_ffn.2.conv.bias")
+            if h2 == 0:
+                self._conv_dgrad(dF_act, B, T, f"{pre}.pos_ffn.2.conv.weight", dH_act, c_bf16=bf, relu_aux=sv.Hh)
+            else:
+                self._conv_dgrad(dF_act, B, T, f"{pre}.pos_ffn.2.conv.weight", dHc)
+                raise NotImplementedError("fs2_b200: second FFN conv with kernel > 1 is not supported in backward")
+            self._conv_wgrad(dH_act, sv.x1_act, B, T, f"{pre}.pos_ffn.0.conv.weight", f"{pre}.pos_ffn.0.conv.weight",
+                             f"{pre}.pos_ffn.0.conv.bias")
+            self._conv_dgrad(dH_act, B, T, f"{pre}.pos_ffn.0.conv.weight", dX1c)
+            # ---- LN1 + attention
+            self._ln_bwd(B, T, D, sv.x_f32, self._P(f"{pre}.norm1.norm.weight"), self._P(f"{pre}.norm1.norm.bias"), 1e-6,
+                         sv.mean1, sv.rstd1, dy=dz2, dy2=dX1c, dy2_fold=h1, branch=sv.proj, drop_b=(p, sv.seeds[1]),
+                         dx_f32=dz1, dact=dProj_act, dgamma=self._G(f"{pre}.norm1.norm.weight"),
+                         dbeta=self._G(f"{pre}.norm1.norm.bias"))
+            self._conv_wgrad(dProj_act, sv.O, B, T, f"{pre}.self_att.att.out_proj.weight",
+                             f"{pre}.self_att.att.out_proj.weight", f"{pre}.self_att.att.out_proj.bias")
+            self._conv_dgrad(dProj_act, B, T, f"{pre}.self_att.att.out_proj.weight", dO_act, c_bf16=bf)
+            # dPd = dO V^T
+            L.gemm(mode=0, M=T, N=T, K=hd, A=dO_act, A_off=PAD * D, lda=D, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * D,
+                   B=sv.qkv, B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld,
+                   batch1=H, batch2=B, Cout=dPd, ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=bf)
+            # dV = Pd^T dO
+            L.gemm(mode=2, M=T, N=hd, K=T, A=sv.Pd, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
+                   B=dO_act, B_off=PAD * D, ldb=D, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * D, batch1=H, batch2=B,
+                   Cout=dqkv, C_off=PAD * ld + 2 * D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
+            L.call("fs2_softmax_bwd", sv.P, dPd, lens, B, H, T, ldk, scale, p, sv.seeds[0], dS, int(bf))
+            # dQ = dS K ; dK = dS^T Q
+            L.gemm(mode=1, M=T, N=hd, K=T, A=dS, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
+                   B=sv.qkv, B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
+                   Cout=dqkv, C_off=PAD * ld, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
+            L.gemm(mode=2, M=T, N=hd, K=T, A=dS, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
+                   B=sv.qkv, B_off=PAD * ld, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
+                   Cout=dqkv, C_off=PAD * ld + D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
+            self._conv_wgrad(dqkv, sv.x_act, B, T, f"{pre}.self_att.att.in_proj_weight",
+                             f"{pre}.self_att.att.in_proj_weight", f"{pre}.self_att.att.in_proj_bias")
+            self._conv_dgrad(dqkv, B, T, f"{pre}.self_att.att.in_proj_weight", dXa)
+            # gradient wrt this layer's input = dz1 + dXa ; ping-pong the buffers
+            dy_a, dz1 = dz1, dy_a
+            if dy_b is None:
+                dy_b = self._f32(rows, D)
+            dy_b, dXa = dXa, dy_b
+        return dy_a, dy_b
+
+    # ---------------------------------------------------------------- variance predictor
+    def _pred_fwd(self, pname, x_act, B, T, lens, scale, base_seed, site, training):
+        D = self.D
+        rows = B * (T + 2 * PAD)
+        h = (self.kd - 1) // 2
+        p = self.var_p if training else 0.0
+        sv = _Saved()
+        sv.x_act = x_act
+        sv.p = p
+        sv.scale = float(scale)
+        sv.seeds = [self._site_seed(base_seed, site), self._site_seed(base_seed, site + 1)]
+        sv.h1 = self._f32(rows, D)
+        self._conv(x_act, B, T, f"{pname}.conv1.conv.weight", sv.h1, c_bf16=False,
+                   bias=self._P(f"{pname}.conv1.conv.bias"), relu=1)
+        sv.a1 = self._act(rows, D)
+        sv.mean1, sv.rstd1 = self._f32(rows), self._f32(rows)
+        self._ln_fwd(B, T, D, sv.h1, self._P(f"{pname}.ln1.norm.weight"), self._P(f"{pname}.ln1.norm.bias"), 1e-5,
+                     drop_a=(p, sv.seeds[0]), lens=lens, out_act=sv.a1, halo=h, mean=sv.mean1, rstd=sv.rstd1)
+        sv.h2 = self._f32(rows, D)
+        self._conv(sv.a1, B, T, f"{pname}.conv2.conv.weight", sv.h2, c_bf16=False,
+                   bias=self._P(f"{pname}.conv2.conv.bias"), relu=1)
+        sv.mean2, sv.rstd2 = self._f32(rows), self._f32(rows)
+        out = torch.empty(B, T, device=x_act.device, dtype=torch.float32)
+        self._ln_fwd(B, T, D, sv.h2, self._P(f"{pname}.ln2.norm.weight"), self._P(f"{pname}.ln2.norm.bias"), 1e-5,
+                     drop_a=(p, sv.seeds[1]), lens=lens, mean=sv.mean2, rstd=sv.rstd2,
+                     head=(self._P(f"{pname}.linear.w.weight"), self._P(f"{pname}.linear.w.bias"), out, sv.scale))
+        return out, sv
+
+    def _pred_bwd(self, pname, sv, dpred, B, T, lens, dx_out):
+        """dpred (B,T) plain -> dx_out (fp32 padded rows incl. halo, to be folded with width kd//2 and masked)."""
+        D = self.D
+        rows = B * (T + 2 * PAD)
+        h = (self.kd - 1) // 2
+        p = sv.p
+        d2_act, d1_act = self._act(rows, D), self._act(rows, D)
+        dA1c = self._f32(rows, D)
+        self._ln_bwd(B, T, D, sv.h2, self._P(f"{pname}.ln2.norm.weight"), self._P(f"{pname}.ln2.norm.bias"), 1e-5,
+                     sv.mean2, sv.rstd2, dhead=dpred, head_w=self._P(f"{pname}.linear.w.weight"), head_scale=sv.scale,
+                     drop_a=(p, sv.seeds[1]), lens=lens, relu_x=1, dact=d2_act,
+                     dgamma=self._G(f"{pname}.ln2.norm.weight"), dbeta=self._G(f"{pname}.ln2.norm.bias"),
+                     dhead_w=self._G(f"{pname}.linear.w.weight"), dhead_b=self._G(f"{pname}.linear.w.bias"))
+        self._conv_wgrad(d2_act, sv.a1, B, T, f"{pname}.conv2.conv.weight", f"{pname}.conv2.conv.weight",
+                         f"{pname}.conv2.conv.bias")
+        self._conv_dgrad(d2_act, B, T, f"{pname}.conv2.conv.weight", dA1c)
+        self._ln_bwd(B, T, D, sv.h1, self._P(f"{pname}.ln1.norm.weight"), self._P(f"{pname}.ln1.norm.bias"), 1e-5,
+                     sv.mean1, sv.rstd1, dy2=dA1c, dy2_fold=h, drop_a=(p, sv.seeds[0]), lens=lens, relu_x=1,
+                     dact=d1_act, dgamma=self._G(f"{pname}.ln1.norm.weight"), dbeta=self._G(f"{pname}.ln1.norm.bias"))
+        self._conv_wgrad(d1_act, sv.x_act, B, T, f"{pname}.conv1.conv.weight", f"{pname}.conv1.conv.weight",
+                         f"{pname}.conv1.conv.bias")
+        self._conv_dgrad(d1_act, B, T, f"{pname}.conv1.conv.weight", dx_out)
+
+    # --------------------------------------------------------------------------- forward
+    def forward(self, tokens, speakers, durations=None, pitch=None, energy=None, pace=1.0, pitch_rate=1.0,
+                energy_rate=1.0, intensity=None):
+        """Same contract as reference model.py:279-441.  Returns (mel_post, postnet_output, predict_durations,
+        predict_pitch, avg_pitch, predict_energy, avg_energy, mel_lens[CPU int64])."""
+        if intensity is None:
+            raise ValueError("intensity (B, Tp, 5) is required (reference model.py:356-358 concatenates it)")
+        outs = _FS2Function.apply(self._anchor, self, tokens, speakers, durations, pitch, energy, float(pace),
+                                  float(pitch_rate), float(energy_rate), intensity)
+        mel, post, pd, pp, ap, pe, ae = outs
+        has_p, has_e = pitch is not None, energy is not None
+        return (mel, post, pd, pp, ap if has_p else None, pe, ae if has_e else None, self._last_mel_lens_cpu)
+
+    def _forward_impl(self, tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate, intensity):
+        st = self.store
+        if not tokens.is_cuda:
+            raise RuntimeError("fs2_b200: inputs must be CUDA tensors (there is no CPU fallback)")
+        dev = tokens.device
+        if st.flat.device != dev:
+            raise RuntimeError("fs2_b200: model and inputs are on different devices")
+        if not st.views_intact():
+            st.reflatten()
+        if self._arenas is None:
+            self._arenas = (Arena(torch.float32), Arena(torch.bfloat16 if self._bf16 else torch.float32), Arena(torch.int32))
+        for a in self._arenas:
+            a.reset(dev)
+        self._generation += 1
+        training = self.training
+        bf = self._bf16
+        D, n_mels = self.D, self.n_mels
+        st.pack(bf)
+        tokens = tokens.contiguous().long()
+        speakers = speakers.contiguous().long()
+        intensity = intensity.contiguous().float()
+        B, Tp = tokens.shape
+        if Tp <= PAD:
+            raise ValueError("fs2_b200: need more than 4 phoneme positions (reflect padding of the k=9 conv, as torch)")
+        rowsP = B * (Tp + 2 * PAD)
+        base_seed = (self._seed_base + 0x632BE59BD9B4E019 * self._generation) & _M64
+        ctx = _Saved()
+        ctx.generation = self._generation
+        ctx.B, ctx.Tp = B, Tp
+        ctx.tokens, ctx.speakers, ctx.intensity = tokens, speakers, intensity
+        ctx.teacher = durations is not None
+        pe_enc = self.sinusoidal_positional_embed_encoder.pe
+        pe_dec = self.sinusoidal_positional_embed_decoder.pe
+
+        # ---- LengthRegulator scan first (teacher-forced): its only host read-back overlaps the encoder
+        ends = self._i32(B, Tp)
+        mel_lens = self._i32(B)
+        ctx.ends, ctx.mel_lens = ends, mel_lens
+        if self._pin_lens is None or self._pin_lens.numel() < B:
+            self._pin_lens = torch.empty(max(B, 64), dtype=torch.int32).pin_memory()
+        ev = None
+        if durations is not None:
+            durations = durations.contiguous().long()
+            L.call("fs2_lr_prepare", durations, None, pace, B, Tp, ends, mel_lens)
+            self._pin_lens[:B].copy_(mel_lens, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+
+        # ---- encoder (model.py:331-347)
+        src_lens = self._i32(B)
+        ctx.src_lens = src_lens
+        x_f32, x_act = self._f32(rowsP, D), self._act(rowsP, D)
+        L.call("fs2_embed_posenc", tokens, self._P("encPreNet.token_embedding.Embedding.weight"), pe_enc, B, Tp, D,
+               self.padding_idx, x_f32, x_act, int(bf), src_lens)
+        self._tr("enc_in", x_f32, B, Tp, D)
+        enc_f32, enc_act, ctx.enc_saves, ctx.enc_fin = self._stack_fwd(
+            self.enc, x_f32, x_act, B, Tp, src_lens, src_lens, 0, base_seed, 100, training)
+        ctx.enc_act = enc_act
+        self._tr("enc_out", enc_f32, B, Tp, D)
+
+        # ---- speaker + intensity conditioning (model.py:352-360)
+        hv = (self.kd - 1) // 2
+        G = self._f32(rowsP, D)
+        self._conv(enc_act, B, Tp, "concat_proj.tok", G, c_bf16=False)
+        c_f32, c_act = self._f32(rowsP, D), self._act(rowsP, D)
+        L.call("fs2_cond_finish", G, self._P("concat_proj.w.weight"), self._P("speaker_emb.Embedding.weight"), speakers,
+               intensity, src_lens, B, Tp, D, self._f32(B, D), c_f32, c_act, int(bf), hv)
+        self._tr("cond", c_f32, B, Tp, D)
+
+        # ---- variance adaptor (model.py:365-403)
+        pred_dur, ctx.sv_dur = self._pred_fwd("durPred", c_act, B, Tp, src_lens, 1.0, base_seed, 10, training)
+        pred_pitch, ctx.sv_pitch = self._pred_fwd("pitchPred", c_act, B, Tp, src_lens, pitch_rate, base_seed, 12, training)
+        avg_pitch = torch.zeros(B, Tp, device=dev, dtype=torch.float32)
+        if pitch is not None:
+            if durations is None:
+                raise ValueError("pitch targets need durations (average_over_durations, model.py:383)")
+            pitch = pitch.contiguous().float()
+            L.call("fs2_avg_over_durations", pitch, durations, B, Tp, pitch.shape[1], avg_pitch, None, None, None)
+            contour_p = avg_pitch
+        else:
+            contour_p = pred_pitch
+        ctx.contour_p = contour_p
+        ap_f32, ap_act = self._f32(rowsP, D), self._act(rowsP, D)
+        L.call("fs2_embed_add", c_f32, contour_p, self._P("pitchEmbed.conv.weight"), self._P("pitchEmbed.conv.bias"),
+               self.kp, src_lens, B, Tp, D, ap_f32, ap_act, int(bf), hv)
+        self._tr("after_pitch", ap_f32, B, Tp, D)
+        pred_energy, ctx.sv_energy = self._pred_fwd("energyPred", ap_act, B, Tp, src_lens, energy_rate, base_seed, 14, training)
+        avg_energy = torch.zeros(B, Tp, device=dev, dtype=torch.float32)
+        if energy is not None:
+            if durations is None:
+                raise ValueError("energy targets need durations (average_over_durations, model.py:397)")
+            energy = energy.contiguous().float()
+            L.call("fs2_avg_over_durations", energy, durations, B, Tp, energy.shape[1], avg_energy, None, None, None)
+            contour_e = avg_energy
+        else:
+            contour_e = pred_energy
+        ctx.contour_e = contour_e
+        ae_f32 = self._f32(rowsP, D)
+        L.call("fs2_embed_add", ap_f32, contour_e, self._P("energyEmbed.conv.weight"), self._P("energyEmbed.conv.bias"),
+               self.ke, src_lens, B, Tp, D, ae_f32, None, int(bf), 0)
+        self._tr("after_energy", ae_f32, B, Tp, D)
+
+        # ---- LengthRegulator (model.py:406-423)
+        if durations is None:
+            fdur = self._f32(B, Tp)
+            L.call("fs2_dur_decode", pred_dur, B * Tp, fdur)
+            L.call("fs2_lr_prepare", None, fdur, pace, B, Tp, ends, mel_lens)
+            self._pin_lens[:B].copy_(mel_lens, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        ev.synchronize()
+        mel_lens_cpu = self._pin_lens[:B].to(torch.int64).clone()
+        Tm = int(mel_lens_cpu.max())
+        if Tm > 2500:
+            raise ValueError("fs2_b200: more than 2500 frames (the positional table of the reference ends there)")
+        if Tm <= PAD:
+            raise ValueError("fs2_b200: need more than 4 mel frames (reflect padding of the k=9 conv, as torch)")
+        ctx.Tm = Tm
+        self._last_mel_lens_cpu = mel_lens_cpu
+        rowsM = B * (Tm + 2 * PAD)
+        d0_f32, d0_act = self._f32(rowsM, D), self._act(rowsM, D)
+        L.call("fs2_lr_expand", ae_f32, Tp + 2 * PAD, PAD, ends, mel_lens, pe_dec, B, Tp, Tm, D, d0_f32, d0_act, int(bf),
+               Tm + 2 * PAD, PAD, None)
+        self._tr("dec_in", d0_f32, B, Tm, D)
+
+        # ---- decoder + mel projection + PostNet (model.py:425-431)
+        dec_f32, dec_act, ctx.dec_saves, ctx.dec_fin = self._stack_fwd(
+            self.dec, d0_f32, d0_act, B, Tm, mel_lens, None, 0, base_seed, 200, training)
+        ctx.dec_act = dec_act
+        self._tr("dec_out", dec_f32, B, Tm, D)
+        hp = (self.kpn - 1) // 2
+        mel_raw = self._f32(rowsM, n_mels)
+        self._conv(dec_act, B, Tm, "linear.w.weight", mel_raw, c_bf16=False, bias=self._P("linear.w.bias"))
+        mel_post = torch.empty(B, Tm, n_mels, device=dev, dtype=torch.float32)
+        mel_f32, mel_act = self._f32(rowsM, n_mels), self._act(rowsM, n_mels)
+        L.call("fs2_unpad_mask", mel_raw, mel_lens, B, Tm, n_mels, mel_post, mel_act, int(bf), hp)
+        L.call("fs2_pad_rows", mel_post, None, B, Tm, n_mels, 1.0, mel_f32, None, int(bf))
+        ctx.mel_act = mel_act
+        pn = _Saved()
+        ctx.pn = pn
+        pn.p = self.pn_p if training else 0.0
+        pn.seeds = [self._site_seed(base_seed, 20 + i) for i in range(3)]
+        E = self.E
+        pn.c1 = self._f32(rowsM, E)
+        self._conv(mel_act, B, Tm, "postnet.conv_pre.conv.weight", pn.c1, c_bf16=False, bias=self._P("postnet.conv_pre.conv.bias"))
+        pn.a1 = self._act(rowsM, E)
+        pn.mean1, pn.rstd1 = self._f32(rowsM), self._f32(rowsM)
+        self._ln_fwd(B, Tm, E, pn.c1, self._P("postnet.ln1.weight"), self._P("postnet.ln1.bias"), 1e-5, tanh=1,
+                     drop_a=(pn.p, pn.seeds[0]), out_act=pn.a1, halo=hp, mean=pn.mean1, rstd=pn.rstd1)
+        pn.mid = [pn.a1]
+        cur = pn.a1
+        n_mid = self.npn - 2
+        pn.c_last = None
+        for i in range(n_mid):
+            last = i == n_mid - 1
+            wname = f"postnet.convs_intermedite.{i}.conv"
+            if last:
+                pn.c_last = self._f32(rowsM, E)
+                self._conv(cur, B, Tm, wname + ".weight", pn.c_last, c_bf16=False, bias=self._P(wname + ".bias"))
+            else:
+                nxt = self._act(rowsM, E)
+                self._conv(cur, B, Tm, wname + ".weight", nxt, c_bf16=bf, bias=self._P(wname + ".bias"), halo=hp)
+                pn.mid.append(nxt)
+                cur = nxt
+        if n_mid == 0:
+            raise NotImplementedError("fs2_b200: postnet_n_convolutions must be >= 3")
+        pn.a2 = self._act(rowsM, E)
+        pn.mean2, pn.rstd2 = self._f32(rowsM), self._f32(rowsM)
+        self._ln_fwd(B, Tm, E, pn.c_last, self._P("postnet.ln2.weight"), self._P("postnet.ln2.bias"), 1e-5, tanh=1,
+                     drop_a=(pn.p, pn.seeds[1]), out_act=pn.a2, halo=hp, mean=pn.mean2, rstd=pn.rstd2)
+        pn.c5 = self._f32(rowsM, n_mels)
+        self._conv(pn.a2, B, Tm, "postnet.conv_post.conv.weight", pn.c5, c_bf16=False, bias=self._P("postnet.conv_post.conv.bias"))
+        pn.mean3, pn.rstd3 = self._f32(rowsM), self._f32(rowsM)
+        post_pad = self._f32(rowsM, n_mels)
+        self._ln_fwd(B, Tm, n_mels, pn.c5, self._P("postnet.ln3.weight"), self._P("postnet.ln3.bias"), 1e-5,
+                     drop_a=(pn.p, pn.seeds[2]), post_add=mel_f32, out_f32=post_pad, mean=pn.mean3, rstd=pn.rstd3)
+        postnet_out = torch.empty(B, Tm, n_mels, device=dev, dtype=torch.float32)
+        L.call("fs2_unpad_mask", post_pad, None, B, Tm, n_mels, postnet_out, None, int(bf), 0)
+        ctx.pitch_rate, ctx.energy_rate = pitch_rate, energy_rate
+        ctx.has_targets = (pitch is not None) and (energy is not None)
+        outs = (mel_post, postnet_out, pred_dur, pred_pitch.unsqueeze(-1), avg_pitch.unsqueeze(-1),
+                pred_energy.unsqueeze(-1), avg_energy.unsqueeze(-1))
+        return outs, ctx
+
+    # -------------------------------------------------------------------------- backward
+    def _backward_impl(self, ctx, dmel, dpost, dpd, dpp, dpe):
+        if ctx.generation != self._generation:
+            raise RuntimeError("fs2_b200: backward() of a forward whose workspace has been reused by a later forward; "
+                               "call backward before the next forward of the same model")
+        if not (ctx.teacher and ctx.has_targets):
+            raise NotImplementedError("fs2_b200: backward needs teacher-forced durations, pitch and energy "
+                                      "(the reference's training call, train.py:72)")
+        st = self.store
+        st.ensure_grads()
+        bf = self._bf16
+        D, n_mels, E = self.D, self.n_mels, self.E
+        B, Tp, Tm = ctx.B, ctx.Tp, ctx.Tm
+        rowsP, rowsM = B * (Tp + 2 * PAD), B * (Tm + 2 * PAD)
+        hp = (self.kpn - 1) // 2
+        hv = (self.kd - 1) // 2
+        pn = ctx.pn
+        dev = dmel.device
+        dmel = dmel.contiguous().float()
+        dpost = dpost.contiguous().float()
+
+        # ---- PostNet (postnet_output = LN3-drop(conv_post(...)) + mel_post)
+        dpost_pad = self._f32(rowsM, n_mels)
+        L.call("fs2_pad_rows", dpost, None, B, Tm, n_mels, 1.0, dpost_pad, None, int(bf))
+        d5_act = self._act(rowsM, n_mels)
+        self._ln_bwd(B, Tm, n_mels, pn.c5, self._P("postnet.ln3.weight"), self._P("postnet.ln3.bias"), 1e-5, pn.mean3,
+                     pn.rstd3, dy=dpost_pad, drop_a=(pn.p, pn.seeds[2]), dact=d5_act,
+                     dgamma=self._G("postnet.ln3.weight"), dbeta=self._G("postnet.ln3.bias"))
+        self._conv_wgrad(d5_act, pn.a2, B, Tm, "postnet.conv_post.conv.weight", "postnet.conv_post.conv.weight",
+                         "postnet.conv_post.conv.bias")
+        dE_c = self._f32(rowsM, E)
+        self._conv_dgrad(d5_act, B, Tm, "postnet.conv_post.conv.weight", dE_c)
+        dE_act = self._act(rowsM, E)
+        self._ln_bwd(B, Tm, E, pn.c_last, self._P("postnet.ln2.weight"), self._P("postnet.ln2.bias"), 1e-5, pn.mean2,
+                     pn.rstd2, dy2=dE_c, dy2_fold=hp, tanh=1, drop_a=(pn.p, pn.seeds[1]), dact=dE_act,
+                     dgamma=self._G("postnet.ln2.weight"), dbeta=self._G("postnet.ln2.bias"))
+        n_mid = self.npn - 2
+        for i in reversed(range(n_mid)):
+            wname = f"postnet.convs_intermedite.{i}.conv"
+            self._conv_wgrad(dE_act, pn.mid[i], B, Tm, wname + ".weight", wname + ".weight", wname + ".bias")
+            self._conv_dgrad(dE_act, B, Tm, wname + ".weight", dE_c)
+            if i > 0:
+                L.call("fs2_fold_halo", dE_c, B, Tm, E, hp, None, None, None, None, dE_act, int(bf))
+        d1_act = self._act(rowsM, E)
+        self._ln_bwd(B, Tm, E, pn.c1, self._P("postnet.ln1.weight"), self._P("postnet.ln1.bias"), 1e-5, pn.mean1,
+                     pn.rstd1, dy2=dE_c, dy2_fold=hp, tanh=1, drop_a=(pn.p, pn.seeds[0]), dact=d1_act,
+                     dgamma=self._G("postnet.ln1.weight"), dbeta=self._G("postnet.ln1.bias"))
+        self._conv_wgrad(d1_act, ctx.mel_act, B, Tm, "postnet.conv_pre.conv.weight", "postnet.conv_pre.conv.weight",
+                         "postnet.conv_pre.conv.bias")
+        dmel_c = self._f32(rowsM, n_mels)
+        self._conv_dgrad(d1_act, B, Tm, "postnet.conv_pre.conv.weight", dmel_c)
+        # total gradient wrt mel_post (= linear(dec) * mask): conv_pre path + direct + postnet residual, masked
+        dmel_pad = self._f32(rowsM, n_mels)
+        L.call("fs2_pad_rows", dmel, dpost, B, Tm, n_mels, 1.0, dmel_pad, None, int(bf))
+        dmelm_act = self._act(rowsM, n_mels)
+        L.call("fs2_fold_halo", dmel_c, B, Tm, n_mels, hp, dmel_pad, None, ctx.mel_lens, None, dmelm_act, int(bf))
+        self._conv_wgrad(dmelm_act, ctx.dec_act, B, Tm, "linear.w.weight", "linear.w.weight", "linear.w.bias")
+        ddec = self._f32(rowsM, D)
+        self._conv_dgrad(dmelm_act, B, Tm, "linear.w.weight", ddec)
+
+        # ---- decoder
+        da, db_ = self._stack_bwd(self.dec, ctx.dec_saves, ctx.dec_fin, ddec, None, B, Tm, ctx.mel_lens, None)
+        # ---- LengthRegulator: segment sums (rows f >= mel_len are never inside a segment -> mask is implicit)
+        dAE = self._f32(rowsP, D)
+        L.call("fs2_lr_bwd", da, db_, Tm + 2 * PAD, PAD, ctx.ends, ctx.mel_lens, B, Tp, Tm, D, dAE, Tp + 2 * PAD, PAD)
+        # ---- energy embed + predictor
+        L.call("fs2_embed_add_bwd", dAE, ctx.contour_e, self.ke, B, Tp, D, self._G("energyEmbed.conv.weight"),
+               self._G("energyEmbed.conv.bias"))
+        dxe = self._f32(rowsP, D)
+        self._pred_bwd("energyPred", ctx.sv_energy, dpe.contiguous().float().view(B, Tp), B, Tp, ctx.src_lens, dxe)
+        dAP = self._f32(rowsP, D)
+        L.call("fs2_fold_halo", dxe, B, Tp, D, hv, None, None, ctx.src_lens, dAP, None, int(bf))
+        L.call("fs2_add_", dAP, dAE, rowsP * D)
+        # ---- pitch embed + pitch / duration predictors
+        L.call("fs2_embed_add_bwd", dAP, ctx.contour_p, self.kp, B, Tp, D, self._G("pitchEmbed.conv.weight"),
+               self._G("pitchEmbed.conv.bias"))
+        dxp, dxd = self._f32(rowsP, D), self._f32(rowsP, D)
+        self._pred_bwd("pitchPred", ctx.sv_pitch, dpp.contiguous().float().view(B, Tp), B, Tp, ctx.src_lens, dxp)
+        self._pred_bwd("durPred", ctx.sv_dur, dpd.contiguous().float().view(B, Tp), B, Tp, ctx.src_lens, dxd)
+        L.call("fs2_add_", dxp, dxd, rowsP * D)
+        # dC = (dAP + fold(dxp + dxd)) * mask   (conditioning output is masked, model.py:360)
+        dC_f32, dC_act = self._f32(rowsP, D), self._act(rowsP, D)
+        L.call("fs2_fold_halo", dxp, B, Tp, D, hv, None, None, ctx.src_lens, dC_f32, None, int(bf))
+        L.call("fs2_fold_halo", None, B, Tp, D, 0, dC_f32, dAP, ctx.src_lens, dC_f32, dC_act, int(bf))
+        # ---- conditioning
+        L.call("fs2_cond_bwd", dC_f32, self._P("concat_proj.w.weight"), self._P("speaker_emb.Embedding.weight"),
+               ctx.speakers, ctx.intensity, B, Tp, D, self._f32(B, D), self._G("concat_proj.w.weight"),
+               self._G("speaker_emb.Embedding.weight"))
+        self._conv_wgrad(dC_act, ctx.enc_act, B, Tp, "concat_proj.tok", "concat_proj.w.weight", None)
+        denc = self._f32(rowsP, D)
+        self._conv_dgrad(dC_act, B, Tp, "concat_proj.tok", denc)
+        # ---- encoder + embedding
+        ea, eb = self._stack_bwd(self.enc, ctx.enc_saves, ctx.enc_fin, denc, None, B, Tp, ctx.src_lens, ctx.src_lens)
+        if eb is not None:
+            L.call("fs2_add_", ea, eb, rowsP * D)
+        L.call("fs2_embedding_bwd", ea, ctx.tokens, B, Tp, D, self.padding_idx,
+               self._G("encPreNet.token_embedding.Embedding.weight"))
+
+
+class _FS2Function(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, anchor, model, tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate, intensity):
+        outs, ctx = model._forward_impl(tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate, intensity)
+        fctx.model, fctx.ctx = model, ctx
+        fctx.mark_non_differentiable(outs[4], outs[6])
+        return outs
+
+    @staticmethod
+    def backward(fctx, dmel, dpost, dpd, dpp, dap, dpe, dae):
+        fctx.model._backward_impl(fctx.ctx, dmel, dpost, dpd, dpp, dpe)
+        return (torch.zeros(1, device=dmel.device),) + (None,) * 10

@@ -47,6 +47,7 @@ typedef struct {
   const void* A; long long lda, a_s1, a_s2; int a_rows, a_inner, a_row_off, a_tap_step;
   const void* B; long long ldb, b_s1, b_s2; int b_rows, b_inner, b_row_off, b_tap_step;
   long long c_tap_stride;
+  long long c_col_stride;  /* mode 2 only: element stride between consecutive n (0/1 = contiguous) */
   void* C; int c_bf16; long long ldc, c_s1, c_s2; int c_row_off, c_col_off;
   int accumulate;          /* 1: atomically add into fp32 C */
   int split_k;             /* mode 2 only; >1 implies accumulate */
@@ -65,15 +66,21 @@ int fs2_gemm_tc(const Fs2Gemm* g, void* stream);     /* tcgen05 + TMA, bf16 oper
 int fs2_gemm_tc_error_flag(void);
 
 /* ------------------------------------------------------------ row-wise kernels -- */
-/* model.py:335-337  encPreNet embedding + sinusoidal pos-enc + padding mask.
- * tokens (B,Tp) i64; emb (V,D) f32; pe (>=Tp, D) f32.  out_f32/out_act in padded row space. */
+/* Rule for every producer of a padded-row tensor: rect rows get values; halo rows get the reflect mirror
+ * (width `halo`, needs T > halo) and zeros otherwise. */
+
+/* model.py:331-337  key-padding mask + encPreNet embedding + sinusoidal pos-enc + mask.
+ * tokens (B,Tp) i64; emb (V,D) f32; pe (>=Tp, D) f32.  src_lens[b] = number of non-pad tokens (the later
+ * masks assume padding is a suffix, as the reference collate produces: dataset.py:76-80). */
 int fs2_embed_posenc(const int64_t* tokens, const float* emb, const float* pe, int B, int Tp, int D,
                      int pad_idx, float* out_f32, void* out_act, int act_bf16, int* src_lens, void* stream);
+int fs2_embedding_bwd(const float* dx /*padded rows*/, const int64_t* tokens, int B, int Tp, int D, int pad_idx,
+                      float* demb /* += */, void* stream);
 
-/* LayerNorm family (speechbrain LayerNorm / nn.LayerNorm call sites: TransformerEncoderLayer
- * norm1/norm2, TransformerEncoder.norm, DurationPredictor ln1/ln2, PostNet ln1-3).
+/* LayerNorm family (speechbrain LayerNorm / nn.LayerNorm call sites: TransformerEncoderLayer norm1/norm2,
+ * TransformerEncoder.norm, DurationPredictor ln1/ln2 + linear head, PostNet ln1-3).
  *   z = x + drop_b(branch);  u = LN(z)*gamma+beta;  v = tanh?(u);  w = drop_a(v);
- *   out = w * rowmask?  (+ post_add)          ; optional head: scalar[r] = dot(out, head_w)+head_b */
+ *   out = w * rowmask? (+ post_add);   optional head: head_out[b,t] = (dot(out, head_w)+head_b)*head_scale */
 typedef struct {
   int B, T, C;
   const float* x; const float* branch;     /* padded row space fp32; branch may be NULL */
@@ -85,99 +92,114 @@ typedef struct {
   const float* post_add;                    /* NULL or fp32 padded-row tensor added after everything */
   float* out_f32; void* out_act; int act_bf16; int halo;
   float* mean; float* rstd;                 /* [rows] saved statistics (may be NULL) */
-  const float* head_w; const float* head_b; float* head_out; float head_scale; /* optional 384->1 head; head_out is (B,T) plain */
+  const float* head_w; const float* head_b; float* head_out; float head_scale; /* head_out is (B,T) plain */
 } Fs2LnFwd;
 int fs2_ln_fwd(const Fs2LnFwd* p, void* stream);
 
+/* Backward of the above.  Gradient wrt `out` of row (b,t) = dy + reflect-fold_p(dy2) + dhead*head_scale*head_w.
+ * Outputs: dx_f32 = dz (grad wrt z; multiplied by (x>0) when relu_x, for x = relu(conv));
+ *          dact   = drop_b-backward(dz) when branch != NULL else dz, in operand storage, zero halo rows. */
 typedef struct {
   int B, T, C;
-  const float* dy; const float* dy2; int dy2_fold;   /* dy2 optional; dy2_fold=p>0: dy2 is a conv-dgrad output to be reflect-folded */
-  const float* dhead; const float* head_w; float head_scale; /* optional: + dhead[b,t]*head_w */
+  const float* dy; const float* dy2; int dy2_fold;   /* both optional; dy2_fold=p>0: dy2 is a conv-dgrad output whose halo rows fold back */
+  const float* dhead; const float* head_w; float head_scale;
   const float* x; const float* branch;
   float drop_b_p; unsigned long long drop_b_seed;
   const float* gamma; const float* beta; float eps; int tanh_act;
   float drop_a_p; unsigned long long drop_a_seed;
   const int* lens;
   const float* mean; const float* rstd;
-  float* dx_f32;            /* dz (fp32, padded rows; invalid rows zero) */
-  void* dbranch_act; int act_bf16;   /* drop_b-backward of dz, operand storage, zero halo */
-  float* dgamma; float* dbeta;       /* accumulated (+=) */
-  float* dhead_w;                    /* accumulated (+=), optional */
+  int relu_x;
+  float* dx_f32; void* dact; int act_bf16;
+  float* dgamma; float* dbeta; float* dhead_w; float* dhead_b;   /* accumulated (+=) */
 } Fs2LnBwd;
 int fs2_ln_bwd(const Fs2LnBwd* p, void* stream);
 
-/* model.py:352-360 speaker/intensity conditioning, split-weight form:
- * y = (G + Ws.spk_emb[spk[b]] + Wi.intensity[b,t]) * mask ; G = token_feats.Wt^T (a GEMM) */
-int fs2_cond_finish(const float* G, const float* Wcat /*(D, 2D+5)*/, const float* spk_emb, const int64_t* speakers,
-                    const float* intensity /*(B,Tp,5)*/, const int* lens, int B, int Tp, int D,
-                    float* y_f32, void* y_act, int act_bf16, int halo, void* stream);
-int fs2_cond_bwd(const float* dy /*padded rows fp32, already masked*/, const float* Wcat, const float* spk_emb,
-                 const int64_t* speakers, const float* intensity, int B, int Tp, int D, int n_speakers,
-                 float* dWcat, float* dspk_emb, void* stream);
-
-/* speechbrain average_over_durations (model.py:383, 397): mean over non-zero frames per phoneme.
- * values (B,Tm) f32; durs (B,Tp) i64 -> avg (B,Tp) f32; also emits starts/ends (B,Tp) i32 and nz counts. */
-int fs2_avg_over_durations(const float* values, const int64_t* durs, int B, int Tp, int Tm,
-                           float* avg, int* starts, int* ends, int* nz, void* stream);
-
-/* pitchEmbed / energyEmbed: Conv1d(1->D,k,reflect) over the phoneme axis + add (model.py:384-389, 398-403).
- * contour (B,Tp) f32 plain.  y_f32 (unmasked) and y_act (masked copy = predictor input). */
-int fs2_embed_add(const float* x, const float* contour, const float* w /*(D,1,k)*/, const float* bias, int ksize,
-                  const int* lens, int B, int Tp, int D, float* y_f32, void* y_act, int act_bf16, int halo, void* stream);
-int fs2_embed_add_bwd(const float* dy /*padded rows*/, const float* contour, int ksize, int B, int Tp, int D,
-                      float* dw, float* dbias, void* stream);
-
-/* LengthRegulator = speechbrain upsample (model.py:406-410) + get_mask_from_lengths + decoder
- * pos-enc + mask (model.py:411-423).
- * fs2_lr_prepare: frames[b,p] = (long)(pace * dur[b,p]) (fdur != NULL: float durations, inference),
- *                 ends = inclusive cumsum (i32), mel_lens[b].
- * fs2_lr_expand:  out[b,f,:] = (in[b, idx(f), :] + pe[f,:]) for f < mel_lens[b], else 0;
- *                 frame2ph[b,f] = idx(f) or -1.  in/out row pitch + offset let the same kernel serve
- *                 plain (B,T,D) tensors (pitch=T, off=0) and the padded row space. */
-int fs2_lr_prepare(const int64_t* dur, const float* fdur, float pace, int B, int Tp, int* ends, int* mel_lens, void* stream);
-int fs2_lr_expand(const float* in, int in_pitch, int in_off, const int* ends, const int* mel_lens, const float* pe,
-                  int B, int Tp, int Tm, int D, float* out_f32, void* out_act, int act_bf16,
-                  int out_pitch, int out_off, int* frame2ph, void* stream);
-/* backward: dphon[b,p,:] = sum over the phoneme's frames of dframes (segment sum, no atomics) */
-int fs2_lr_bwd(const float* dframes, int f_pitch, int f_off, const int* ends, const int* mel_lens,
-               int B, int Tp, int Tm, int D, float* dphon, int p_pitch, int p_off, void* stream);
-
-/* softmax over keys with the reference's attn_mask quirk (model.py:338-343, 414-419):
- * keys valid for (b,h) are [0, min(len[b], len[(b*H+h) % B])).  S (B*H, T, ldk) fp32 -> P, Pd. */
+/* softmax over keys with the reference's attn_mask quirk (model.py:338-343, 414-419; SURVEY Q1):
+ * keys valid for (b,h) are [0, min(len[b], len[(b*H+h) % B])).  S (B*H, T, ldk) fp32 -> P (and Pd = dropout(P)
+ * when drop_p > 0).  P = softmax(scale*S); columns >= kv are written as 0. */
 int fs2_softmax_fwd(const float* S, const int* lens, int B, int H, int T, int ldk, float scale,
                     float drop_p, unsigned long long seed, void* P, void* Pd, int act_bf16, void* stream);
 int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens, int B, int H, int T, int ldk, float scale,
                     float drop_p, unsigned long long seed, void* dS, int act_bf16, void* stream);
 
+/* model.py:352-360 speaker/intensity conditioning, split-weight form (no cat):
+ * y = (G + Ws.spk_emb[spk[b]] + Wi.intensity[b,t]) * mask ; G = token_feats.Wt^T (a GEMM).
+ * Wcat is concat_proj.w.weight (D, 2D+5).  sp_ws: B*D floats scratch. */
+int fs2_cond_finish(const float* G, const float* Wcat, const float* spk_emb, const int64_t* speakers,
+                    const float* intensity /*(B,Tp,5)*/, const int* lens, int B, int Tp, int D, float* sp_ws,
+                    float* y_f32, void* y_act, int act_bf16, int halo, void* stream);
+/* dy: padded rows fp32, already masked.  Accumulates dWcat[:, D:2D+5] and dspk_emb.  dsum_ws: B*D floats. */
+int fs2_cond_bwd(const float* dy, const float* Wcat, const float* spk_emb, const int64_t* speakers,
+                 const float* intensity, int B, int Tp, int D, float* dsum_ws, float* dWcat, float* dspk_emb,
+                 void* stream);
+
+/* speechbrain average_over_durations (model.py:383, 397): mean over non-zero frames per phoneme, computed as
+ * differences of fp32 prefix sums (torch CPU cumsum semantics: double accumulator, fp32 prefixes).
+ * values (B,Tm) f32; durs (B,Tp) i64 -> avg (B,Tp) f32; optional starts/ends (B,Tp) i32 and nz counts. */
+int fs2_avg_over_durations(const float* values, const int64_t* durs, int B, int Tp, int Tm,
+                           float* avg, int* starts, int* ends, int* nz, void* stream);
+
+/* pitchEmbed / energyEmbed: Conv1d(1->D,k,reflect) over the phoneme axis + add (model.py:384-389, 398-403).
+ * contour (B,Tp) f32 plain.  y_f32 is unmasked (as the reference); y_act = masked copy (next predictor's input). */
+int fs2_embed_add(const float* x, const float* contour, const float* w /*(D,1,k)*/, const float* bias, int ksize,
+                  const int* lens, int B, int Tp, int D, float* y_f32, void* y_act, int act_bf16, int halo, void* stream);
+int fs2_embed_add_bwd(const float* dy /*padded rows*/, const float* contour, int ksize, int B, int Tp, int D,
+                      float* dw, float* dbias, void* stream);
+
+/* LengthRegulator = speechbrain upsample (model.py:406-410) + get_mask_from_lengths + decoder pos-enc + mask
+ * (model.py:411-423).
+ * fs2_dur_decode: fdur = clamp(expm1(log_dur), 0)                                    (model.py:372-375)
+ * fs2_lr_prepare: frames[b,p] = (long)(pace * dur[b,p]) (fdur != NULL: float durations, inference),
+ *                 ends = inclusive cumsum (i32), mel_lens[b].
+ * fs2_lr_expand:  out[b,f,:] = in[b, idx(f), :] + pe[f,:] for f < mel_lens[b], else 0; frame2ph[b,f] = idx(f)
+ *                 or -1.  Row pitch + offset let one kernel serve plain (B,T,D) tensors (pitch=T, off=0) and
+ *                 the padded row space (pitch=T+8, off=4). */
+int fs2_dur_decode(const float* log_dur, long long n, float* fdur, void* stream);
+int fs2_lr_prepare(const int64_t* dur, const float* fdur, float pace, int B, int Tp, int* ends, int* mel_lens, void* stream);
+int fs2_lr_expand(const float* in, int in_pitch, int in_off, const int* ends, const int* mel_lens, const float* pe,
+                  int B, int Tp, int Tm, int D, float* out_f32, void* out_act, int act_bf16,
+                  int out_pitch, int out_off, int* frame2ph, void* stream);
+/* backward: dphon[b,p,:] = sum over the phoneme's frames of (dframes + dframes2) (segment sum, no atomics) */
+int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pitch, int f_off, const int* ends,
+               const int* mel_lens, int B, int Tp, int Tm, int D, float* dphon, int p_pitch, int p_off, void* stream);
+
 /* misc row-space utilities */
-int fs2_fold_halo(const float* src, int B, int T, int C, int p, const float* add, const int* lens,
+/* out = (src + reflect-fold_p(src) + add + add2) * rowmask, zero halo */
+int fs2_fold_halo(const float* src, int B, int T, int C, int p, const float* add, const float* add2, const int* lens,
                   float* out_f32, void* out_act, int act_bf16, void* stream);
 int fs2_colsum(const void* x, int x_bf16, long long rows, int C, long long ld, float* out /* += */, void* stream);
 int fs2_unpad_mask(const float* src, const int* lens, int B, int T, int C, float* out_plain, void* out_act,
                    int act_bf16, int halo, void* stream);
-int fs2_pad_rows(const float* src_plain, int B, int T, int C, float scale, float* out_f32, void* out_act, int act_bf16, void* stream);
-int fs2_embedding_bwd(const float* dx /*padded rows*/, const int64_t* tokens, int B, int Tp, int D, int pad_idx,
-                      float* demb /* += */, void* stream);
+int fs2_pad_rows(const float* src_plain, const float* src2_plain, int B, int T, int C, float scale, float* out_f32,
+                 void* out_act, int act_bf16, void* stream);
+/* weight packing, one launch for the whole parameter set: dst[co, j, ci] = src[co*src_ld + ci*k + j]
+ * (torch Conv1d (Cout,Cin,k) -> tap-major K rows that the implicit GEMM reads) */
+typedef struct { long long src_off, dst_off, src_ld; int cout, cin, k, pad_; } Fs2PackItem;
+int fs2_pack_weights(const Fs2PackItem* items_dev, int n_items, const float* src_base, void* dst_base, int dst_bf16,
+                     void* stream);
 int fs2_cast_bf16(const float* src, void* dst, long long n, void* stream);
 int fs2_add_(float* dst, const float* src, long long n, void* stream);
+int fs2_memset(void* dst, int value, long long nbytes, void* stream);
 
 /* ---------------------------------------------------------------------- losses -- */
 /* loss.py:101-160 per-sample sliced MSE x5, mean over B; fused forward + gradient.
- * out[0..4] = mel, postnet, dur, pitch, energy (un-weighted).  Gradients are scaled by w[i]. */
+ * out[0..4] = mel, postnet, dur, pitch, energy (un-weighted).  Gradients (plain layouts, same shapes as the
+ * predictions) are d(sum_i w[i]*loss_i). Pitch/energy slice the PHONEME axis with the mel length (quirk Q5). */
 int fs2_mse_losses(const float* mel_out, const float* post_out, const float* mel_tgt, const float* log_dur_pred,
                    const int64_t* dur_tgt, const float* pitch_pred, const float* pitch_tgt,
                    const float* energy_pred, const float* energy_tgt, const int64_t* mel_len, const int64_t* phon_len,
-                   int B, int Tp, int Tm, int n_mels, const float* w /*5 weights (device)*/,
+                   int B, int Tp, int Tm, int n_mels, const float* w /*5 host floats*/, float* sums_ws /*5*B floats*/,
                    float* out, float* dmel, float* dpost, float* ddur, float* dpitch, float* denergy, void* stream);
-/* speechbrain SSIMLoss (loss.py:155): masked per-sample min-max norm + 11x11 gaussian SSIM.
- * out[0] = clamped loss; dmel_out += weight * dL/dmel_out.  ws: scratch, fs2_ssim_ws_floats() floats. */
+/* speechbrain SSIMLoss (loss.py:155): masked per-sample min-max norm + 11x11 gaussian SSIM (valid conv).
+ * out[0] = loss clamped as the reference does (>1 -> 1, <0 -> 0, both with zero gradient);
+ * dmel_out += weight * dL/dmel_out when not NULL.  ws: fs2_ssim_ws_floats() floats of scratch. */
 long long fs2_ssim_ws_floats(int B, int Tm, int n_mels);
 int fs2_ssim_loss(const float* mel_out, const float* mel_tgt, const int64_t* mel_len, int B, int Tm, int n_mels,
-                  const float* weight /*device scalar*/, float* out, float* dmel_out /* += , may be NULL */,
-                  float* ws, void* stream);
+                  float weight, float* out, float* dmel_out, float* ws, void* stream);
 
-/* train.py:81 AdamW (torch defaults) over one flat buffer; also refreshes the bf16 shadow. */
-int fs2_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+/* train.py:81 AdamW (torch defaults: decoupled weight decay, bias correction) over one flat buffer */
+int fs2_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
               float beta2, float eps, float wd, int step, float grad_scale, void* stream);
 
 /* train.py:16-51 duration-segment mean of frame intensities ("next" row f-1) */
