@@ -1,0 +1,112 @@
+"""Host-side logic that needs no GPU: flat parameter store / state_dict contract, synthetic batch recipe,
+data-parallel sharding and the flat-gradient all-reduce over gloo (world_size 2)."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+PKG = "fine-grained-emotional-control-of-tts_b200"
+
+
+def test_state_dict_interchanges_with_oracle(pkg):
+    import fs2_oracle as O
+    m = pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4)
+    o = O.build(seed=1)
+    sd_o, sd_m = o.state_dict(), m.state_dict()
+    assert list(sd_o.keys()) == sorted(sd_o.keys(), key=list(sd_o.keys()).index)
+    assert set(sd_o) == set(sd_m)
+    assert all(sd_o[k].shape == sd_m[k].shape for k in sd_o)
+    m.load_state_dict(sd_o)
+    assert m.store.views_intact()
+    for k in ("decoder.layers.2.pos_ffn.0.conv.weight", "concat_proj.w.weight", "postnet.ln3.bias"):
+        assert torch.equal(m.state_dict()[k], sd_o[k])
+    o2 = O.build(seed=2)
+    o2.load_state_dict(m.state_dict())         # and back: checkpoints interchange (train.py:253 <-> inference.py:27)
+    assert torch.equal(o2.state_dict()["durPred.ln1.norm.weight"], sd_o["durPred.ln1.norm.weight"])
+    assert sum(p.numel() for p in m.parameters()) == 85295299
+
+
+def test_postnet_ln_alt_keys(pkg):
+    m = pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4)
+    sd = m.state_dict()
+    for i in (1, 2, 3):
+        for leaf in ("weight", "bias"):
+            sd[f"postnet.ln{i}.norm.{leaf}"] = sd.pop(f"postnet.ln{i}.{leaf}") + 1.0
+    m.load_state_dict(sd)
+    assert torch.allclose(m.state_dict()["postnet.ln2.weight"], torch.full((512,), 2.0))
+
+
+def test_flat_views_survive_module_apply(pkg):
+    m = pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4)
+    w = m.state_dict()["linear.w.weight"].clone()
+    m = m.to("cpu").float()
+    assert m.store.views_intact()
+    assert torch.equal(m.state_dict()["linear.w.weight"], w)
+    with pytest.raises(RuntimeError):
+        m.double()
+
+
+def test_constructor_validation(pkg):
+    cfg = dict(pkg.DEFAULT_MODEL_CONFIG)
+    with pytest.raises(NotImplementedError):
+        pkg.FastSpeech2(**{**cfg, "ffn_type": "regularFFN"}, n_speakers=4)
+    with pytest.raises(ValueError):
+        pkg.FastSpeech2(**{**cfg, "ffn_cnn_kernel_size_list": [11, 1]}, n_speakers=4)
+    with pytest.raises(NotImplementedError):
+        pkg.Loss(**{**pkg.DEFAULT_LOSS_CONFIG, "log_scale_durations": False})
+
+
+def test_synthetic_batch_recipe():
+    data = importlib.import_module(PKG + ".data")
+    batches = data.synthetic_batches(8, 3, seed=1234, rank=0)
+    for batch, intensity in batches:
+        tokens, speakers, in_lens, mel, pitch, energy, dur, out_lens = batch[:8]
+        B, Tp = tokens.shape
+        assert B == 8 and Tp <= 128 and mel.shape[1] <= 800 and mel.shape[2] == 80
+        assert (in_lens[:-1] >= in_lens[1:]).all()                       # sorted by descending Tp (dataset.py:65-67)
+        assert torch.equal(dur.sum(1), out_lens)                          # mel_len == sum(dur)
+        assert int(out_lens.max()) == mel.shape[1]
+        for b in range(B):
+            assert (tokens[b, : in_lens[b]] > 0).all() and (tokens[b, in_lens[b]:] == 0).all()
+            assert (mel[b, out_lens[b]:] == 0).all() and (intensity[b, in_lens[b]:] == 0).all()
+        assert intensity.shape == (B, Tp, 5)
+        assert batch[10].shape == (B, 82, mel.shape[1])
+    other = data.synthetic_batches(8, 1, seed=1234, rank=1)
+    assert not torch.equal(other[0][0][0], batches[0][0][0]) or other[0][0][0].shape != batches[0][0][0].shape
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    par = importlib.import_module(PKG + ".parallel")
+    r, w, _ = par.init_from_env("gloo")
+    flat = torch.full((1000,), float(rank + 1))
+    par.allreduce_flat_(flat, w)
+    p = torch.arange(10.0) * (rank + 1)
+    par.broadcast_flat_(p, 0)
+    shard = par.shard_for_rank(list(range(11)), r, w)
+    q.put((rank, flat[0].item(), p.tolist(), shard))
+    dist.destroy_process_group()
+
+
+def test_dp_allreduce_and_sharding_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == 3.0 and res[1][1] == 3.0                       # SUM over ranks of the flat buffer
+    assert res[0][2] == res[1][2] == [float(i) for i in range(10)]      # replicas identical after broadcast
+    assert res[0][3] == [0, 2, 4, 6, 8] and res[1][3] == [1, 3, 5, 7, 9]
