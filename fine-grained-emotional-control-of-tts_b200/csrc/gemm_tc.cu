@@ -26,7 +26,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
-constexpr int NTHREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NTHREADS = 32 * (2 + NUM_EPI_WARPS);
 
 struct TcParams {
   Fs2Gemm g;
@@ -35,6 +36,7 @@ struct TcParams {
   int kb_per_split;
   int nsplit;
   int ntiles_per_tap; // mode 2
+  int m_tiles, n_tiles_total, total_tiles;
   int pa[4], pb[4];   // tensor-map dim slot of (inner,row,i1,i2) for A and B
   int* err;
 };
@@ -52,6 +54,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -137,43 +142,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 template <int MODE, int BN, int STAGES>
-__global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                            const __grid_constant__ CUtensorMap tmB,
-                                                            const TcParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const TcParams p) {
   constexpr int A_BYTES = BM * BK * 2;          // 16 KB
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr bool A_MN = (MODE == 2);
   constexpr bool B_MN = (MODE != 0);
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+  constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;     // two accumulator buffers
+  constexpr int CHUNKS_PER_HALF = BN / 64;                   // 32-column chunks per epilogue column-half
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Fs2Gemm& g = p.g;
   int* err = p.err;
-
-  const int nt = blockIdx.x;
-  const int m0 = blockIdx.y * BM;
-  const int zb = blockIdx.z / p.nsplit, zs = blockIdx.z % p.nsplit;
-  const int i1 = zb % g.batch1, i2 = zb / g.batch1;
-  int tapN = 0, n0 = nt * BN;
-  if (MODE == 2) { tapN = nt / p.ntiles_per_tap; n0 = (nt % p.ntiles_per_tap) * BN; }
-  int kb_begin = zs * p.kb_per_split;
-  int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
-  const int nkb = kb_end - kb_begin;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(accum_bar), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), NUM_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -188,132 +188,217 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Persistent tile loop: tile t -> (n-tile fastest so CTAs running together share the A rows in L2).
+  // Every role walks the same sequence; smem stage / phase counters run across tiles.
   if (warp == 0) {
-    if (lane == 0 && nkb > 0) {
+    if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        if (!mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, err)) break;
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, STAGE_BYTES);
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
-        const int kb = kb_begin + it;
-        if (MODE == 0 || MODE == 1) {
-          const int j = kb / p.kb_per_tap;
-          const int kk = (kb - j * p.kb_per_tap) * BK;
-          tma_issue(sa, &tmA, fb, p.pa, kk, g.a_row_off + m0 + j * g.a_tap_step, i1, i2);
-          if (MODE == 0) {
-            tma_issue(sb, &tmB, fb, p.pb, j * g.b_tap_step + kk, n0, i1, i2);
+      uint32_t it = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x) {
+        const int nt = t % p.n_tiles_total;
+        const int rest = t / p.n_tiles_total;
+        const int m0 = (rest % p.m_tiles) * BM;
+        const int z = rest / p.m_tiles;
+        const int zb = z / p.nsplit, zs = z % p.nsplit;
+        const int i1 = zb % g.batch1, i2 = zb / g.batch1;
+        int tapN = 0, n0 = nt * BN;
+        if (MODE == 2) { tapN = nt / p.ntiles_per_tap; n0 = (nt % p.ntiles_per_tap) * BN; }
+        const int kb_begin = zs * p.kb_per_split;
+        const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (!mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, err)) { ok = false; break; }
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          if (MODE == 0 || MODE == 1) {
+            const int j = kb / p.kb_per_tap;
+            const int kk = (kb - j * p.kb_per_tap) * BK;
+            tma_issue(sa, &tmA, fb, p.pa, kk, g.a_row_off + m0 + j * g.a_tap_step, i1, i2);
+            if (MODE == 0) {
+              tma_issue(sb, &tmB, fb, p.pb, j * g.b_tap_step + kk, n0, i1, i2);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_issue(sb + i * (BK * 128), &tmB, fb, p.pb, n0 + 64 * i + j * g.b_tap_step, g.b_row_off + kk, i1, i2);
+            }
           } else {
+            const int k0 = kb * BK;
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_issue(sa + i * (BK * 128), &tmA, fb, p.pa, m0 + 64 * i, g.a_row_off + k0, i1, i2);
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
-              tma_issue(sb + i * (BK * 128), &tmB, fb, p.pb, n0 + 64 * i + j * g.b_tap_step, g.b_row_off + kk, i1, i2);
+              tma_issue(sb + i * (BK * 128), &tmB, fb, p.pb, n0 + 64 * i, g.b_row_off + k0 + tapN * g.b_tap_step, i1, i2);
           }
-        } else {
-          const int k0 = kb * BK;
-#pragma unroll
-          for (int i = 0; i < BM / 64; ++i)
-            tma_issue(sa + i * (BK * 128), &tmA, fb, p.pa, m0 + 64 * i, g.a_row_off + k0, i1, i2);
-#pragma unroll
-          for (int i = 0; i < BN / 64; ++i)
-            tma_issue(sb + i * (BK * 128), &tmB, fb, p.pb, n0 + 64 * i, g.b_row_off + k0 + tapN * g.b_tap_step, i1, i2);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nkb > 0) {
+    if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t it = 0, tc = 0;
       bool ok = true;
-      for (int it = 0; it < nkb && ok; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        if (!mbar_wait(smem_u32(&full_bar[s]), ph, err)) { ok = false; break; }
+      for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x, ++tc) {
+        const int z = (t / p.n_tiles_total) / p.m_tiles;
+        const int zs = z % p.nsplit;
+        const int kb_begin = zs * p.kb_per_split;
+        const int nkb = min(p.total_kb, kb_begin + p.kb_per_split) - kb_begin;
+        const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+        if (!mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1, err)) { ok = false; break; }
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          if (!mbar_wait(smem_u32(&full_bar[s]), ph, err)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major: 16 elements = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
-          // MN-major: 16 k-rows = 2 groups of 8 rows (1024 B each); 64-wide MN blocks 8192 B apart.
-          const uint64_t ad = A_MN ? smem_desc(sa + k * 2048, BK * 128, 1024) : smem_desc(sa + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? smem_desc(sb + k * 2048, BK * 128, 1024) : smem_desc(sb + k * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 elements = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
+            // MN-major: 16 k-rows = 2 groups of 8 rows (1024 B each); 64-wide MN blocks 8192 B apart.
+            const uint64_t ad = A_MN ? smem_desc(sa + k * 2048, BK * 128, 1024) : smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? smem_desc(sb + k * 2048, BK * 128, 1024) : smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
         }
-        umma_commit(smem_u32(&empty_bar[s]));
+        if (ok) umma_commit(smem_u32(&tfull_bar[as]));
       }
-      umma_commit(smem_u32(accum_bar));
     }
   } else {
-    // ---------------- epilogue: 4 warps, TMEM lane quadrant = warp % 4 ----------------
+    // ---------------- epilogue: 8 warps; TMEM lane quadrant = warp % 4, column half = (warp-2)/4 ----------------
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    bool ok = true;
-    if (nkb > 0) ok = mbar_wait(smem_u32(accum_bar), 0, err);
-    tc_fence_after();
-    EpiRow er;
-    const bool row_ok = ok && (m < g.M);
-    if (row_ok) epi_row_setup(g, i1, i2, m, er);
+    const int half = (warp - 2) >> 2;
     const bool atomic = p.nsplit > 1 || g.accumulate;
     const long long cstr = (MODE == 2 && g.c_col_stride > 1) ? g.c_col_stride : 1;
-    const long long colbase = (MODE == 2) ? (long long)tapN * g.c_tap_stride + n0 * cstr : n0;
-    const bool vec_f32 = cstr == 1 && !g.c_bf16 && !atomic && ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2 | colbase) % 4 == 0) &&
-                         (((uintptr_t)g.C) % 16 == 0);
-    const bool vec_bf16 = cstr == 1 && g.c_bf16 && ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2 | colbase) % 8 == 0) &&
-                          (((uintptr_t)g.C) % 16 == 0);
+    const bool al4 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 4 == 0) && (((uintptr_t)g.C) % 16 == 0);
+    const bool al8 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 8 == 0) && (((uintptr_t)g.C) % 16 == 0);
+    const bool aux_al = g.relu_aux == nullptr || (((uintptr_t)g.relu_aux) % 16 == 0);
+    uint32_t tc = 0;
+    bool ok = true;
+    for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x, ++tc) {
+      const int nt = t % p.n_tiles_total;
+      const int rest = t / p.n_tiles_total;
+      const int m0 = (rest % p.m_tiles) * BM;
+      const int z = rest / p.m_tiles;
+      const int zb = z / p.nsplit;
+      const int i1 = zb % g.batch1, i2 = zb / g.batch1;
+      int tapN = 0, n0 = nt * BN;
+      if (MODE == 2) { tapN = nt / p.ntiles_per_tap; n0 = (nt % p.ntiles_per_tap) * BN; }
+      const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+      const int m = m0 + q * 32 + lane;
+      EpiRow er;
+      const bool row_ok = (m < g.M);
+      if (row_ok) epi_row_setup(g, i1, i2, m, er);
+      const long long colbase = (MODE == 2) ? (long long)tapN * g.c_tap_stride + n0 * cstr : n0;
+      const bool vec_f32 = cstr == 1 && !g.c_bf16 && !atomic && al4 && (colbase % 4 == 0) && aux_al;
+      const bool vec_bf16 = cstr == 1 && g.c_bf16 && al8 && (colbase % 8 == 0) && aux_al;
+      if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, err)) { ok = false; break; }
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      if (n0 + c * 32 >= g.N) break;       // warp-uniform
-      uint32_t r[32];
-      if (nkb > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      } else {
+      for (int ci = 0; ci < CHUNKS_PER_HALF; ++ci) {
+        const int c = half * CHUNKS_PER_HALF + ci;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+        if (ci == CHUNKS_PER_HALF - 1) {
+          // all of this warp's TMEM reads are complete: hand the accumulator buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
+        }
+        const int nb0 = n0 + c * 32;
+        if (nb0 >= g.N || !row_ok || er.skip) continue;
+        const long long col0 = colbase + (long long)c * 32 * cstr;
+        const bool full = (nb0 + 32 <= g.N);
+        if (full && (vec_f32 || vec_bf16)) {
+          float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = 0;
-      }
-      if (!row_ok || er.skip) continue;
-      const int nb0 = n0 + c * 32;
-      const long long col0 = colbase + c * 32 * cstr;
-      const bool full = (nb0 + 32 <= g.N);
-      if (full && (vec_f32 || vec_bf16)) {
-        float v[32];
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(r[i]) * g.alpha;
+            if (g.bias) x += g.bias[nb0 + i];
+            if (g.relu) x = fmaxf(x, 0.f);
+            v[i] = er.live ? x : 0.f;
+          }
+          if (g.relu_aux) {
+            if (g.aux_bf16) {
+              const uint4* ap = reinterpret_cast<const uint4*>((const bf16*)g.relu_aux + er.base + col0);
+              uint4 a[4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = epi_value(g, er, col0 + i, nb0 + i, __uint_as_float(r[i]));
-        if (vec_f32) {
-          float* dst = (float*)g.C + er.base + col0;
+              for (int i = 0; i < 4; ++i) a[i] = ap[i];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t w[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
-            const long long mo = mi ? er.mirror2 : er.mirror;
-            if (mo) {
+                for (int j = 0; j < 4; ++j) {
+                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                  if (!((w[j] & 0x8000u) == 0 && (w[j] & 0x7FFFu) != 0)) v[i * 8 + j * 2] = 0.f;
+                  if (!((w[j] & 0x80000000u) == 0 && (w[j] & 0x7FFF0000u) != 0)) v[i * 8 + j * 2 + 1] = 0.f;
+                }
+              }
+            } else {
+              const float4* ap = reinterpret_cast<const float4*>((const float*)g.relu_aux + er.base + col0);
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                st4(dst + mo + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+              for (int i = 0; i < 8; ++i) {
+                float4 a = ap[i];
+                if (!(a.x > 0.f)) v[4 * i] = 0.f;
+                if (!(a.y > 0.f)) v[4 * i + 1] = 0.f;
+                if (!(a.z > 0.f)) v[4 * i + 2] = 0.f;
+                if (!(a.w > 0.f)) v[4 * i + 3] = 0.f;
+              }
+            }
+          }
+          if (vec_f32) {
+            float* dst = (float*)g.C + er.base + col0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+              const long long mo = mi ? er.mirror2 : er.mirror;
+              if (mo) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  st4(dst + mo + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+              }
+            }
+          } else {
+            bf16* dst = (bf16*)g.C + er.base + col0;
+            uint4 pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+              pk[i].x = *reinterpret_cast<uint32_t*>(&h0);
+              pk[i].y = *reinterpret_cast<uint32_t*>(&h1);
+              pk[i].z = *reinterpret_cast<uint32_t*>(&h2);
+              pk[i].w = *reinterpret_cast<uint32_t*>(&h3);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = pk[i];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+              const long long mo = mi ? er.mirror2 : er.mirror;
+              if (mo) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst + mo)[i] = pk[i];
+              }
             }
           }
         } else {
-          bf16* dst = (bf16*)g.C + er.base + col0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-#pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
-            const long long mo = mi ? er.mirror2 : er.mirror;
-            if (mo) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                st4(dst + mo + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-            }
-          }
+          for (int i = 0; i < 32; ++i)
+            if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
       }
     }
   }
@@ -392,20 +477,55 @@ int make_map(const void* base, long long inner, long long rows, int b1, int b2, 
     fs2_set_error(msg);
     return FS2_ERR_CUDA;
   }
+  if (g_map_cache.size() > 8192) g_map_cache.clear();   // shapes vary per batch: keep the cache bounded
   g_map_cache[key] = *out;
   return FS2_OK;
 }
 
+int g_num_sms = 0;
+
 template <int MODE, int BN, int STAGES>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, dim3 grid, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
   constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(tc_gemm_kernel<MODE, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    CUDA_CHECK_RET(cudaGetDevice(&dev));
+    CUDA_CHECK_RET(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  p.ntiles_per_tap = (p.g.N + BN - 1) / BN;
+  p.n_tiles_total = (p.g.mode == 2) ? p.ntiles_per_tap * p.g.taps : p.ntiles_per_tap;
+  p.m_tiles = (p.g.M + BM - 1) / BM;
+  const long long total = (long long)p.n_tiles_total * p.m_tiles * p.g.batch1 * p.g.batch2 * p.nsplit;
+  if (total > 0x7FFFFFFF) { fs2_set_error("fs2_gemm_tc: too many tiles"); return FS2_ERR_ARG; }
+  p.total_tiles = (int)total;
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   tc_gemm_kernel<MODE, BN, STAGES><<<grid, NTHREADS, SMEM, st>>>(ta, tb, p);
   return fs2_check_launch();
+}
+
+template <int MODE>
+int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
+  if (bn == 256) return launch<MODE, 256, 4>(ta, tb, p, st);
+  if (bn == 192) return launch<MODE, 192, 5>(ta, tb, p, st);
+  return launch<MODE, 128, 6>(ta, tb, p, st);
+}
+
+// tile width: least padded columns, ties -> wider tile
+int pick_bn(int N) {
+  int best = 128;
+  long long best_pad = ((N + 127) / 128) * 128LL;
+  const int cands[2] = {192, 256};
+  for (int i = 0; i < 2; ++i) {
+    long long pad = ((N + cands[i] - 1) / cands[i]) * (long long)cands[i];
+    if (pad <= best_pad) { best_pad = pad; best = cands[i]; }
+  }
+  return best;
 }
 
 }  // namespace
@@ -425,7 +545,7 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return FS2_OK;
   int rc = get_encode();
   if (rc) return rc;
-  constexpr int BN = 128;
+  const int BN = pick_bn(g.N);
   TcParams p;
   memset(&p, 0, sizeof p);
   p.g = g;
@@ -436,7 +556,6 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   p.kb_per_split = (p.total_kb + p.nsplit - 1) / p.nsplit;
   p.nsplit = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (p.nsplit > 1 && g.c_bf16) { fs2_set_error("fs2_gemm_tc: split_k needs fp32 C"); return FS2_ERR_ARG; }
-  p.ntiles_per_tap = (g.N + BN - 1) / BN;
   int* errp = nullptr;
   CUDA_CHECK_RET(cudaGetSymbolAddress((void**)&errp, g_tc_error));
   p.err = errp;
@@ -448,12 +567,10 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   if (g.mode == 0) rc = make_map(g.B, g.b_inner, g.b_rows, g.batch1, g.batch2, g.ldb, g.b_s1, g.b_s2, BK, BN, &tb, p.pb);
   else rc = make_map(g.B, g.b_inner, g.b_rows, g.batch1, g.batch2, g.ldb, g.b_s1, g.b_s2, 64, BK, &tb, p.pb);
   if (rc) return rc;
-  int ntiles = (g.mode == 2) ? p.ntiles_per_tap * g.taps : p.ntiles_per_tap;
-  dim3 grid(ntiles, (g.M + BM - 1) / BM, g.batch1 * g.batch2 * p.nsplit);
   cudaStream_t st = (cudaStream_t)stream;
-  if (g.mode == 0) return launch<0, BN, 3>(ta, tb, p, grid, st);
-  if (g.mode == 1) return launch<1, BN, 3>(ta, tb, p, grid, st);
-  if (g.mode == 2) return launch<2, BN, 3>(ta, tb, p, grid, st);
+  if (g.mode == 0) return dispatch_bn<0>(BN, ta, tb, p, st);
+  if (g.mode == 1) return dispatch_bn<1>(BN, ta, tb, p, st);
+  if (g.mode == 2) return dispatch_bn<2>(BN, ta, tb, p, st);
   fs2_set_error("fs2_gemm_tc: bad mode");
   return FS2_ERR_ARG;
 }

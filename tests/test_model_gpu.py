@@ -170,7 +170,8 @@ def test_train_mode_dropout_runs_and_is_seeded(pkg, oracle64):
     model.manual_seed(7)
     model._generation = 0
     p2, l2 = run_model(pkg, model, c)
-    assert torch.equal(p1[0], p2[0]) and float(l1["total_loss"]) == float(l2["total_loss"])    # same seed, same masks
+    assert torch.equal(p1[0], p2[0]) and torch.equal(p1[1], p2[1])                                 # same seed, same masks
+    assert abs(float(l1["total_loss"]) - float(l2["total_loss"])) <= 1e-5 * abs(float(l1["total_loss"]))   # atomics order only
     assert torch.isfinite(g1).all() and g1.abs().sum() > 0
     p3, _ = run_model(pkg, model, c)                                                             # next step: new masks
     assert not torch.equal(p1[0], p3[0])
