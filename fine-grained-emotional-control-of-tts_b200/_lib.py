@@ -27,8 +27,9 @@ SIGNATURES = {
     "fs2_embedding_bwd": "ppiiiipp",
     "fs2_ln_fwd": "pp",
     "fs2_ln_bwd": "pp",
-    "fs2_softmax_fwd": "ppiiiiffQppip",
-    "fs2_softmax_bwd": "pppiiiiffQpip",
+    "fs2_softmax_fwd": "ppiiiiffQpppip",
+    "fs2_softmax_bwd": "pppiiiiffQppip",
+    "fs2_counter_add": "pQp",
     "fs2_cond_finish": "ppppppiiipppiip",
     "fs2_cond_bwd": "pppppiiipppp",
     "fs2_avg_over_durations": "ppiiippppp",
@@ -85,6 +86,7 @@ class Fs2LnFwd(C.Structure):
         ("mean", C.c_void_p), ("rstd", C.c_void_p),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p),
         ("head_scale", C.c_float),
+        ("seed_dev", C.c_void_p),
     ]
 
 
@@ -101,6 +103,7 @@ class Fs2LnBwd(C.Structure):
         ("relu_x", C.c_int),
         ("dx_f32", C.c_void_p), ("dact", C.c_void_p), ("act_bf16", C.c_int),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dhead_w", C.c_void_p), ("dhead_b", C.c_void_p),
+        ("seed_dev", C.c_void_p),
     ]
 
 

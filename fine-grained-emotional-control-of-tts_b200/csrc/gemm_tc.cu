@@ -556,8 +556,8 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   p.kb_per_split = (p.total_kb + p.nsplit - 1) / p.nsplit;
   p.nsplit = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (p.nsplit > 1 && g.c_bf16) { fs2_set_error("fs2_gemm_tc: split_k needs fp32 C"); return FS2_ERR_ARG; }
-  int* errp = nullptr;
-  CUDA_CHECK_RET(cudaGetSymbolAddress((void**)&errp, g_tc_error));
+  static int* errp = nullptr;     // resolved once (also keeps the call out of CUDA-graph captures)
+  if (!errp) CUDA_CHECK_RET(cudaGetSymbolAddress((void**)&errp, g_tc_error));
   p.err = errp;
   CUtensorMap ta, tb;
   // A: mode 0/1 K-major box (64 k, 128 rows); mode 2 MN-major box (64 m, 64 k-rows)

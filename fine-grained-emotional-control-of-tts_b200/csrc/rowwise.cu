@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p) {
   const long long rows = (long long)p.B * TP;
   const float invC = 1.0f / (float)C;
   TA* oa = (TA*)p.out_act;
-  const DropCfg db{p.drop_b_p, p.drop_b_seed}, da{p.drop_a_p, p.drop_a_seed};
+  const unsigned long long bump = p.seed_dev ? mix64(*p.seed_dev) : 0ull;
+  const DropCfg db{p.drop_b_p, p.drop_b_seed ^ bump}, da{p.drop_a_p, p.drop_a_seed ^ bump};
   for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
     int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
     const long long ro = r * C;
@@ -221,7 +222,8 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
   const long long rows = (long long)p.B * TP;
   const float invC = 1.0f / (float)C;
   TA* da_out = (TA*)p.dact;
-  const DropCfg db{p.drop_b_p, p.drop_b_seed}, da{p.drop_a_p, p.drop_a_seed};
+  const unsigned long long bump = p.seed_dev ? mix64(*p.seed_dev) : 0ull;
+  const DropCfg db{p.drop_b_p, p.drop_b_seed ^ bump}, da{p.drop_a_p, p.drop_a_seed ^ bump};
   float4 dg[MAXV], dbt[MAXV], dhw[MAXV];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) dg[i] = dbt[i] = dhw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -347,8 +349,9 @@ __device__ __forceinline__ int quirk_kv(const int* lens, int B, int H, int bh) {
 
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) softmax_fwd_kernel(const float* S, const int* lens, int B, int H, int T,
-                                                              int ldk, float scale, DropCfg dc, TA* P, TA* Pd) {
+                                                              int ldk, float scale, DropCfg dc, const unsigned long long* seed_dev, TA* P, TA* Pd) {
   const int lane = threadIdx.x & 31;
+  if (seed_dev) dc.seed ^= mix64(*seed_dev);
   const long long rows = (long long)B * H * T;
   for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
     const int bh = (int)(r / T);
@@ -392,8 +395,10 @@ __global__ void __launch_bounds__(THREADS) softmax_fwd_kernel(const float* S, co
 
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) softmax_bwd_kernel(const TA* P, const float* dPd, const int* lens, int B,
-                                                              int H, int T, int ldk, float scale, DropCfg dc, TA* dS) {
+                                                              int H, int T, int ldk, float scale, DropCfg dc,
+                                                              const unsigned long long* seed_dev, TA* dS) {
   const int lane = threadIdx.x & 31;
+  if (seed_dev) dc.seed ^= mix64(*seed_dev);
   const long long rows = (long long)B * H * T;
   for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
     const int bh = (int)(r / T);
@@ -835,6 +840,8 @@ __global__ void pack_weights_kernel(const Fs2PackItem* items, const float* src_b
   }
 }
 
+__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
+
 __global__ void cast_bf16_kernel(const float* s, bf16* d, long long n) {
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) st4(d + i, ld4(s + i));
@@ -948,23 +955,25 @@ extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
 }
 
 extern "C" int fs2_softmax_fwd(const float* S, const int* lens, int B, int H, int T, int ldk, float scale, float drop_p,
-                               unsigned long long seed, void* P, void* Pd, int act_bf16, void* stream) {
+                               unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd,
+                               int act_bf16, void* stream) {
   REQUIRE(S && lens && P && ldk % 4 == 0 && ldk >= T, "fs2_softmax_fwd: bad arguments");
   DropCfg dc{drop_p, seed};
   if (drop_p <= 0.f) Pd = nullptr;
   const long long rows = (long long)B * H * T;
-  if (act_bf16) softmax_fwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(S, lens, B, H, T, ldk, scale, dc, (bf16*)P, (bf16*)Pd);
-  else softmax_fwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(S, lens, B, H, T, ldk, scale, dc, (float*)P, (float*)Pd);
+  if (act_bf16) softmax_fwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(S, lens, B, H, T, ldk, scale, dc, seed_dev, (bf16*)P, (bf16*)Pd);
+  else softmax_fwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(S, lens, B, H, T, ldk, scale, dc, seed_dev, (float*)P, (float*)Pd);
   return fs2_check_launch();
 }
 
 extern "C" int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens, int B, int H, int T, int ldk,
-                               float scale, float drop_p, unsigned long long seed, void* dS, int act_bf16, void* stream) {
+                               float scale, float drop_p, unsigned long long seed, const unsigned long long* seed_dev,
+                               void* dS, int act_bf16, void* stream) {
   REQUIRE(P && dPd && lens && dS && ldk % 4 == 0, "fs2_softmax_bwd: bad arguments");
   DropCfg dc{drop_p, seed};
   const long long rows = (long long)B * H * T;
-  if (act_bf16) softmax_bwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>((const bf16*)P, dPd, lens, B, H, T, ldk, scale, dc, (bf16*)dS);
-  else softmax_bwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>((const float*)P, dPd, lens, B, H, T, ldk, scale, dc, (float*)dS);
+  if (act_bf16) softmax_bwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>((const bf16*)P, dPd, lens, B, H, T, ldk, scale, dc, seed_dev, (bf16*)dS);
+  else softmax_bwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>((const float*)P, dPd, lens, B, H, T, ldk, scale, dc, seed_dev, (float*)dS);
   return fs2_check_launch();
 }
 
@@ -1107,6 +1116,12 @@ extern "C" int fs2_cast_bf16(const float* src, void* dst, long long n, void* str
 extern "C" int fs2_add_(float* dst, const float* src, long long n, void* stream) {
   REQUIRE(src && dst, "fs2_add_: null pointer");
   add_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ST>>>(dst, src, n);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_counter_add(unsigned long long* ctr, unsigned long long inc, void* stream) {
+  REQUIRE(ctr, "fs2_counter_add: null pointer");
+  counter_add_kernel<<<1, 1, 0, ST>>>(ctr, inc);
   return fs2_check_launch();
 }
 

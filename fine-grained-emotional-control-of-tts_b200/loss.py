@@ -10,6 +10,9 @@ import torch.nn as nn
 from . import _lib as L
 
 
+_WEIGHT_CACHE = {}
+
+
 class _LossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mel_out, post_out, log_dur, pitch_pred, energy_pred, pitch_tgt, energy_tgt, mel_tgt, dur_tgt,
@@ -53,7 +56,11 @@ class _LossFn(torch.autograd.Function):
         ctx.grads = (dmel, dpost, ddur, dpitch, denergy)
         ctx.shapes = None
         # out[0..4] = mel, postnet, dur, pitch, energy (un-weighted); out[5] = ssim
-        wv = torch.tensor([w_mel, w_post, w_dur, w_pitch, w_energy, w_ssim], device=dev, dtype=torch.float32)
+        key = (weights, dev)
+        wv = _WEIGHT_CACHE.get(key)
+        if wv is None:
+            wv = torch.tensor([w_mel, w_post, w_dur, w_pitch, w_energy, w_ssim], device=dev, dtype=torch.float32)
+            _WEIGHT_CACHE[key] = wv
         comps = out[:6] * wv
         total = comps.sum()
         ctx.mark_non_differentiable(comps)

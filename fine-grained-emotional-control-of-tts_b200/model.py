@@ -168,6 +168,12 @@ class FastSpeech2(nn.Module):
         self._arenas = None
         self._seed_base = 0x1234
         self._generation = 0
+        self._ctr = None              # device-side dropout step counter (uint64 in an int64 tensor)
+        self.use_cuda_graphs = False  # opt-in: replay the captured step per (B, Tp, Tm) -- see _graph_forward
+        self._graphs = {}
+        self._seen = set()
+        self._pre = None
+        self.replayed_launches = 0    # kernels launched through graph replays (fs2_launch_count only sees captures)
         self.trace = None        # set to a dict to collect unpadded intermediates (debug / parity tests)
         self._pin_lens = None
 
@@ -176,6 +182,9 @@ class FastSpeech2(nn.Module):
         super()._apply(fn, *a, **kw)
         self.store.reflatten()
         self._anchor = torch.zeros(1, device=self.store.flat.device, requires_grad=True)
+        self._ctr = None
+        self._graphs.clear()
+        self._pre = None
         return self
 
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -188,8 +197,11 @@ class FastSpeech2(nn.Module):
         return super().load_state_dict(sd, strict=strict, **kw)
 
     def manual_seed(self, seed):
-        """Seed of the counter-based dropout masks."""
+        """Seed of the counter-based dropout masks (also rewinds the per-step counter)."""
         self._seed_base = int(seed) & _M64
+        if self._ctr is not None:
+            self._ctr.zero_()
+        self._graphs.clear()       # seeds are baked into captured launches
 
     # --------------------------------------------------------------------------- helpers
     @property
@@ -275,6 +287,7 @@ class FastSpeech2(nn.Module):
         if head is not None:
             hw, hb, hout, hs = head
             p.head_w, p.head_b, p.head_out, p.head_scale = hw.data_ptr(), hb.data_ptr(), hout.data_ptr(), hs
+        p.seed_dev = self._ctr.data_ptr()
         L.call("fs2_ln_fwd", L.C.addressof(p))
 
     def _ln_bwd(self, B, T, C, x, gamma, beta, eps, mean, rstd, *, dy=None, dy2=None, dy2_fold=0, dhead=None,
@@ -303,6 +316,7 @@ class FastSpeech2(nn.Module):
         p.dbeta = dbeta.data_ptr() if dbeta is not None else None
         p.dhead_w = dhead_w.data_ptr() if dhead_w is not None else None
         p.dhead_b = dhead_b.data_ptr() if dhead_b is not None else None
+        p.seed_dev = self._ctr.data_ptr()
         L.call("fs2_ln_bwd", L.C.addressof(p))
 
     # ------------------------------------------------------------------- FFT block stack
@@ -317,7 +331,7 @@ class FastSpeech2(nn.Module):
         L.gemm(mode=0, M=T, N=T, K=hd, A=qkv, A_off=PAD * ld, lda=ld, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * ld,
                B=qkv, B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
                Cout=S, ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=bf)
-        L.call("fs2_softmax_fwd", S, lens, B, H, T, ldk, 1.0 / math.sqrt(hd), p_drop, seed, P,
+        L.call("fs2_softmax_fwd", S, lens, B, H, T, ldk, 1.0 / math.sqrt(hd), p_drop, seed, self._ctr, P,
                Pd if p_drop > 0 else None, int(bf))
         # O[b,:,h] = Pd V
         L.gemm(mode=1, M=T, N=hd, K=T, A=Pd, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
@@ -437,7 +451,7 @@ class FastSpeech2(nn.Module):
             L.gemm(mode=2, M=T, N=hd, K=T, A=sv.Pd, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
                    B=dO_act, B_off=PAD * D, ldb=D, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * D, batch1=H, batch2=B,
                    Cout=dqkv, C_off=PAD * ld + 2 * D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
-            L.call("fs2_softmax_bwd", sv.P, dPd, lens, B, H, T, ldk, scale, p, sv.seeds[0], dS, int(bf))
+            L.call("fs2_softmax_bwd", sv.P, dPd, lens, B, H, T, ldk, scale, p, sv.seeds[0], self._ctr, dS, int(bf))
             # dQ = dS K ; dK = dS^T Q
             L.gemm(mode=1, M=T, N=hd, K=T, A=dS, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
                    B=sv.qkv, B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
@@ -515,11 +529,13 @@ class FastSpeech2(nn.Module):
             raise ValueError("intensity (B, Tp, 5) is required (reference model.py:356-358 concatenates it)")
         outs = _FS2Function.apply(self._anchor, self, tokens, speakers, durations, pitch, energy, float(pace),
                                   float(pitch_rate), float(energy_rate), intensity)
+        outs = outs[:7]
         mel, post, pd, pp, ap, pe, ae = outs
         has_p, has_e = pitch is not None, energy is not None
         return (mel, post, pd, pp, ap if has_p else None, pe, ae if has_e else None, self._last_mel_lens_cpu)
 
-    def _forward_impl(self, tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate, intensity):
+    def _forward_impl(self, tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate, intensity,
+                      Tm_known=None):
         st = self.store
         if not tokens.is_cuda:
             raise RuntimeError("fs2_b200: inputs must be CUDA tensors (there is no CPU fallback)")
@@ -533,7 +549,11 @@ class FastSpeech2(nn.Module):
         for a in self._arenas:
             a.reset(dev)
         self._generation += 1
+        if self._ctr is None or self._ctr.device != dev:
+            self._ctr = torch.zeros(1, dtype=torch.int64, device=dev)
         training = self.training
+        if training:
+            L.call("fs2_counter_add", self._ctr, 1)
         bf = self._bf16
         D, n_mels = self.D, self.n_mels
         st.pack(bf)
@@ -544,7 +564,7 @@ class FastSpeech2(nn.Module):
         if Tp <= PAD:
             raise ValueError("fs2_b200: need more than 4 phoneme positions (reflect padding of the k=9 conv, as torch)")
         rowsP = B * (Tp + 2 * PAD)
-        base_seed = (self._seed_base + 0x632BE59BD9B4E019 * self._generation) & _M64
+        base_seed = self._seed_base
         ctx = _Saved()
         ctx.generation = self._generation
         ctx.B, ctx.Tp = B, Tp
@@ -563,9 +583,10 @@ class FastSpeech2(nn.Module):
         if durations is not None:
             durations = durations.contiguous().long()
             L.call("fs2_lr_prepare", durations, None, pace, B, Tp, ends, mel_lens)
-            self._pin_lens[:B].copy_(mel_lens, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
+            if Tm_known is None:
+                self._pin_lens[:B].copy_(mel_lens, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
 
         # ---- encoder (model.py:331-347)
         src_lens = self._i32(B)
@@ -629,15 +650,18 @@ class FastSpeech2(nn.Module):
             self._pin_lens[:B].copy_(mel_lens, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
-        ev.synchronize()
-        mel_lens_cpu = self._pin_lens[:B].to(torch.int64).clone()
-        Tm = int(mel_lens_cpu.max())
+        if Tm_known is None:
+            ev.synchronize()
+            mel_lens_cpu = self._pin_lens[:B].to(torch.int64).clone()
+            Tm = int(mel_lens_cpu.max())
+            self._last_mel_lens_cpu = mel_lens_cpu
+        else:
+            Tm = Tm_known
         if Tm > 2500:
             raise ValueError("fs2_b200: more than 2500 frames (the positional table of the reference ends there)")
         if Tm <= PAD:
             raise ValueError("fs2_b200: need more than 4 mel frames (reflect padding of the k=9 conv, as torch)")
         ctx.Tm = Tm
-        self._last_mel_lens_cpu = mel_lens_cpu
         rowsM = B * (Tm + 2 * PAD)
         d0_f32, d0_act = self._f32(rowsM, D), self._act(rowsM, D)
         L.call("fs2_lr_expand", ae_f32, Tp + 2 * PAD, PAD, ends, mel_lens, pe_dec, B, Tp, Tm, D, d0_f32, d0_act, int(bf),
@@ -704,15 +728,16 @@ class FastSpeech2(nn.Module):
         return outs, ctx
 
     # -------------------------------------------------------------------------- backward
-    def _backward_impl(self, ctx, dmel, dpost, dpd, dpp, dpe):
-        if ctx.generation != self._generation:
+    def _backward_impl(self, ctx, dmel, dpost, dpd, dpp, dpe, capturing=False):
+        if not capturing and ctx.generation != self._generation:
             raise RuntimeError("fs2_b200: backward() of a forward whose workspace has been reused by a later forward; "
                                "call backward before the next forward of the same model")
         if not (ctx.teacher and ctx.has_targets):
             raise NotImplementedError("fs2_b200: backward needs teacher-forced durations, pitch and energy "
                                       "(the reference's training call, train.py:72)")
         st = self.store
-        st.ensure_grads()
+        if not capturing:
+            st.ensure_grads()
         bf = self._bf16
         D, n_mels, E = self.D, self.n_mels, self.E
         B, Tp, Tm = ctx.B, ctx.Tp, ctx.Tm
@@ -802,15 +827,110 @@ class FastSpeech2(nn.Module):
                self._G("encPreNet.token_embedding.Embedding.weight"))
 
 
+    # ---------------------------------------------------------------------- CUDA graphs
+    def _graph_eligible(self, durations, pitch, energy):
+        return self.use_cuda_graphs and durations is not None and pitch is not None and energy is not None \
+            and self.trace is None
+
+    def _probe_Tm(self, durations, pace, B, Tp):
+        """Eager duration scan + the step's single host read-back (mel_lens)."""
+        dev = durations.device
+        if self._pre is None or self._pre[0].numel() < B * Tp or self._pre[0].device != dev:
+            self._pre = (torch.zeros(max(B * Tp, 64 * 128), dtype=torch.int32, device=dev),
+                         torch.zeros(max(B, 64), dtype=torch.int32, device=dev))
+        if self._pin_lens is None or self._pin_lens.numel() < B:
+            self._pin_lens = torch.empty(max(B, 64), dtype=torch.int32).pin_memory()
+        L.call("fs2_lr_prepare", durations, None, pace, B, Tp, self._pre[0], self._pre[1])
+        self._pin_lens[:B].copy_(self._pre[1][:B], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        mel_lens_cpu = self._pin_lens[:B].to(torch.int64).clone()
+        self._last_mel_lens_cpu = mel_lens_cpu
+        return int(mel_lens_cpu.max())
+
+    def _graph_forward(self, tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate, intensity):
+        """Returns (outs, ctx, entry).  First sight of a shape runs eagerly (sizes the arenas, configures the
+        kernels); the second captures forward and backward graphs; later steps copy the inputs into the static
+        slots and replay."""
+        tokens = tokens.contiguous().long()
+        durations = durations.contiguous().long()
+        B, Tp = tokens.shape
+        Tm = self._probe_Tm(durations, pace, B, Tp)
+        key = (B, Tp, Tm, pitch.shape[1], energy.shape[1], self.training, self.precision, pace, pitch_rate, energy_rate)
+        ins = (tokens, speakers.contiguous().long(), durations, pitch.contiguous().float(), energy.contiguous().float(),
+               intensity.contiguous().float())
+        entry = self._graphs.get(key)
+        if entry is None:
+            if key not in self._seen:
+                self._seen.add(key)
+                outs, ctx = self._forward_impl(tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate,
+                                               intensity, Tm_known=Tm)
+                return outs, ctx, None
+            entry = self._capture(key, ins, Tm, pace, pitch_rate, energy_rate)
+        else:
+            for dst, src in zip(entry.static_in, ins):
+                dst.copy_(src, non_blocking=True)
+        self._generation += 1
+        entry.ctx.generation = self._generation
+        entry.fwd.replay()
+        self.replayed_launches += entry.n_fwd
+        return entry.outs, entry.ctx, entry
+
+    def _capture(self, key, ins, Tm, pace, pitch_rate, energy_rate):
+        st = self.store
+        st.ensure_grads()
+        assert self._ctr is not None and self._arenas is not None      # an eager step of this shape came first
+        for a in self._arenas:
+            a.reset(ins[0].device)          # any regrowth happens here, outside the capture
+        entry = _Saved()
+        entry.static_in = [t.clone() for t in ins]
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
+        with torch.cuda.graph(g):
+            outs, ctx = self._forward_impl(*entry.static_in[:3], entry.static_in[3], entry.static_in[4], pace, pitch_rate,
+                                           energy_rate, entry.static_in[5], Tm_known=Tm)
+        entry.fwd, entry.outs, entry.ctx = g, outs, ctx
+        entry.n_fwd = L.launch_count() - n0
+        n0 = L.launch_count()
+        entry.arena_bufs = [a.buf for a in self._arenas]
+        entry.grad_in = [torch.zeros_like(outs[i]) for i in (0, 1, 2, 3, 5)]
+        gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb):
+            self._backward_impl(ctx, *entry.grad_in, capturing=True)
+        entry.bwd = gb
+        entry.n_bwd = L.launch_count() - n0
+        self._graphs[key] = entry
+        return entry
+
+
 class _FS2Function(torch.autograd.Function):
     @staticmethod
     def forward(fctx, anchor, model, tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate, intensity):
-        outs, ctx = model._forward_impl(tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate, intensity)
-        fctx.model, fctx.ctx = model, ctx
+        entry = None
+        if model._graph_eligible(durations, pitch, energy):
+            outs, ctx, entry = model._graph_forward(tokens, speakers, durations, pitch, energy, pace, pitch_rate,
+                                                    energy_rate, intensity)
+        else:
+            outs, ctx = model._forward_impl(tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate,
+                                            intensity)
+        fctx.model, fctx.ctx, fctx.entry = model, ctx, entry
+        if entry is not None:
+            # static graph outputs: hand out views so autograd sees fresh tensors each step
+            outs = tuple(o.view_as(o) for o in outs)
         fctx.mark_non_differentiable(outs[4], outs[6])
         return outs
 
     @staticmethod
     def backward(fctx, dmel, dpost, dpd, dpp, dap, dpe, dae):
-        fctx.model._backward_impl(fctx.ctx, dmel, dpost, dpd, dpp, dpe)
+        model, entry = fctx.model, fctx.entry
+        if entry is None:
+            model._backward_impl(fctx.ctx, dmel, dpost, dpd, dpp, dpe)
+        else:
+            if fctx.ctx.generation != model._generation:
+                raise RuntimeError("fs2_b200: backward() of a forward whose workspace has been reused by a later forward")
+            model.store.ensure_grads()
+            for dst, src in zip(entry.grad_in, (dmel, dpost, dpd, dpp, dpe)):
+                dst.copy_(src.reshape(dst.shape), non_blocking=True)
+            entry.bwd.replay()
+            model.replayed_launches += entry.n_bwd
         return (torch.zeros(1, device=dmel.device),) + (None,) * 10

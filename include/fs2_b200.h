@@ -93,6 +93,7 @@ typedef struct {
   float* out_f32; void* out_act; int act_bf16; int halo;
   float* mean; float* rstd;                 /* [rows] saved statistics (may be NULL) */
   const float* head_w; const float* head_b; float* head_out; float head_scale; /* head_out is (B,T) plain */
+  const unsigned long long* seed_dev;       /* optional device counter mixed into both dropout seeds (CUDA-graph replay) */
 } Fs2LnFwd;
 int fs2_ln_fwd(const Fs2LnFwd* p, void* stream);
 
@@ -112,6 +113,7 @@ typedef struct {
   int relu_x;
   float* dx_f32; void* dact; int act_bf16;
   float* dgamma; float* dbeta; float* dhead_w; float* dhead_b;   /* accumulated (+=) */
+  const unsigned long long* seed_dev;
 } Fs2LnBwd;
 int fs2_ln_bwd(const Fs2LnBwd* p, void* stream);
 
@@ -119,9 +121,13 @@ int fs2_ln_bwd(const Fs2LnBwd* p, void* stream);
  * keys valid for (b,h) are [0, min(len[b], len[(b*H+h) % B])).  S (B*H, T, ldk) fp32 -> P (and Pd = dropout(P)
  * when drop_p > 0).  P = softmax(scale*S); columns >= kv are written as 0. */
 int fs2_softmax_fwd(const float* S, const int* lens, int B, int H, int T, int ldk, float scale,
-                    float drop_p, unsigned long long seed, void* P, void* Pd, int act_bf16, void* stream);
+                    float drop_p, unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd,
+                    int act_bf16, void* stream);
 int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens, int B, int H, int T, int ldk, float scale,
-                    float drop_p, unsigned long long seed, void* dS, int act_bf16, void* stream);
+                    float drop_p, unsigned long long seed, const unsigned long long* seed_dev, void* dS, int act_bf16,
+                    void* stream);
+/* *ctr += inc (the device-side dropout step counter; first node of a captured forward graph) */
+int fs2_counter_add(unsigned long long* ctr, unsigned long long inc, void* stream);
 
 /* model.py:352-360 speaker/intensity conditioning, split-weight form (no cat):
  * y = (G + Ws.spk_emb[spk[b]] + Wi.intensity[b,t]) * mask ; G = token_feats.Wt^T (a GEMM).

@@ -233,7 +233,7 @@ def test_softmax_mask_quirk(lib):
     S = randn(B * H, T, ldk, seed=2)
     P = torch.full((B * H, T, ldk), float("nan"), device="cuda")
     scale = 1 / math.sqrt(192)
-    lib.call("fs2_softmax_fwd", S, lens, B, H, T, ldk, scale, 0.0, 0, P, None, 0)
+    lib.call("fs2_softmax_fwd", S, lens, B, H, T, ldk, scale, 0.0, 0, None, P, None, 0)
     pad = torch.arange(T, device="cuda")[None, :] >= lens[:, None]
     ref = torch.zeros(B * H, T, ldk, device="cuda")
     for b in range(B):
@@ -245,7 +245,7 @@ def test_softmax_mask_quirk(lib):
     dP = randn(B * H, T, ldk, seed=3)
     Pr = ref.clone().requires_grad_()
     dS = torch.empty_like(P)
-    lib.call("fs2_softmax_bwd", P, dP, lens, B, H, T, ldk, scale, 0.0, 0, dS, 0)
+    lib.call("fs2_softmax_bwd", P, dP, lens, B, H, T, ldk, scale, 0.0, 0, None, dS, 0)
     Sr = S.clone().requires_grad_()
     out = torch.zeros_like(ref)
     for b in range(B):

@@ -164,11 +164,9 @@ def test_train_mode_dropout_runs_and_is_seeded(pkg, oracle64):
     c = torch.load(os.path.join(GOLD, "synthetic_b4.pt"))["case"]
     model = build_model(pkg, oracle64, "bf16").train()
     model.manual_seed(7)
-    model._generation = 0
     p1, l1 = run_model(pkg, model, c)
     g1 = model.store.flat_grad.clone()
     model.manual_seed(7)
-    model._generation = 0
     p2, l2 = run_model(pkg, model, c)
     assert torch.equal(p1[0], p2[0]) and torch.equal(p1[1], p2[1])                                 # same seed, same masks
     assert abs(float(l1["total_loss"]) - float(l2["total_loss"])) <= 1e-5 * abs(float(l1["total_loss"]))   # atomics order only
@@ -179,6 +177,28 @@ def test_train_mode_dropout_runs_and_is_seeded(pkg, oracle64):
     pe_, le = run_model(pkg, model, c, with_grad=False)
     # train-mode loss is a noisy version of the eval loss (dropout 0.1/0.5): same order of magnitude
     assert 0.5 < float(l1["total_loss"]) / float(le["total_loss"]) < 2.0
+
+
+def test_cuda_graph_replay_matches_eager(pkg, oracle64):
+    """use_cuda_graphs: eager first step, capture on the second, replay afterwards -- same outputs and gradients
+    as the eager path (eval mode; bf16 forward is deterministic, gradients differ only by atomics order)."""
+    c = torch.load(os.path.join(GOLD, "synthetic_b4.pt"))["case"]
+    eager = build_model(pkg, oracle64, "bf16")
+    pe_, le = run_model(pkg, eager, c)
+    g_e = eager.store.flat_grad.clone()
+    graphed = build_model(pkg, oracle64, "bf16")
+    graphed.use_cuda_graphs = True
+    for step in range(4):
+        pg, lg = run_model(pkg, graphed, c)
+        assert torch.equal(pg[0], pe_[0]) and torch.equal(pg[1], pe_[1]) and torch.equal(pg[7], pe_[7])
+        assert abs(float(lg["total_loss"]) - float(le["total_loss"])) <= 1e-5 * abs(float(le["total_loss"]))
+        rl2 = ((graphed.store.flat_grad - g_e).norm() / g_e.norm()).item()
+        assert rl2 <= 1e-4, (step, rl2)
+    assert len(graphed._graphs) == 1
+    # train mode under replay: the device-side counter gives every step fresh dropout masks
+    graphed.train()
+    outs = [run_model(pkg, graphed, c)[0][0].clone() for _ in range(4)]
+    assert not torch.equal(outs[2], outs[3])
 
 
 def test_backward_guard_and_grad_accumulation(pkg, oracle64):

@@ -70,7 +70,7 @@ def main():
     fa = 2.0 * B * H * T * T * (D // H)
     hd, TP, ld = D // H, T + 2 * PAD, 3 * D
     rec("attn QK^T", fa, timeit(lambda i: L.gemm(mode=0, M=T, N=T, K=hd, A=qkv[i % R], A_off=PAD * ld, lda=ld, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * ld, B=qkv[i % R], B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B, Cout=S[i % 2], ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=True)))
-    rec("attn softmax fwd (bytes GB/s)", 0.0, timeit(lambda i: L.call("fs2_softmax_fwd", S[i % 2], lens, B, H, T, ldk, 0.07, 0.0, 0, P[i % 2], None, 1)))
+    rec("attn softmax fwd (bytes GB/s)", 0.0, timeit(lambda i: L.call("fs2_softmax_fwd", S[i % 2], lens, B, H, T, ldk, 0.07, 0.0, 0, None, P[i % 2], None, 1)))
     rec("attn PV", fa, timeit(lambda i: L.gemm(mode=1, M=T, N=hd, K=T, A=P[i % 2], lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk, B=qkv[i % R], B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B, Cout=xD[i % R], C_off=PAD * D, ldc=D, c_s1=hd, c_s2=TP * D, c_bf16=True, ab_bf16=True)))
     rec("attn dV = P^T dO", fa, timeit(lambda i: L.gemm(mode=2, M=T, N=hd, K=T, A=P[i % 2], lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk, B=xD[i % R], B_off=PAD * D, ldb=D, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * D, batch1=H, batch2=B, Cout=qkv[i % R], C_off=PAD * ld + 2 * D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=True, ab_bf16=True)))
     fp = 2.0 * rows * E * E * 5
