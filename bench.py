@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-mel-lens", action="store_true", help="read mel_lens back synchronously every step (the reference's contract)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -248,6 +249,7 @@ def main():
     torch.manual_seed(0)
     model = pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4, precision=args.precision).to(dev).train()
     model.use_cuda_graphs = not args.no_graphs
+    model.async_mel_lens = not args.sync_mel_lens
     crit = pkg.Loss(**pkg.DEFAULT_LOSS_CONFIG)
     opt = pkg.FusedAdamW(model, lr=1e-4)
     trainer = par.DataParallelStep(model, crit, opt)
@@ -324,6 +326,7 @@ def main():
                    "padded_shapes_Tp_Tm": shapes, "parallelism": f"dp{world}",
                    "l2_policy": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed",
                    "dropout": "on (train mode, counter-based masks)",
+                   "mel_lens": "async (pinned, Tm = pitch.shape[1], device-side check)" if model.async_mel_lens else "synchronous read-back",
                    "launch": "CUDA-graph replay per (B,Tp,Tm) shape" if model.use_cuda_graphs else "eager launches from Python"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 4 * BATCH,
                 "ms_per_step": ms_e / args.steps,

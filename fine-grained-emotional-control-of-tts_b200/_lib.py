@@ -37,6 +37,7 @@ SIGNATURES = {
     "fs2_embed_add_bwd": "ppiiiippp",
     "fs2_dur_decode": "pqpp",
     "fs2_lr_prepare": "ppfiippp",
+    "fs2_lr_finalize": "piippp",
     "fs2_lr_expand": "piipppiiiippiiipp",
     "fs2_lr_bwd": "ppiippiiiipiip",
     "fs2_fold_halo": "piiiipppppip",

@@ -661,6 +661,18 @@ __global__ void lr_prepare_kernel(const int64_t* dur, const float* fdur, float p
   if (lane == 0) mel_lens[b] = carry;
 }
 
+// mel_lens -> int64 copy for the host + a check that the caller-supplied frame count equals max(mel_lens)
+__global__ void lr_finalize_kernel(const int* mel_lens, int B, int Tm_expected, long long* out_i64, int* flag) {
+  int mx = 0;
+  for (int b = threadIdx.x; b < B; b += 32) {
+    int v = mel_lens[b];
+    out_i64[b] = v;
+    mx = max(mx, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (threadIdx.x == 0 && mx != Tm_expected) atomicExch(flag, mx == 0 ? -1 : mx);
+}
+
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) lr_expand_kernel(const float* in, int in_pitch, int in_off, const int* ends,
                                                             const int* mel_lens, const float* pe, int B, int Tp, int Tm,
@@ -1039,6 +1051,12 @@ extern "C" int fs2_lr_prepare(const int64_t* dur, const float* fdur, float pace,
                               void* stream) {
   REQUIRE((dur || fdur) && ends && mel_lens, "fs2_lr_prepare: null pointer");
   lr_prepare_kernel<<<B, 32, 0, ST>>>(dur, fdur, pace, B, Tp, ends, mel_lens);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_lr_finalize(const int* mel_lens, int B, int Tm_expected, long long* out_i64, int* flag, void* stream) {
+  REQUIRE(mel_lens && out_i64 && flag, "fs2_lr_finalize: null pointer");
+  lr_finalize_kernel<<<1, 32, 0, ST>>>(mel_lens, B, Tm_expected, out_i64, flag);
   return fs2_check_launch();
 }
 

@@ -173,6 +173,8 @@ class FastSpeech2(nn.Module):
         self._graphs = {}
         self._seen = set()
         self._pre = None
+        self.async_mel_lens = False   # opt-in: no host sync; Tm is taken from pitch.shape[1], mel_lens arrives in pinned memory
+        self._async_bufs = None
         self.replayed_launches = 0    # kernels launched through graph replays (fs2_launch_count only sees captures)
         self.trace = None        # set to a dict to collect unpadded intermediates (debug / parity tests)
         self._pin_lens = None
@@ -587,6 +589,12 @@ class FastSpeech2(nn.Module):
                 self._pin_lens[:B].copy_(mel_lens, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
+            elif self.async_mel_lens:
+                lens64, flag, pin64, pinflag = self._async_buffers(dev)
+                L.call("fs2_lr_finalize", mel_lens, B, Tm_known, lens64, flag)
+                pin64.copy_(lens64, non_blocking=True)
+                pinflag.copy_(flag, non_blocking=True)
+                self._last_mel_lens_cpu = pin64[:B]
 
         # ---- encoder (model.py:331-347)
         src_lens = self._i32(B)
@@ -832,6 +840,20 @@ class FastSpeech2(nn.Module):
         return self.use_cuda_graphs and durations is not None and pitch is not None and energy is not None \
             and self.trace is None
 
+    def _async_buffers(self, dev):
+        if self._async_bufs is None or self._async_bufs[0].device != dev:
+            self._async_bufs = (torch.zeros(256, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
+                                torch.zeros(256, dtype=torch.int64).pin_memory(), torch.zeros(1, dtype=torch.int32).pin_memory())
+        return self._async_bufs
+
+    def _check_async_flag(self):
+        if self._async_bufs is not None and int(self._async_bufs[3][0]) != 0:
+            got = int(self._async_bufs[3][0])
+            self._async_bufs[1].zero_()
+            self._async_bufs[3].zero_()
+            raise RuntimeError(f"fs2_b200: async_mel_lens: a previous batch had max(sum(durations)) = {got} frames, which is "
+                               "not pitch.shape[1]; its outputs were computed on the wrong rectangle")
+
     def _probe_Tm(self, durations, pace, B, Tp):
         """Eager duration scan + the step's single host read-back (mel_lens)."""
         dev = durations.device
@@ -854,7 +876,11 @@ class FastSpeech2(nn.Module):
         tokens = tokens.contiguous().long()
         durations = durations.contiguous().long()
         B, Tp = tokens.shape
-        Tm = self._probe_Tm(durations, pace, B, Tp)
+        if self.async_mel_lens and B <= 256:
+            self._check_async_flag()
+            Tm = int(pitch.shape[1])
+        else:
+            Tm = self._probe_Tm(durations, pace, B, Tp)
         key = (B, Tp, Tm, pitch.shape[1], energy.shape[1], self.training, self.precision, pace, pitch_rate, energy_rate)
         ins = (tokens, speakers.contiguous().long(), durations, pitch.contiguous().float(), energy.contiguous().float(),
                intensity.contiguous().float())
@@ -911,8 +937,12 @@ class _FS2Function(torch.autograd.Function):
             outs, ctx, entry = model._graph_forward(tokens, speakers, durations, pitch, energy, pace, pitch_rate,
                                                     energy_rate, intensity)
         else:
+            tm = None
+            if model.async_mel_lens and durations is not None and pitch is not None and tokens.shape[0] <= 256:
+                model._check_async_flag()
+                tm = int(pitch.shape[1])
             outs, ctx = model._forward_impl(tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate,
-                                            intensity)
+                                            intensity, Tm_known=tm)
         fctx.model, fctx.ctx, fctx.entry = model, ctx, entry
         if entry is not None:
             # static graph outputs: hand out views so autograd sees fresh tensors each step

@@ -163,6 +163,9 @@ int fs2_embed_add_bwd(const float* dy /*padded rows*/, const float* contour, int
  *                 the padded row space (pitch=T+8, off=4). */
 int fs2_dur_decode(const float* log_dur, long long n, float* fdur, void* stream);
 int fs2_lr_prepare(const int64_t* dur, const float* fdur, float pace, int B, int Tp, int* ends, int* mel_lens, void* stream);
+/* sync-free variant: the caller states Tm (= the padded frame axis of the batch); out_i64 = mel_lens as int64 for an
+ * asynchronous host copy, *flag is set (to the real maximum) when max(mel_lens) != Tm_expected */
+int fs2_lr_finalize(const int* mel_lens, int B, int Tm_expected, long long* out_i64, int* flag, void* stream);
 int fs2_lr_expand(const float* in, int in_pitch, int in_off, const int* ends, const int* mel_lens, const float* pe,
                   int B, int Tp, int Tm, int D, float* out_f32, void* out_act, int act_bf16,
                   int out_pitch, int out_off, int* frame2ph, void* stream);

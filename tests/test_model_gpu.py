@@ -201,6 +201,27 @@ def test_cuda_graph_replay_matches_eager(pkg, oracle64):
     assert not torch.equal(outs[2], outs[3])
 
 
+def test_async_mel_lens_has_no_host_sync_and_checks_the_hint(pkg, oracle64):
+    """async_mel_lens: Tm comes from pitch.shape[1]; mel_lens arrives in pinned memory (valid after a stream sync);
+    a batch whose max(sum(dur)) differs from the hint is reported at the next forward."""
+    c = torch.load(os.path.join(GOLD, "synthetic_b4.pt"))["case"]
+    ref = build_model(pkg, oracle64, "fp32")
+    p_ref, _ = run_model(pkg, ref, c, with_grad=False)
+    m = build_model(pkg, oracle64, "fp32")
+    m.async_mel_lens = True
+    p, _ = run_model(pkg, m, c, with_grad=False)           # run_model synchronises
+    assert torch.equal(p[0], p_ref[0]) and torch.equal(p[1], p_ref[1])
+    assert p[7].tolist() == p_ref[7].tolist() and p[7].dtype == torch.int64 and not p[7].is_cuda
+    bad = dict(c)
+    bad["pitch"] = torch.cat([c["pitch"], torch.zeros(4, 3)], 1)
+    bad["energy"] = torch.cat([c["energy"], torch.zeros(4, 3)], 1)
+    tokens, speakers, dur, pitch, energy, intensity, *_ = cuda_batch(bad)
+    m(tokens, speakers, dur, pitch, energy, intensity=intensity)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="async_mel_lens"):
+        run_model(pkg, m, c, with_grad=False)
+
+
 def test_backward_guard_and_grad_accumulation(pkg, oracle64):
     c = torch.load(os.path.join(GOLD, "docstring_case.pt"))["case"]
     model = build_model(pkg, oracle64, "fp32")
