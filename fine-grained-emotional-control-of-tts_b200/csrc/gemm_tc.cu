@@ -552,6 +552,25 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   p.kb_per_tap = (g.K + BK - 1) / BK;
   p.total_kb = (g.mode == 2) ? p.kb_per_tap : p.kb_per_tap * g.taps;
   p.nsplit = (g.mode == 2 && g.split_k > 1) ? g.split_k : 1;
+  if (g.mode == 2 && g.split_k <= 0) {
+    // auto split-K: the persistent grid walks tiles*split work items in waves of one item per SM; pick the split
+    // that minimises waves * (k-blocks per item + the atomic epilogue's cost in k-block units)
+    if (g_num_sms == 0) {
+      int dev = 0;
+      CUDA_CHECK_RET(cudaGetDevice(&dev));
+      CUDA_CHECK_RET(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long tiles = (long long)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.taps * g.batch1 * g.batch2;
+    const int epi_kb = 8;
+    long long best_cost = -1;
+    int best = 1;
+    for (int s = 1; s <= 64 && s <= p.total_kb; ++s) {
+      const long long waves = (tiles * s + g_num_sms - 1) / g_num_sms;
+      const long long cost = waves * ((p.total_kb + s - 1) / s + (s > 1 || g.accumulate ? epi_kb : epi_kb / 2));
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+    }
+    p.nsplit = best;
+  }
   if (p.nsplit > p.total_kb) p.nsplit = p.total_kb;
   p.kb_per_split = (p.total_kb + p.nsplit - 1) / p.nsplit;
   p.nsplit = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;

@@ -258,8 +258,7 @@ class FastSpeech2(nn.Module):
         w = self.store.pw(wname)
         rows = B * (T + 2 * PAD)
         p = (w.k - 1) // 2
-        tiles = ((w.cin + 127) // 128) * w.k * ((w.cout + 127) // 128)
-        split = max(1, min((rows + 63) // 64, 1184 // max(tiles, 1)))
+        split = 0            # auto: chosen by fs2_gemm_tc from the tile count and the SM count
         o, _ = self.store.offsets[wkey]
         src_ld = w.src_ld
         L.gemm(mode=2, M=w.cout, N=w.cin, K=rows, taps=w.k, A=dy, lda=w.cout, a_rows=rows, a_inner=w.cout,

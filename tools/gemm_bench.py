@@ -51,32 +51,37 @@ def main():
     lay = lambda i: f"decoder.layers.{i % 6}"
     res = []
 
-    def rec(name, flops, ms):
+    only = os.environ.get("ONLY")
+
+    def rec(name, flops, fn):
+        if only and only not in name:
+            return
+        ms = timeit(fn, iters=int(os.environ.get("ITERS", 10)), warm=int(os.environ.get("WARM", 3)))
         res.append((name, flops, ms))
         print(f"{name:34s} {ms*1e3:9.1f} us  {flops/ms/1e9:8.1f} TFLOP/s", flush=True)
 
     f9 = 2.0 * rows * Fd * D * 9
     f1 = 2.0 * rows * Fd * D
-    rec("fwd conv9 384->1536 relu bf16", f9, timeit(lambda i: m._conv(xD[i % R], B, T, lay(i) + ".pos_ffn.0.conv.weight", oF[i % R], c_bf16=True, bias=m._P(lay(i) + ".pos_ffn.0.conv.bias"), relu=1)))
-    rec("fwd conv1 1536->384 f32", f1, timeit(lambda i: m._conv(xF[i % R], B, T, lay(i) + ".pos_ffn.2.conv.weight", oD32[i % R], c_bf16=False, bias=m._P(lay(i) + ".pos_ffn.2.conv.bias"))))
-    rec("fwd qkv 384->1152 bf16", 2.0 * rows * 3 * D * D, timeit(lambda i: m._conv(xD[i % R], B, T, lay(i) + ".self_att.att.in_proj_weight", qkv[i % R], c_bf16=True)))
-    rec("fwd out_proj 384->384 f32", 2.0 * rows * D * D, timeit(lambda i: m._conv(xD[i % R], B, T, lay(i) + ".self_att.att.out_proj.weight", oD32[i % R], c_bf16=False)))
-    rec("dgrad conv9 1536->384 f32", f9, timeit(lambda i: m._conv_dgrad(xF[i % R], B, T, lay(i) + ".pos_ffn.0.conv.weight", oD32[i % R])))
-    rec("dgrad conv1 384->1536 bf16 relu_aux", f1, timeit(lambda i: m._conv_dgrad(xD[i % R], B, T, lay(i) + ".pos_ffn.2.conv.weight", oF[i % R], c_bf16=True, relu_aux=xF[(i + 1) % R])))
-    rec("dgrad qkv 1152->384 f32", 2.0 * rows * 3 * D * D, timeit(lambda i: m._conv_dgrad(qkv[i % R], B, T, lay(i) + ".self_att.att.in_proj_weight", oD32[i % R])))
-    rec("wgrad conv9 (+colsum)", f9, timeit(lambda i: m._conv_wgrad(xF[i % R], xD[i % R], B, T, lay(i) + ".pos_ffn.0.conv.weight", lay(i) + ".pos_ffn.0.conv.weight", lay(i) + ".pos_ffn.0.conv.bias")))
-    rec("wgrad conv1 (+colsum)", f1, timeit(lambda i: m._conv_wgrad(xD[i % R], xF[i % R], B, T, lay(i) + ".pos_ffn.2.conv.weight", lay(i) + ".pos_ffn.2.conv.weight", lay(i) + ".pos_ffn.2.conv.bias")))
-    rec("wgrad qkv (+colsum)", 2.0 * rows * 3 * D * D, timeit(lambda i: m._conv_wgrad(qkv[i % R], xD[i % R], B, T, lay(i) + ".self_att.att.in_proj_weight", lay(i) + ".self_att.att.in_proj_weight", lay(i) + ".self_att.att.in_proj_bias")))
+    rec("fwd conv9 384->1536 relu bf16", f9, (lambda i: m._conv(xD[i % R], B, T, lay(i) + ".pos_ffn.0.conv.weight", oF[i % R], c_bf16=True, bias=m._P(lay(i) + ".pos_ffn.0.conv.bias"), relu=1)))
+    rec("fwd conv1 1536->384 f32", f1, (lambda i: m._conv(xF[i % R], B, T, lay(i) + ".pos_ffn.2.conv.weight", oD32[i % R], c_bf16=False, bias=m._P(lay(i) + ".pos_ffn.2.conv.bias"))))
+    rec("fwd qkv 384->1152 bf16", 2.0 * rows * 3 * D * D, (lambda i: m._conv(xD[i % R], B, T, lay(i) + ".self_att.att.in_proj_weight", qkv[i % R], c_bf16=True)))
+    rec("fwd out_proj 384->384 f32", 2.0 * rows * D * D, (lambda i: m._conv(xD[i % R], B, T, lay(i) + ".self_att.att.out_proj.weight", oD32[i % R], c_bf16=False)))
+    rec("dgrad conv9 1536->384 f32", f9, (lambda i: m._conv_dgrad(xF[i % R], B, T, lay(i) + ".pos_ffn.0.conv.weight", oD32[i % R])))
+    rec("dgrad conv1 384->1536 bf16 relu_aux", f1, (lambda i: m._conv_dgrad(xD[i % R], B, T, lay(i) + ".pos_ffn.2.conv.weight", oF[i % R], c_bf16=True, relu_aux=xF[(i + 1) % R])))
+    rec("dgrad qkv 1152->384 f32", 2.0 * rows * 3 * D * D, (lambda i: m._conv_dgrad(qkv[i % R], B, T, lay(i) + ".self_att.att.in_proj_weight", oD32[i % R])))
+    rec("wgrad conv9 (+colsum)", f9, (lambda i: m._conv_wgrad(xF[i % R], xD[i % R], B, T, lay(i) + ".pos_ffn.0.conv.weight", lay(i) + ".pos_ffn.0.conv.weight", lay(i) + ".pos_ffn.0.conv.bias")))
+    rec("wgrad conv1 (+colsum)", f1, (lambda i: m._conv_wgrad(xD[i % R], xF[i % R], B, T, lay(i) + ".pos_ffn.2.conv.weight", lay(i) + ".pos_ffn.2.conv.weight", lay(i) + ".pos_ffn.2.conv.bias")))
+    rec("wgrad qkv (+colsum)", 2.0 * rows * 3 * D * D, (lambda i: m._conv_wgrad(qkv[i % R], xD[i % R], B, T, lay(i) + ".self_att.att.in_proj_weight", lay(i) + ".self_att.att.in_proj_weight", lay(i) + ".self_att.att.in_proj_bias")))
     fa = 2.0 * B * H * T * T * (D // H)
     hd, TP, ld = D // H, T + 2 * PAD, 3 * D
-    rec("attn QK^T", fa, timeit(lambda i: L.gemm(mode=0, M=T, N=T, K=hd, A=qkv[i % R], A_off=PAD * ld, lda=ld, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * ld, B=qkv[i % R], B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B, Cout=S[i % 2], ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=True)))
-    rec("attn softmax fwd (bytes GB/s)", 0.0, timeit(lambda i: L.call("fs2_softmax_fwd", S[i % 2], lens, B, H, T, ldk, 0.07, 0.0, 0, None, P[i % 2], None, 1)))
-    rec("attn PV", fa, timeit(lambda i: L.gemm(mode=1, M=T, N=hd, K=T, A=P[i % 2], lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk, B=qkv[i % R], B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B, Cout=xD[i % R], C_off=PAD * D, ldc=D, c_s1=hd, c_s2=TP * D, c_bf16=True, ab_bf16=True)))
-    rec("attn dV = P^T dO", fa, timeit(lambda i: L.gemm(mode=2, M=T, N=hd, K=T, A=P[i % 2], lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk, B=xD[i % R], B_off=PAD * D, ldb=D, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * D, batch1=H, batch2=B, Cout=qkv[i % R], C_off=PAD * ld + 2 * D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=True, ab_bf16=True)))
+    rec("attn QK^T", fa, (lambda i: L.gemm(mode=0, M=T, N=T, K=hd, A=qkv[i % R], A_off=PAD * ld, lda=ld, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * ld, B=qkv[i % R], B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B, Cout=S[i % 2], ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=True)))
+    rec("attn softmax fwd (bytes GB/s)", 0.0, (lambda i: L.call("fs2_softmax_fwd", S[i % 2], lens, B, H, T, ldk, 0.07, 0.0, 0, None, P[i % 2], None, 1)))
+    rec("attn PV", fa, (lambda i: L.gemm(mode=1, M=T, N=hd, K=T, A=P[i % 2], lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk, B=qkv[i % R], B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B, Cout=xD[i % R], C_off=PAD * D, ldc=D, c_s1=hd, c_s2=TP * D, c_bf16=True, ab_bf16=True)))
+    rec("attn dV = P^T dO", fa, (lambda i: L.gemm(mode=2, M=T, N=hd, K=T, A=P[i % 2], lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk, B=xD[i % R], B_off=PAD * D, ldb=D, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * D, batch1=H, batch2=B, Cout=qkv[i % R], C_off=PAD * ld + 2 * D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=True, ab_bf16=True)))
     fp = 2.0 * rows * E * E * 5
-    rec("postnet conv5 512->512 bf16", fp, timeit(lambda i: m._conv(xE[i % R], B, T, f"postnet.convs_intermedite.{i % 3}.conv.weight", oE[i % R], c_bf16=True, halo=2)))
-    rec("postnet dgrad conv5", fp, timeit(lambda i: m._conv_dgrad(xE[i % R], B, T, f"postnet.convs_intermedite.{i % 3}.conv.weight", o32E[i % 2])))
-    rec("postnet wgrad conv5", fp, timeit(lambda i: m._conv_wgrad(xE[i % R], xE[(i + 1) % R], B, T, f"postnet.convs_intermedite.{i % 3}.conv.weight", f"postnet.convs_intermedite.{i % 3}.conv.weight", f"postnet.convs_intermedite.{i % 3}.conv.bias")))
+    rec("postnet conv5 512->512 bf16", fp, (lambda i: m._conv(xE[i % R], B, T, f"postnet.convs_intermedite.{i % 3}.conv.weight", oE[i % R], c_bf16=True, halo=2)))
+    rec("postnet dgrad conv5", fp, (lambda i: m._conv_dgrad(xE[i % R], B, T, f"postnet.convs_intermedite.{i % 3}.conv.weight", o32E[i % 2])))
+    rec("postnet wgrad conv5", fp, (lambda i: m._conv_wgrad(xE[i % R], xE[(i + 1) % R], B, T, f"postnet.convs_intermedite.{i % 3}.conv.weight", f"postnet.convs_intermedite.{i % 3}.conv.weight", f"postnet.convs_intermedite.{i % 3}.conv.bias")))
     tot = sum(r[2] for r in res)
     print("flag", L.gemm_tc_error_flag())
 
