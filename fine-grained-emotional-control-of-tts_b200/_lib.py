@@ -207,3 +207,19 @@ def gemm(*, mode, M, N, K, A, lda, a_rows, a_inner, B, ldb, b_rows, b_inner, Cou
 
 def gemm_tc_error_flag():
     return int(load().fs2_gemm_tc_error_flag())
+
+
+def gemm_tc_tune(pair=2, cfg=-1):
+    """Measurement hook: kernel / tile selection of fs2_gemm_tc (see include/fs2_b200.h)."""
+    lib = load()
+    lib.fs2_gemm_tc_tune.argtypes = [C.c_int, C.c_int]
+    lib.fs2_gemm_tc_tune.restype = C.c_int
+    check(lib.fs2_gemm_tc_tune(int(pair), int(cfg)), "fs2_gemm_tc_tune")
+
+
+def gemm_tc_set_debug(buf):
+    """buf: int64 CUDA tensor of >= 2 elements, or None to switch the clock probe off."""
+    lib = load()
+    lib.fs2_gemm_tc_set_debug.argtypes = [C.c_void_p]
+    lib.fs2_gemm_tc_set_debug.restype = C.c_int
+    check(lib.fs2_gemm_tc_set_debug(C.c_void_p(buf.data_ptr()) if buf is not None else None), "fs2_gemm_tc_set_debug")

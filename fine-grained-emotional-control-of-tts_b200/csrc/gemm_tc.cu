@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -39,6 +40,8 @@ struct TcParams {
   int m_tiles, n_tiles_total, total_tiles;
   int pa[4], pb[4];   // tensor-map dim slot of (inner,row,i1,i2) for A and B
   int* err;
+  long long* dbg;     // optional: {SM cycles, nanoseconds} of unit 0's lifetime (clock probe for measurements)
+  int dbg_mode;       // measurements only (results are garbage): 1 = MMA issue without TMA, 2 = TMA without MMA
 };
 
 __device__ int g_tc_error = 0;
@@ -94,12 +97,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
 }
 __device__ __forceinline__ void tma_issue(uint32_t dst, const CUtensorMap* tm, uint32_t bar, const int* perm, int inner,
                                           int row, int i1, int i2) {
-  int c[4];
-  c[perm[0]] = inner;
-  c[perm[1]] = row;
-  c[perm[2]] = i1;
-  c[perm[3]] = i2;
-  tma_load_4d(dst, tm, bar, c[0], c[1], c[2], c[3]);
+  const int p1 = perm[1], p2 = perm[2];
+  const int c1 = (p1 == 1) ? row : (p2 == 1) ? i1 : i2;
+  const int c2 = (p1 == 2) ? row : (p2 == 2) ? i1 : i2;
+  const int c3 = (p1 == 3) ? row : (p2 == 3) ? i1 : i2;
+  tma_load_4d(dst, tm, bar, inner, c1, c2, c3);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -139,6 +141,168 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+
+// ------------------------------------------------------------------ CTA-pair (cta_group::2) helpers --
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load whose completion bytes are credited to an mbarrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t cluster_bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+template <int NCTA>
+__device__ __forceinline__ void tma_issue_x(uint32_t dst, const CUtensorMap* tm, uint32_t bar, const int* perm, int inner,
+                                            int row, int i1, int i2) {
+  // perm[0] is always 0 (the contiguous dimension); select the rest without a dynamically indexed (local-memory) array
+  const int p1 = perm[1], p2 = perm[2];
+  const int c1 = (p1 == 1) ? row : (p2 == 1) ? i1 : i2;
+  const int c2 = (p1 == 2) ? row : (p2 == 2) ? i1 : i2;
+  const int c3 = (p1 == 3) ? row : (p2 == 3) ? i1 : i2;
+  if (NCTA == 2) tma_load_4d_pair(dst, tm, bar, inner, c1, c2, c3);
+  else tma_load_4d(dst, tm, bar, inner, c1, c2, c3);
+}
+template <int NCTA>
+__device__ __forceinline__ void umma_bf16_x(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  if (NCTA == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
+// MMA-completion arrive; in pair mode the same barrier offset is signalled in both CTAs
+template <int NCTA>
+__device__ __forceinline__ void umma_commit_x(uint32_t bar) {
+  if (NCTA == 2) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}
+
+// One 32-column accumulator chunk of one output row: scale/bias/ReLU/masks, then vector or scalar stores
+// (halo mirror rows included).  r[] holds the fp32 accumulators of columns [nb0, nb0+32).
+template <int MODE>
+__device__ __forceinline__ void epi_chunk(const Fs2Gemm& g, const EpiRow& er, const uint32_t* r, int nb0, long long col0,
+                                          long long cstr, bool atomic, bool vec_f32, bool vec_bf16) {
+  const bool full = (nb0 + 32 <= g.N);
+  if (full && (vec_f32 || vec_bf16)) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float x = __uint_as_float(r[i]) * g.alpha;
+      if (g.bias) x += g.bias[nb0 + i];
+      if (g.relu) x = fmaxf(x, 0.f);
+      v[i] = er.live ? x : 0.f;
+    }
+    if (g.relu_aux) {
+      if (g.aux_bf16) {
+        const uint4* ap = reinterpret_cast<const uint4*>((const bf16*)g.relu_aux + er.base + col0);
+        uint4 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = ap[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t w[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            if (!((w[j] & 0x8000u) == 0 && (w[j] & 0x7FFFu) != 0)) v[i * 8 + j * 2] = 0.f;
+            if (!((w[j] & 0x80000000u) == 0 && (w[j] & 0x7FFF0000u) != 0)) v[i * 8 + j * 2 + 1] = 0.f;
+          }
+        }
+      } else {
+        const float4* ap = reinterpret_cast<const float4*>((const float*)g.relu_aux + er.base + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 a = ap[i];
+          if (!(a.x > 0.f)) v[4 * i] = 0.f;
+          if (!(a.y > 0.f)) v[4 * i + 1] = 0.f;
+          if (!(a.z > 0.f)) v[4 * i + 2] = 0.f;
+          if (!(a.w > 0.f)) v[4 * i + 3] = 0.f;
+        }
+      }
+    }
+    if (vec_f32) {
+      float* dst = (float*)g.C + er.base + col0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const long long mo = mi ? er.mirror2 : er.mirror;
+        if (mo) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st4(dst + mo + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        }
+      }
+    } else {
+      bf16* dst = (bf16*)g.C + er.base + col0;
+      uint4 pk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+        pk[i].x = *reinterpret_cast<uint32_t*>(&h0);
+        pk[i].y = *reinterpret_cast<uint32_t*>(&h1);
+        pk[i].z = *reinterpret_cast<uint32_t*>(&h2);
+        pk[i].w = *reinterpret_cast<uint32_t*>(&h3);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = pk[i];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const long long mo = mi ? er.mirror2 : er.mirror;
+        if (mo) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst + mo)[i] = pk[i];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
+  }
 }
 
 template <int MODE, int BN, int STAGES>
@@ -317,88 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         }
         const int nb0 = n0 + c * 32;
         if (nb0 >= g.N || !row_ok || er.skip) continue;
-        const long long col0 = colbase + (long long)c * 32 * cstr;
-        const bool full = (nb0 + 32 <= g.N);
-        if (full && (vec_f32 || vec_bf16)) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(r[i]) * g.alpha;
-            if (g.bias) x += g.bias[nb0 + i];
-            if (g.relu) x = fmaxf(x, 0.f);
-            v[i] = er.live ? x : 0.f;
-          }
-          if (g.relu_aux) {
-            if (g.aux_bf16) {
-              const uint4* ap = reinterpret_cast<const uint4*>((const bf16*)g.relu_aux + er.base + col0);
-              uint4 a[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) a[i] = ap[i];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint32_t w[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                  if (!((w[j] & 0x8000u) == 0 && (w[j] & 0x7FFFu) != 0)) v[i * 8 + j * 2] = 0.f;
-                  if (!((w[j] & 0x80000000u) == 0 && (w[j] & 0x7FFF0000u) != 0)) v[i * 8 + j * 2 + 1] = 0.f;
-                }
-              }
-            } else {
-              const float4* ap = reinterpret_cast<const float4*>((const float*)g.relu_aux + er.base + col0);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float4 a = ap[i];
-                if (!(a.x > 0.f)) v[4 * i] = 0.f;
-                if (!(a.y > 0.f)) v[4 * i + 1] = 0.f;
-                if (!(a.z > 0.f)) v[4 * i + 2] = 0.f;
-                if (!(a.w > 0.f)) v[4 * i + 3] = 0.f;
-              }
-            }
-          }
-          if (vec_f32) {
-            float* dst = (float*)g.C + er.base + col0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi) {
-              const long long mo = mi ? er.mirror2 : er.mirror;
-              if (mo) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  st4(dst + mo + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-              }
-            }
-          } else {
-            bf16* dst = (bf16*)g.C + er.base + col0;
-            uint4 pk[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-              pk[i].x = *reinterpret_cast<uint32_t*>(&h0);
-              pk[i].y = *reinterpret_cast<uint32_t*>(&h1);
-              pk[i].z = *reinterpret_cast<uint32_t*>(&h2);
-              pk[i].w = *reinterpret_cast<uint32_t*>(&h3);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = pk[i];
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi) {
-              const long long mo = mi ? er.mirror2 : er.mirror;
-              if (mo) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst + mo)[i] = pk[i];
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
-        }
+        epi_chunk<MODE>(g, er, r, nb0, colbase + (long long)c * 32 * cstr, cstr, atomic, vec_f32, vec_bf16);
       }
     }
   }
@@ -408,6 +491,254 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
+  }
+}
+
+
+// =====================================================================================================
+// CTA-pair kernel: two SMs of one TPC (a 2-CTA cluster) compute one 256 x TILE_N tile with
+// tcgen05.mma.cta_group::2.  CTA r of the pair stages its own 128 A rows and ITS HALF of every B sub-tile
+// (BNS/2 columns), so per output element the L2 -> SM traffic is 1.5-2x lower than in the single-CTA kernel
+// (the single-CTA kernel is L2-fabric bound, see profiles/).  TILE_N = NSUB * BNS: up to three MMAs of N = BNS
+// share one A tile (N = 384 = 2 x 192 K-major or 3 x 128 MN-major); the accumulator is double-buffered in TMEM when
+// 2 * TILE_N <= 512 columns.  The leader CTA (rank 0) issues every MMA; completion is multicast to both CTAs'
+// barriers; both CTAs run their own TMA producer and epilogue warps.  NCTA = 1 gives the same tiling on one SM.
+template <int MODE, int BNS, int NSUB, int STAGES, int NCTA>
+__global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const TcParams p) {
+  constexpr int TILE_N = BNS * NSUB;
+  constexpr int BSUB_ROWS = BNS / NCTA;               // B rows (output columns) this CTA stages per sub-tile
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr int BSUB_BYTES = BSUB_ROWS * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + NSUB * BSUB_BYTES;
+  constexpr bool A_MN = (MODE == 2);
+  constexpr bool B_MN = (MODE != 0);
+  constexpr int ACC_BUFS = (2 * TILE_N <= 512) ? 2 : 1;
+  constexpr int TMEM_COLS = (ACC_BUFS * TILE_N <= 128) ? 128 : (ACC_BUFS * TILE_N <= 256) ? 256 : 512;
+  constexpr int CHUNKS_PER_HALF = TILE_N / 64;
+  static_assert(TILE_N % 64 == 0 && TILE_N <= 512, "tile width");
+  static_assert(BNS % 16 == 0 && BNS <= 256 && BSUB_ROWS % 8 == 0, "UMMA N");
+  static_assert(MODE == 0 || BSUB_ROWS % 64 == 0, "MN-major B is staged in 64-column boxes");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Fs2Gemm& g = p.g;
+  int* err = p.err;
+  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;
+  const int unit = (NCTA == 2) ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int nunits = (NCTA == 2) ? (int)cluster_count_x() : (int)gridDim.x;
+  long long dbg_c0 = 0;
+  uint64_t dbg_t0 = 0;
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { dbg_c0 = clock64(); dbg_t0 = globaltimer_ns(); }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);      // the leader's producer arrives once (+ the pair's transaction bytes)
+      mbar_init(smem_u32(&empty_bar[s]), 1);     // one MMA commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull_bar[s]), 1);
+      mbar_init(smem_u32(&tempty_bar[s]), NUM_EPI_WARPS * NCTA);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    if (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs of the pair)
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = p.dbg_mode != 1;
+      const int p1a = p.pa[1], p2a = p.pa[2], p1b = p.pb[1], p2b = p.pb[2];
+      const int pa_[4] = {0, p1a, p2a, 0}, pb_[4] = {0, p1b, p2b, 0};
+      for (int t = unit; t < p.total_tiles && ok; t += nunits) {
+        const int nt = t % p.n_tiles_total;
+        const int rest = t / p.n_tiles_total;
+        const int m0 = (rest % p.m_tiles) * (BM * NCTA) + (int)rank * BM;
+        const int z = rest / p.m_tiles;
+        const int zb = z / p.nsplit, zs = z % p.nsplit;
+        const int i1 = zb % g.batch1, i2 = zb / g.batch1;
+        int tapN = 0, n0 = nt * TILE_N;
+        if (MODE == 2) { tapN = nt / p.ntiles_per_tap; n0 = (nt % p.ntiles_per_tap) * TILE_N; }
+        const int kb_begin = zs * p.kb_per_split;
+        const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
+        // running (tap, k offset) of the current k-block: no division inside the loop
+        int j = (MODE == 2) ? 0 : kb_begin / p.kb_per_tap;
+        int kk = (MODE == 2) ? kb_begin * BK : (kb_begin - j * p.kb_per_tap) * BK;
+        const int kk_end = p.kb_per_tap * BK;
+        const int nbase = n0 + (int)rank * BSUB_ROWS;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, err)) { ok = false; break; }
+          const uint32_t fb_local = smem_u32(&full_bar[s]);
+          const uint32_t fb = (NCTA == 2) ? mapa_rank(fb_local, 0) : fb_local;   // bytes are credited to the leader
+          if (rank == 0) mbar_expect_tx(fb_local, STAGE_BYTES * NCTA);
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          if (MODE == 0 || MODE == 1) {
+            tma_issue_x<NCTA>(sa, &tmA, fb, pa_, kk, g.a_row_off + m0 + j * g.a_tap_step, i1, i2);
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+              const int nb = nbase + sub * BNS;
+              if (MODE == 0) {
+                tma_issue_x<NCTA>(sb + sub * BSUB_BYTES, &tmB, fb, pb_, j * g.b_tap_step + kk, nb, i1, i2);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BSUB_ROWS / 64; ++i)
+                  tma_issue_x<NCTA>(sb + sub * BSUB_BYTES + i * (BK * 128), &tmB, fb, pb_, nb + 64 * i + j * g.b_tap_step,
+                                    g.b_row_off + kk, i1, i2);
+              }
+            }
+            kk += BK;
+            if (kk >= kk_end) { kk = 0; ++j; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_issue_x<NCTA>(sa + i * (BK * 128), &tmA, fb, pa_, m0 + 64 * i, g.a_row_off + kk, i1, i2);
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+              const int nb = nbase + sub * BNS;
+#pragma unroll
+              for (int i = 0; i < BSUB_ROWS / 64; ++i)
+                tma_issue_x<NCTA>(sb + sub * BSUB_BYTES + i * (BK * 128), &tmB, fb, pb_, nb + 64 * i,
+                                  g.b_row_off + kk + tapN * g.b_tap_step, i1, i2);
+            }
+            kk += BK;
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only, one thread)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BNS >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
+      uint32_t tc = 0, ph = 0;
+      int s = 0;
+      bool ok = true;
+      for (int t = unit; t < p.total_tiles && ok; t += nunits, ++tc) {
+        const int z = (t / p.n_tiles_total) / p.m_tiles;
+        const int zs = z % p.nsplit;
+        const int kb_begin = zs * p.kb_per_split;
+        const int nkb = min(p.total_kb, kb_begin + p.kb_per_split) - kb_begin;
+        const uint32_t as = tc % ACC_BUFS, aph = (tc / ACC_BUFS) & 1;
+        if (!mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1, err)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * TILE_N;
+        for (int i = 0; i < nkb; ++i) {
+          if (p.dbg_mode != 1 && !mbar_wait(smem_u32(&full_bar[s]), ph, err)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            if (p.dbg_mode == 2) break;
+            const uint64_t ad = A_MN ? smem_desc(sa + k * 2048, BK * 128, 1024) : smem_desc(sa + k * 32, 16, 1024);
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+              const uint32_t sbs = sb + sub * BSUB_BYTES;
+              const uint64_t bd = B_MN ? smem_desc(sbs + k * 2048, BK * 128, 1024) : smem_desc(sbs + k * 32, 16, 1024);
+              umma_bf16_x<NCTA>(tmem_d + sub * BNS, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit_x<NCTA>(smem_u32(&empty_bar[s]));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (ok) umma_commit_x<NCTA>(smem_u32(&tfull_bar[as]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (both CTAs; own 128 rows of the tile)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const bool atomic = p.nsplit > 1 || g.accumulate;
+    const long long cstr = (MODE == 2 && g.c_col_stride > 1) ? g.c_col_stride : 1;
+    const bool al4 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 4 == 0) && (((uintptr_t)g.C) % 16 == 0);
+    const bool al8 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 8 == 0) && (((uintptr_t)g.C) % 16 == 0);
+    const bool aux_al = g.relu_aux == nullptr || (((uintptr_t)g.relu_aux) % 16 == 0);
+    uint32_t tc = 0;
+    bool ok = true;
+    for (int t = unit; t < p.total_tiles && ok; t += nunits, ++tc) {
+      const int nt = t % p.n_tiles_total;
+      const int rest = t / p.n_tiles_total;
+      const int m0 = (rest % p.m_tiles) * (BM * NCTA) + (int)rank * BM;
+      const int z = rest / p.m_tiles;
+      const int zb = z / p.nsplit;
+      const int i1 = zb % g.batch1, i2 = zb / g.batch1;
+      int tapN = 0, n0 = nt * TILE_N;
+      if (MODE == 2) { tapN = nt / p.ntiles_per_tap; n0 = (nt % p.ntiles_per_tap) * TILE_N; }
+      const uint32_t as = tc % ACC_BUFS, aph = (tc / ACC_BUFS) & 1;
+      const int m = m0 + q * 32 + lane;
+      EpiRow er;
+      const bool row_ok = (m < g.M);
+      if (row_ok) epi_row_setup(g, i1, i2, m, er);
+      const long long colbase = (MODE == 2) ? (long long)tapN * g.c_tap_stride + n0 * cstr : n0;
+      const bool vec_f32 = cstr == 1 && !g.c_bf16 && !atomic && al4 && (colbase % 4 == 0) && aux_al;
+      const bool vec_bf16 = cstr == 1 && g.c_bf16 && al8 && (colbase % 8 == 0) && aux_al;
+      if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, err)) { ok = false; break; }
+      tc_fence_after();
+#pragma unroll 1
+      for (int ci = 0; ci < CHUNKS_PER_HALF; ++ci) {
+        const int c = half * CHUNKS_PER_HALF + ci;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TILE_N + c * 32), r);
+        if (ci == CHUNKS_PER_HALF - 1) {
+          // this warp's TMEM reads are done: hand the accumulator buffer back to the (leader's) MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t tb = smem_u32(&tempty_bar[as]);
+            if (NCTA == 2 && rank != 0) mbar_arrive_cluster(mapa_rank(tb, 0));
+            else mbar_arrive(tb);
+          }
+        }
+        const int nb0 = n0 + c * 32;
+        if (nb0 >= g.N || !row_ok || er.skip) continue;
+        epi_chunk<MODE>(g, er, r, nb0, colbase + (long long)c * 32 * cstr, cstr, atomic, vec_f32, vec_bf16);
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();     // nobody leaves while the peer can still signal its barriers
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    p.dbg[0] = clock64() - dbg_c0;
+    p.dbg[1] = (long long)(globaltimer_ns() - dbg_t0);
+  }
+  if (warp == 1) {
+    if (NCTA == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
 
@@ -516,8 +847,9 @@ int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, TcParams& 
   return launch<MODE, 128, 6>(ta, tb, p, st);
 }
 
-// tile width: least padded columns, ties -> wider tile
-int pick_bn(int N) {
+// tile width: least padded columns, ties -> wider tile; when that leaves SMs without a tile (short M, e.g. the
+// phoneme-side GEMMs) fall back to 128-wide tiles
+int pick_bn(int N, long long m_tiles_x_batch) {
   int best = 128;
   long long best_pad = ((N + 127) / 128) * 128LL;
   const int cands[2] = {192, 256};
@@ -525,10 +857,144 @@ int pick_bn(int N) {
     long long pad = ((N + cands[i] - 1) / cands[i]) * (long long)cands[i];
     if (pad <= best_pad) { best_pad = pad; best = cands[i]; }
   }
+  if (best != 128 && g_num_sms > 0 && m_tiles_x_batch * ((N + best - 1) / best) < g_num_sms &&
+      ((N + 127) / 128) * 128LL <= best_pad + 64)
+    best = 128;
   return best;
 }
 
+
+template <int MODE, int BNS, int NSUB, int STAGES, int NCTA>
+int launch_x(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
+  constexpr int TILE_N = BNS * NSUB;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + NSUB * (BNS / NCTA) * BK * 2) + 1024 + 256;
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static int units = 0;       // CTA pairs (or CTAs) that can be resident at once
+  auto kern = tcx_gemm_kernel<MODE, BNS, NSUB, STAGES, NCTA>;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    CUDA_CHECK_RET(cudaGetDevice(&dev));
+    CUDA_CHECK_RET(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (units == 0) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    if (NCTA == 2) {
+      cfg.gridDim = dim3(g_num_sms / NCTA * NCTA, 1, 1);
+      int nc = 0;
+      CUDA_CHECK_RET(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
+      if (nc <= 0) { fs2_set_error("fs2_gemm_tc: no resident CTA pair possible"); return FS2_ERR_CUDA; }
+      units = nc < g_num_sms / NCTA ? nc : g_num_sms / NCTA;
+    } else {
+      units = g_num_sms;
+    }
+  }
+  p.ntiles_per_tap = (p.g.N + TILE_N - 1) / TILE_N;
+  p.n_tiles_total = (p.g.mode == 2) ? p.ntiles_per_tap * p.g.taps : p.ntiles_per_tap;
+  p.m_tiles = (p.g.M + BM * NCTA - 1) / (BM * NCTA);
+  const long long tiles = (long long)p.n_tiles_total * p.m_tiles * p.g.batch1 * p.g.batch2;
+  if (p.g.mode == 2 && p.g.split_k <= 0) {
+    // auto split-K: the persistent grid walks tiles*split work items in waves of one item per unit; pick the split
+    // that minimises waves * (k-blocks per item + the atomic epilogue's cost in k-block units)
+    const int epi_kb = 8;
+    long long best_cost = -1;
+    int best = 1;
+    for (int s = 1; s <= 64 && s <= p.total_kb; ++s) {
+      const long long waves = (tiles * s + units - 1) / units;
+      const long long cost = waves * ((p.total_kb + s - 1) / s + (s > 1 || p.g.accumulate ? epi_kb : epi_kb / 2));
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+    }
+    p.nsplit = best;
+    p.kb_per_split = (p.total_kb + p.nsplit - 1) / p.nsplit;
+    p.nsplit = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  }
+  const long long total = tiles * p.nsplit;
+  if (total > 0x7FFFFFFF) { fs2_set_error("fs2_gemm_tc: too many tiles"); return FS2_ERR_ARG; }
+  p.total_tiles = (int)total;
+  const int nunits = p.total_tiles < units ? p.total_tiles : units;
+  cfg.gridDim = dim3(nunits * NCTA, 1, 1);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  if (e != cudaSuccess) { fs2_set_error(cudaGetErrorString(e)); return FS2_ERR_CUDA; }
+  return fs2_check_launch();
+}
+
+// Tile configurations of the pair kernel: 0 = 256 x 256 (double-buffered accumulator), 1 = 256 x 384 (2 x 192
+// K-major B, or 3 x 128 MN-major B), 2 = 256 x 128.
+template <int MODE>
+int dispatch_x(int cfg, const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
+  if (cfg == 0) return launch_x<MODE, 256, 1, 6, 2>(ta, tb, p, st);
+  if (cfg == 1) {
+    if constexpr (MODE == 0) return launch_x<MODE, 192, 2, 5, 2>(ta, tb, p, st);
+    else return launch_x<MODE, 128, 3, 5, 2>(ta, tb, p, st);
+  }
+  return launch_x<MODE, 128, 1, 8, 2>(ta, tb, p, st);
+}
+
+// the same tilings on one SM (measurement only: isolates what the CTA pair buys)
+template <int MODE>
+int dispatch_x1(int cfg, const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
+  if (cfg == 0) return launch_x<MODE, 256, 1, 4, 1>(ta, tb, p, st);
+  if (cfg == 1) {
+    if constexpr (MODE == 0) return launch_x<MODE, 192, 2, 3, 1>(ta, tb, p, st);
+    else return launch_x<MODE, 128, 3, 3, 1>(ta, tb, p, st);
+  }
+  return launch_x<MODE, 128, 1, 6, 1>(ta, tb, p, st);
+}
+
+// per-CTA B box rows (mode 0) of a configuration
+int cfg_tile_n(int cfg) { return cfg == 0 ? 256 : cfg == 1 ? 384 : 128; }
+int cfg_bsub_rows(int mode, int cfg) { return cfg == 0 ? 128 : cfg == 1 ? (mode == 0 ? 96 : 64) : 64; }
+
+// least padded columns, ties -> wider tile
+int pick_cfg(int N) {
+  int best = 2;
+  long long best_pad = ((N + 127) / 128) * 128LL;
+  const int cands[2] = {0, 1};
+  for (int i = 0; i < 2; ++i) {
+    const int tn = cfg_tile_n(cands[i]);
+    long long pad = ((N + tn - 1) / tn) * (long long)tn;
+    if (pad <= best_pad) { best_pad = pad; best = cands[i]; }
+  }
+  return best;
+}
+
+int g_dbg_mode = 0;
+int g_use_pair = -1;    // 0: single-CTA kernel only, 1: CTA-pair kernel wherever it applies, 2: heuristic (FS2_TC_PAIR)
+int g_force_cfg = -2;   // FS2_TC_CFG=0|1|2 forces a tile configuration
+
+// heuristic kernel choice (measured on B200, tools/gemm_sweep.py): filled in from the sweep
+bool prefer_pair(const Fs2Gemm& g) {
+  // the pair kernel wins (1-8 %) where its 256-wide tiles divide N and the reduction is long; elsewhere the single-CTA
+  // kernel's exact-fit 192 / 128 tiles are faster (gpurun_out/gemm_sweep4.log)
+  return g.N % 256 == 0 && (long long)g.K * g.taps >= 1024 && g.M >= 2048;
+}
+
 }  // namespace
+
+long long* g_dbg = nullptr;
+extern "C" int fs2_gemm_tc_set_debug(long long* dev_buf) {
+  g_dbg = dev_buf;
+  return FS2_OK;
+}
+
+// tuning hook (tools/gemm_sweep.py): pair = 0 single-CTA, 1 CTA pair, 2 heuristic; cfg = -1 auto or 0|1|2
+extern "C" int fs2_gemm_tc_tune(int pair, int cfg) {
+  g_use_pair = pair & 3;
+  g_dbg_mode = (pair >> 4) & 3;     // bits 4-5: pipeline-isolation experiments (tools/gemm_sweep.py), 0 in production
+  g_force_cfg = cfg;
+  return FS2_OK;
+}
 
 // read-and-clear
 extern "C" int fs2_gemm_tc_error_flag(void) {
@@ -545,7 +1011,8 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return FS2_OK;
   int rc = get_encode();
   if (rc) return rc;
-  const int BN = pick_bn(g.N);
+  const int BN = (g_force_cfg >= 0 && g_force_cfg <= 2 && g_use_pair == 0) ? (g_force_cfg == 0 ? 256 : g_force_cfg == 1 ? 192 : 128)
+                                                                            : pick_bn(g.N, (long long)((g.M + BM - 1) / BM) * g.batch1 * g.batch2);
   TcParams p;
   memset(&p, 0, sizeof p);
   p.g = g;
@@ -578,6 +1045,39 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   static int* errp = nullptr;     // resolved once (also keeps the call out of CUDA-graph captures)
   if (!errp) CUDA_CHECK_RET(cudaGetSymbolAddress((void**)&errp, g_tc_error));
   p.err = errp;
+  p.dbg = g_dbg;
+  p.dbg_mode = g_dbg_mode;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_use_pair < 0) {
+    const char* e = getenv("FS2_TC_PAIR");
+    g_use_pair = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2;
+    const char* c = getenv("FS2_TC_CFG");
+    g_force_cfg = c ? atoi(c) : -1;
+  }
+  const bool pair_ok = g.batch1 * g.batch2 == 1 && g.M > BM;
+  if (pair_ok && (g_use_pair == 1 || g_use_pair == 3 || (g_use_pair == 2 && prefer_pair(g)))) {
+    const int cfg = (g_force_cfg >= 0 && g_force_cfg <= 2) ? g_force_cfg : pick_cfg(g.N);
+    const int ncta = g_use_pair == 3 ? 1 : 2;
+    CUtensorMap ta, tb;
+    if (g.mode == 2) rc = make_map(g.A, g.a_inner, g.a_rows, g.batch1, g.batch2, g.lda, g.a_s1, g.a_s2, 64, BK, &ta, p.pa);
+    else rc = make_map(g.A, g.a_inner, g.a_rows, g.batch1, g.batch2, g.lda, g.a_s1, g.a_s2, BK, BM, &ta, p.pa);
+    if (rc) return rc;
+    if (g.mode == 0)
+      rc = make_map(g.B, g.b_inner, g.b_rows, g.batch1, g.batch2, g.ldb, g.b_s1, g.b_s2, BK, cfg_bsub_rows(0, cfg) * (3 - ncta),
+                    &tb, p.pb);
+    else rc = make_map(g.B, g.b_inner, g.b_rows, g.batch1, g.batch2, g.ldb, g.b_s1, g.b_s2, 64, BK, &tb, p.pb);
+    if (rc) return rc;
+    if (ncta == 1) {
+      if (g.mode == 0) return dispatch_x1<0>(cfg, ta, tb, p, st);
+      if (g.mode == 1) return dispatch_x1<1>(cfg, ta, tb, p, st);
+      return dispatch_x1<2>(cfg, ta, tb, p, st);
+    }
+    if (g.mode == 0) return dispatch_x<0>(cfg, ta, tb, p, st);
+    if (g.mode == 1) return dispatch_x<1>(cfg, ta, tb, p, st);
+    if (g.mode == 2) return dispatch_x<2>(cfg, ta, tb, p, st);
+    fs2_set_error("fs2_gemm_tc: bad mode");
+    return FS2_ERR_ARG;
+  }
   CUtensorMap ta, tb;
   // A: mode 0/1 K-major box (64 k, 128 rows); mode 2 MN-major box (64 m, 64 k-rows)
   if (g.mode == 2) rc = make_map(g.A, g.a_inner, g.a_rows, g.batch1, g.batch2, g.lda, g.a_s1, g.a_s2, 64, BK, &ta, p.pa);
@@ -586,7 +1086,6 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   if (g.mode == 0) rc = make_map(g.B, g.b_inner, g.b_rows, g.batch1, g.batch2, g.ldb, g.b_s1, g.b_s2, BK, BN, &tb, p.pb);
   else rc = make_map(g.B, g.b_inner, g.b_rows, g.batch1, g.batch2, g.ldb, g.b_s1, g.b_s2, 64, BK, &tb, p.pb);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
   if (g.mode == 0) return dispatch_bn<0>(BN, ta, tb, p, st);
   if (g.mode == 1) return dispatch_bn<1>(BN, ta, tb, p, st);
   if (g.mode == 2) return dispatch_bn<2>(BN, ta, tb, p, st);

@@ -64,6 +64,12 @@ int fs2_gemm_simt(const Fs2Gemm* g, void* stream);
 int fs2_gemm_tc(const Fs2Gemm* g, void* stream);     /* tcgen05 + TMA, bf16 operands */
 /* device-side error word of the tensor-core kernel (non-zero: an mbarrier wait timed out) */
 int fs2_gemm_tc_error_flag(void);
+/* kernel selection override for measurements: pair = 0 single-CTA tiles, 1 CTA-pair (cta_group::2) tiles, 2 built-in
+ * heuristic (default); cfg = -1 automatic tile width, or 0|1|2 = 256|384(192)|128 columns */
+int fs2_gemm_tc_tune(int pair, int cfg);
+/* measurement hook: when non-NULL, every CTA-pair GEMM launch writes {SM cycles, nanoseconds} of its first CTA's
+ * lifetime to dev_buf[0..1] (the SM clock the kernel really ran at = cycles / ns) */
+int fs2_gemm_tc_set_debug(long long* dev_buf);
 
 /* ------------------------------------------------------------ row-wise kernels -- */
 /* Rule for every producer of a padded-row tensor: rect rows get values; halo rows get the reflect mirror

@@ -19,7 +19,7 @@ def _run(lib, use_tc, ab_dtype, mode, M, N, K, taps, A, B, c_bf16=False, **kw):
     Nout = N * taps if mode == 2 else N
     C = torch.full((M + kw.get("c_row_off", 0), Nout), float("nan"), device="cuda",
                    dtype=torch.bfloat16 if c_bf16 else torch.float32)
-    if kw.get("split_k", 1) > 1 or kw.get("accumulate", 0):
+    if kw.get("split_k", 1) != 1 or kw.get("accumulate", 0):
         C.zero_()
     lib.gemm(mode=mode, M=M, N=N, K=K, taps=taps, A=A, lda=A.shape[1], a_rows=A.shape[0], a_inner=A.shape[1],
              B=B, ldb=B.shape[1], b_rows=B.shape[0], b_inner=B.shape[1], Cout=C, ldc=Nout, c_bf16=c_bf16,
@@ -42,6 +42,18 @@ CASES = [
     ("wgrad", 2, 256, 128, 400, 9, 400, 256, 400, 128, dict(b_row_off=-4, b_tap_step=1)),
     ("wgrad_split", 2, 256, 128, 2000, 3, 2000, 256, 2000, 128, dict(b_row_off=-1, b_tap_step=1, split_k=4)),
     ("wgrad_m80", 2, 80, 384, 700, 1, 700, 80, 700, 384, {}),
+    # shapes that exercise every tile configuration of the CTA-pair (cta_group::2) kernel, ragged M / N, several waves
+    ("pair_n384_k512", 0, 1100, 384, 512, 1, 1100, 512, 384, 512, {}),
+    ("pair_n1536_conv9", 0, 700, 1536, 128, 9, 708, 128, 1536, 9 * 128, dict(a_tap_step=1, b_tap_step=128)),
+    ("pair_n1152", 0, 520, 1152, 384, 1, 520, 384, 1152, 384, {}),
+    ("pair_waves", 0, 40000, 384, 128, 1, 40000, 128, 384, 128, {}),
+    ("pair_dgrad_n384", 1, 900, 384, 320, 9, 908, 320, 320, 9 * 384, dict(a_row_off=4, a_tap_step=-1, b_tap_step=384)),
+    ("pair_dgrad_n1536", 1, 600, 1536, 384, 1, 600, 384, 384, 1536, {}),
+    ("pair_dgrad_n80", 1, 600, 80, 512, 5, 608, 512, 512, 5 * 80, dict(a_row_off=2, a_tap_step=-1, b_tap_step=80)),
+    ("pair_wgrad_auto", 2, 384, 384, 3000, 9, 3000, 384, 3000, 384, dict(b_row_off=-4, b_tap_step=1, split_k=0)),
+    ("pair_wgrad_n1536", 2, 384, 1536, 1500, 1, 1500, 384, 1500, 1536, dict(split_k=0)),
+    ("pair_wgrad_m1536", 2, 1536, 384, 1500, 3, 1500, 1536, 1500, 384, dict(b_row_off=-1, b_tap_step=1, split_k=0)),
+    ("pair_wgrad_n80", 2, 512, 80, 1300, 5, 1300, 512, 1300, 80, dict(b_row_off=-2, b_tap_step=1, split_k=0)),
 ]
 
 
