@@ -35,6 +35,8 @@ SIGNATURES = {
     "fs2_avg_over_durations": "ppiiippppp",
     "fs2_embed_add": "ppppipiiippiip",
     "fs2_embed_add_bwd": "ppiiiippp",
+    "fs2_attn_fwd": "ppiiiiiffQppppp",
+    "fs2_attn_bwd": "pppppiiiiiffQpppp",
     "fs2_dur_decode": "pqpp",
     "fs2_lr_prepare": "ppfiippp",
     "fs2_lr_finalize": "piippp",

@@ -173,6 +173,7 @@ class FastSpeech2(nn.Module):
         self._graphs = {}
         self._seen = set()
         self._pre = None
+        self.fused_attention = True   # bf16, head_dim 192: fs2_attn_fwd / fs2_attn_bwd instead of GEMM + softmax + GEMM
         self.async_mel_lens = False   # opt-in: no host sync; Tm is taken from pitch.shape[1], mel_lens arrives in pinned memory
         self._async_bufs = None
         self.replayed_launches = 0    # kernels launched through graph replays (fs2_launch_count only sees captures)
@@ -232,6 +233,10 @@ class FastSpeech2(nn.Module):
     @staticmethod
     def _site_seed(base, site):
         return (base * 0x9E3779B97F4A7C15 + site * 0xD1B54A32D192ED03 + 0x2545F4914F6CDD1D) & _M64
+
+    def _fused_attn(self, H):
+        """The fused tcgen05 attention kernel covers the reference geometry (2 heads x 192) in the bf16 path."""
+        return self.fused_attention and self._bf16 and self.D // H == 192 and self.D % H == 0
 
     def _conv(self, x, B, T, wname, out, *, c_bf16, bias=None, relu=0, lens=None, halo=0):
         """y[r] = sum_j x[r + j - p] . W_j (+bias, ReLU, row mask, reflect-halo mirror): model.py Conv1d/Linear sites."""
@@ -326,8 +331,13 @@ class FastSpeech2(nn.Module):
         hd = D // H
         TP = T + 2 * PAD
         ld = 3 * D
-        ldk = S.shape[-1]
+        ldk = P.shape[-1]
         bf = self._bf16
+        if S is None:
+            # fused tcgen05 attention: scores, softmax, dropout and PV in one kernel (attention.cu)
+            L.call("fs2_attn_fwd", qkv, lens, B, H, T, D, ldk, 1.0 / math.sqrt(hd), p_drop, seed, self._ctr, P,
+                   Pd if p_drop > 0 else None, O)
+            return
         # S[b,h] = Q K^T
         L.gemm(mode=0, M=T, N=T, K=hd, A=qkv, A_off=PAD * ld, lda=ld, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * ld,
                B=qkv, B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
@@ -346,7 +356,8 @@ class FastSpeech2(nn.Module):
         ldk = _rup(T, 8)
         bf = self._bf16
         p = cfg["p"] if training else 0.0
-        S = self._f32(B * H, T, ldk)          # scratch, shared by all layers of this stack
+        fused = self._fused_attn(H)
+        S = None if fused else self._f32(B * H, T, ldk)          # scratch, shared by all layers of this stack
         saves = []
         h1, h2 = (self.k0 - 1) // 2, (self.k1 - 1) // 2
         for l in range(nl):
@@ -407,7 +418,8 @@ class FastSpeech2(nn.Module):
         h1, h2 = (self.k0 - 1) // 2, (self.k1 - 1) // 2
         scale = 1.0 / math.sqrt(hd)
         # scratch shared by all layers
-        dPd = self._f32(B * H, T, ldk)
+        fused = self._fused_attn(H)
+        dPd = None if fused else self._f32(B * H, T, ldk)
         dS = self._act(B * H, T, ldk)
         dqkv = self._act(rows, ld)
         dF_act, dH_act = self._act(rows, D), self._act(rows, F)
@@ -444,19 +456,26 @@ class FastSpeech2(nn.Module):
             self._conv_wgrad(dProj_act, sv.O, B, T, f"{pre}.self_att.att.out_proj.weight",
                              f"{pre}.self_att.att.out_proj.weight", f"{pre}.self_att.att.out_proj.bias")
             self._conv_dgrad(dProj_act, B, T, f"{pre}.self_att.att.out_proj.weight", dO_act, c_bf16=bf)
-            # dPd = dO V^T
-            L.gemm(mode=0, M=T, N=T, K=hd, A=dO_act, A_off=PAD * D, lda=D, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * D,
-                   B=sv.qkv, B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld,
-                   batch1=H, batch2=B, Cout=dPd, ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=bf)
+            if not fused:
+                # dPd = dO V^T
+                L.gemm(mode=0, M=T, N=T, K=hd, A=dO_act, A_off=PAD * D, lda=D, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * D,
+                       B=sv.qkv, B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld,
+                       batch1=H, batch2=B, Cout=dPd, ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=bf)
             # dV = Pd^T dO
             L.gemm(mode=2, M=T, N=hd, K=T, A=sv.Pd, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
                    B=dO_act, B_off=PAD * D, ldb=D, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * D, batch1=H, batch2=B,
                    Cout=dqkv, C_off=PAD * ld + 2 * D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
-            L.call("fs2_softmax_bwd", sv.P, dPd, lens, B, H, T, ldk, scale, p, sv.seeds[0], self._ctr, dS, int(bf))
-            # dQ = dS K ; dK = dS^T Q
-            L.gemm(mode=1, M=T, N=hd, K=T, A=dS, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
-                   B=sv.qkv, B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
-                   Cout=dqkv, C_off=PAD * ld, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
+            if fused:
+                # dPd (TMEM) -> dS -> global, dQ = dS K accumulated in TMEM (attention.cu)
+                L.call("fs2_attn_bwd", dO_act, sv.O, sv.qkv, sv.P, lens, B, H, T, D, ldk, scale, p, sv.seeds[0], self._ctr,
+                       dS, dqkv)
+            else:
+                L.call("fs2_softmax_bwd", sv.P, dPd, lens, B, H, T, ldk, scale, p, sv.seeds[0], self._ctr, dS, int(bf))
+                # dQ = dS K
+                L.gemm(mode=1, M=T, N=hd, K=T, A=dS, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
+                       B=sv.qkv, B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
+                       Cout=dqkv, C_off=PAD * ld, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
+            # dK = dS^T Q
             L.gemm(mode=2, M=T, N=hd, K=T, A=dS, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
                    B=sv.qkv, B_off=PAD * ld, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
                    Cout=dqkv, C_off=PAD * ld + D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)

@@ -132,6 +132,18 @@ int fs2_softmax_fwd(const float* S, const int* lens, int B, int H, int T, int ld
 int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens, int B, int H, int T, int ldk, float scale,
                     float drop_p, unsigned long long seed, const unsigned long long* seed_dev, void* dS, int act_bf16,
                     void* stream);
+/* Fused attention for head_dim 192, bf16 (tcgen05: scores and the output accumulator live in TMEM; the fp32 score
+ * matrix never reaches HBM).  Replaces the QK^T GEMM + fs2_softmax_fwd + PV GEMM sequence; same mask quirk, same
+ * counter-based dropout stream (keyed by the element index in P), so it can be mixed with the unfused kernels.
+ * qkv: (B*(T+8), 3D) bf16 padded rows [Q | K | V]; P, Pd: (B*H, T, ldk) bf16 (Pd only when drop_p > 0);
+ * O: (B*(T+8), D) bf16 padded rows, rows t < T written. */
+int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int T, int D, int ldk, float scale, float drop_p,
+                 unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd, void* O, void* stream);
+/* Backward companion: dPd = dO.V^T (TMEM) -> dS = scale*P*(dPd*keep - rowsum(dO*O)) -> dS (B*H, T, ldk) bf16 and
+ * dQ = dS.K written into columns [0, D) of dqkv (B*(T+8), 3D).  dK = dS^T Q and dV = Pd^T dO stay batched GEMMs. */
+int fs2_attn_bwd(const void* dO, const void* O, const void* qkv, const void* P, const int* lens, int B, int H, int T,
+                 int D, int ldk, float scale, float drop_p, unsigned long long seed,
+                 const unsigned long long* seed_dev, void* dS, void* dqkv, void* stream);
 /* *ctr += inc (the device-side dropout step counter; first node of a captured forward graph) */
 int fs2_counter_add(unsigned long long* ctr, unsigned long long inc, void* stream);
 
