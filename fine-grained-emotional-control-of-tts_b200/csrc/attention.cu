@@ -20,16 +20,20 @@
 
 namespace {
 
+long long* g_attn_dbg = nullptr;
+
 constexpr int AQ = 128;        // query rows per CTA
 constexpr int AK = 64;         // keys per block (one 128-byte swizzle row of P)
 constexpr int HD = 192;        // head dimension: three 64-wide swizzle atoms
 constexpr int KSTAGES = 3;
 constexpr int VSTAGES = 2;
-constexpr int ATT_THREADS = 32 * 10;    // TMA, MMA, 8 softmax warps
+// NCH = threads per query row (column slices of a key block): 2 in the forward (8 softmax warps), 4 in the backward
+// (16 warps: the dS math has more loads in flight per column) -- measured on B200, see profiles/r01_attention.md
+constexpr int att_threads(int nch) { return 32 * (2 + 4 * nch); }    // TMA, MMA, 4*NCH softmax warps
 constexpr int Q_BYTES = 3 * AQ * 128;          // 49152
 constexpr int KV_BYTES = 3 * AK * 128;         // 24576
 constexpr int P_BYTES = AQ * 128;              // 16384
-constexpr int ATT_SMEM = Q_BYTES + KSTAGES * KV_BYTES + VSTAGES * KV_BYTES + 2 * P_BYTES + 1024 + 512 + 2 * AQ * 8;
+constexpr int ATT_SMEM = Q_BYTES + KSTAGES * KV_BYTES + VSTAGES * KV_BYTES + 2 * P_BYTES + 1024 + 512 + 4 * AQ * 8;
 constexpr int TMEM_S = 0;      // two 64-column score buffers
 constexpr int TMEM_O = 128;    // 192-column output accumulator
 
@@ -48,6 +52,7 @@ struct AttnParams {
   const bf16* O;               // bwd: forward output (for rowsum(dO*O))
   const bf16* dO;              // bwd
   int* err;
+  long long* dbg;              // optional cycle breakdown of CTA 0 (measurements only)
 };
 
 __device__ __forceinline__ int attn_kv(const int* lens, int B, int H, int bh) {
@@ -66,8 +71,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_constant__ CUtensorMap tmA,
+template <bool BWD, int NCH>
+__global__ void __launch_bounds__(att_threads(NCH), 1) attn_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmKV,
                                                               const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -88,8 +93,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
   uint64_t* pempty = pfull + 2;
   uint64_t* ofull = pempty + 2;           // [1]
   uint32_t* tmem_slot = (uint32_t*)(ofull + 1);
-  float2* xch = (float2*)(tmem_slot + 2);      // [2][AQ] exchange between the two threads of a row
+  float2* xch = (float2*)(tmem_slot + 2);      // [NCH][AQ] exchange between the threads of a row
 
+  constexpr int CW = AK / NCH;                 // score columns per thread and key block
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = p.err;
   const int nqb = (p.T + AQ - 1) / AQ;
@@ -109,8 +115,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
     for (int s = 0; s < VSTAGES; ++s) { mbar_init(smem_u32(&vfull[s]), 1); mbar_init(smem_u32(&vempty[s]), 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&sfull[s]), 1);
-      mbar_init(smem_u32(&sempty[s]), 8);
-      mbar_init(smem_u32(&pfull[s]), 256);
+      mbar_init(smem_u32(&sempty[s]), 4 * NCH);
+      mbar_init(smem_u32(&pfull[s]), 128 * NCH);
       mbar_init(smem_u32(&pempty[s]), 1);
     }
     mbar_init(smem_u32(ofull), 1);
@@ -169,11 +175,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
       bool ok = mbar_wait(smem_u32(qfull), 0, err);
       int s = 0, sv = 0;
       uint32_t ph = 0, phv = 0;
+      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+      long long w_k = 0, w_se = 0, w_pf = 0, w_v = 0, t_all = clock64(), tt = 0;
       for (int job = 0; job <= njobs && ok; ++job) {
         if (job < njobs) {
           const int sb = job & 1;
+          if (prof) tt = clock64();
           if (!mbar_wait(smem_u32(&kfull[s]), ph, err)) { ok = false; break; }
+          if (prof) { long long n = clock64(); w_k += n - tt; tt = n; }
           if (!mbar_wait(smem_u32(&sempty[sb]), ((job >> 1) & 1) ^ 1, err)) { ok = false; break; }
+          if (prof) w_se += clock64() - tt;
           tc_fence_after();
           const uint32_t sk = smem_u32(sK + s * KV_BYTES);
 #pragma unroll
@@ -189,8 +200,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
         const int jv = job - 1 - first_main;      // second contraction of the previous main-pass block
         if (jv >= 0) {
           const int pb = jv & 1;
+          if (prof) tt = clock64();
           if (!mbar_wait(smem_u32(&pfull[pb]), (jv >> 1) & 1, err)) { ok = false; break; }
+          if (prof) { long long n = clock64(); w_pf += n - tt; tt = n; }
           if (!mbar_wait(smem_u32(&vfull[sv]), phv, err)) { ok = false; break; }
+          if (prof) w_v += clock64() - tt;
           tc_fence_after();
           const uint32_t sp = smem_u32(sP + pb * P_BYTES);
           const uint32_t svb = smem_u32(sV + sv * KV_BYTES);
@@ -206,11 +220,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
           if (jv == nkb - 1) umma_commit(smem_u32(ofull));
         }
       }
+      if (prof) {
+        p.dbg[0] = clock64() - t_all; p.dbg[1] = w_k; p.dbg[2] = w_se; p.dbg[3] = w_pf; p.dbg[4] = w_v; p.dbg[5] = njobs;
+      }
     }
   } else {
     // ------------------------------------------------------------------------------------ softmax / dS warps
-    // 8 warps: TMEM lane quadrant q = warp % 4 (32 query rows), column half ch = (warp - 2) / 4 (32 of the block's 64 keys);
-    // two warps per scheduler hide each other's ALU latency.  The two threads of a row combine their statistics once.
+    // 16 warps: TMEM lane quadrant q = warp % 4 (32 query rows), column quarter ch = (warp - 2) / 4 (16 of the block's 64
+    // keys); four warps per scheduler hide each other's latency.  The four threads of a row combine their statistics once.
     const int q = warp & 3;
     const int ch = (warp - 2) >> 2;
     const int row = q * 32 + lane;
@@ -224,12 +241,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
     float mx = -INFINITY, sum = 0.f, inv = 0.f, dsum = 0.f;
     bool ok = true;
     if (BWD && nkb > 0) {
-      // D_i = sum_c dO[t,c] * O[t,c]  (== sum_k Pd*dPd, the softmax-backward row term); each thread takes 96 of the 192 dims
+      // D_i = sum_c dO[t,c] * O[t,c]  (== sum_k Pd*dPd, the softmax-backward row term); each thread takes 48 of the 192 dims
       if (row_valid) {
-        const uint4* a = reinterpret_cast<const uint4*>(p.dO + (long long)(row_base + t) * p.D + h * HD + ch * (HD / 2));
-        const uint4* o = reinterpret_cast<const uint4*>(p.O + (long long)(row_base + t) * p.D + h * HD + ch * (HD / 2));
-#pragma unroll 4
-        for (int i = 0; i < HD / 16; ++i) {
+        const uint4* a = reinterpret_cast<const uint4*>(p.dO + (long long)(row_base + t) * p.D + h * HD + ch * (HD / NCH));
+        const uint4* o = reinterpret_cast<const uint4*>(p.O + (long long)(row_base + t) * p.D + h * HD + ch * (HD / NCH));
+#pragma unroll
+        for (int i = 0; i < HD / NCH / 8; ++i) {
           const uint4 x = a[i], y = o[i];
           const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
@@ -241,72 +258,78 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
         }
       }
       xch[ch * AQ + row] = make_float2(dsum, 0.f);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      dsum += xch[(ch ^ 1) * AQ + row].x;
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * NCH) : "memory");
+      dsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) dsum += xch[c * AQ + row].x;
     }
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
+    long long w_sf = 0, w_ld = 0, w_cmp = 0, w_pe = 0, w_st = 0, t_all = clock64(), tt = 0;
+    uint4 pk[CW / 8];                                             // bwd: this job's P chunk (packed bf16), prefetched
+    auto load_p = [&](int j) {
+      const int c0 = j * AK + ch * CW;
+#pragma unroll
+      for (int i = 0; i < CW / 8; ++i) pk[i] = make_uint4(0, 0, 0, 0);
+      if (row_valid && j < nkb) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.P + ro + c0);
+#pragma unroll
+        for (int i = 0; i < CW / 8; ++i)
+          if (c0 + 8 * i < p.ldk) pk[i] = src[i];
+      }
+    };
+    if (BWD) load_p(0);
     for (int job = 0; job < njobs && ok; ++job) {
       const int sb = job & 1;
       const bool main_pass = job >= first_main;
       const int j = main_pass ? job - first_main : job;
-      const int c0 = j * AK + ch * 32;                            // first key of this thread's 32 columns
+      const int c0 = j * AK + ch * CW;                            // first key of this thread's 16 columns
       const int pb = j & 1;
-      const bool full = (c0 + 32 <= kv);
+      const bool full = (c0 + CW <= kv);
       const bool in_buf = row_valid && c0 < p.ldk;
-      float pr[32];
-      if (BWD) {
-        // P of this block: issued before the wait on the score tile so that the load latency overlaps it
-        if (in_buf) {
-          const uint4* src = reinterpret_cast<const uint4*>(p.P + ro + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 x = make_uint4(0, 0, 0, 0);
-            if (c0 + 8 * i < p.ldk) x = src[i];
-            const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[k]));
-              pr[8 * i + 2 * k] = f.x;
-              pr[8 * i + 2 * k + 1] = f.y;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pr[i] = 0.f;
-        }
-      }
       if (!BWD && job == first_main) {
-        // combine the two column halves' (max, sum) of pass 1
+        // combine the column quarters' (max, sum) of pass 1
         xch[ch * AQ + row] = make_float2(mx, sum);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float2 o = xch[(ch ^ 1) * AQ + row];
-        const float m = fmaxf(mx, o.x);
-        sum = sum * ex2f_(mx - m) + o.y * ex2f_(o.x - m);
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * NCH) : "memory");
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) m = fmaxf(m, xch[c * AQ + row].x);
+        float l = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const float2 o = xch[c * AQ + row];
+          l += o.y * ex2f_(o.x - m);                              // empty quarter: 0 * 2^-inf = 0
+        }
         mx = m;
+        sum = l;
         inv = 1.0f / sum;
       }
+      if (prof) tt = clock64();
       if (!mbar_wait(smem_u32(&sfull[sb]), (job >> 1) & 1, err)) { ok = false; break; }
+      if (prof) { long long n = clock64(); w_sf += n - tt; tt = n; }
       tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(lane_addr + (uint32_t)(TMEM_S + sb * AK + ch * 32), r);
+      uint32_t r[CW];
+      if constexpr (CW == 32) tmem_ld32(lane_addr + (uint32_t)(TMEM_S + sb * AK + ch * CW), r);
+      else tmem_ld16(lane_addr + (uint32_t)(TMEM_S + sb * AK + ch * CW), r);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sempty[sb]));          // score buffer drained by this warp
+      if (prof) { long long n = clock64(); w_ld += n - tt; tt = n; }
       if (!main_pass) {
         // ---- pass 1 (forward only): running max / sum over this thread's columns
         float bm = -INFINITY;
         if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) bm = fmaxf(bm, __uint_as_float(r[i]));
+          for (int i = 0; i < CW; ++i) bm = fmaxf(bm, __uint_as_float(r[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) bm = fmaxf(bm, (c0 + i < kv) ? __uint_as_float(r[i]) : -INFINITY);
+          for (int i = 0; i < CW; ++i) bm = fmaxf(bm, (c0 + i < kv) ? __uint_as_float(r[i]) : -INFINITY);
         }
         bm *= sc2;
         if (bm > mx) { sum *= ex2f_(mx - bm); mx = bm; }          // mx == -inf: sum is 0 and 2^-inf = 0
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < CW; i += 4) {
             a0 += ex2f_(fmaf(__uint_as_float(r[i]), sc2, -mx));
             a1 += ex2f_(fmaf(__uint_as_float(r[i + 1]), sc2, -mx));
             a2 += ex2f_(fmaf(__uint_as_float(r[i + 2]), sc2, -mx));
@@ -314,7 +337,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
           }
         } else if (c0 < kv) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < CW; ++i) {
             const float e = ex2f_(fmaf(__uint_as_float(r[i]), sc2, -mx));
             a0 += (c0 + i < kv) ? e : 0.f;
           }
@@ -323,14 +346,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
         continue;
       }
       // ---- main pass
-      float v[32];
+      float v[CW];
       if (!BWD) {
         if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = ex2f_(fmaf(__uint_as_float(r[i]), sc2, -mx)) * inv;
+          for (int i = 0; i < CW; ++i) v[i] = ex2f_(fmaf(__uint_as_float(r[i]), sc2, -mx)) * inv;
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < CW; ++i) {
             const float e = ex2f_(fmaf(__uint_as_float(r[i]), sc2, -mx)) * inv;
             v[i] = (c0 + i < kv) ? e : 0.f;
           }
@@ -338,21 +361,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
         if (in_buf) {
           uint4* dst = reinterpret_cast<uint4*>(p.P + ro + c0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < CW / 8; ++i)
             if (c0 + 8 * i < p.ldk)
               dst[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
         }
         if (dc.p > 0.f) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < CW / 4; ++i) {
             const float4 k = drop_scale4(dc, (uint64_t)(ro + c0 + 4 * i) >> 2);
             v[4 * i] *= k.x; v[4 * i + 1] *= k.y; v[4 * i + 2] *= k.z; v[4 * i + 3] *= k.w;
           }
           if (in_buf && p.Pd) {
             uint4* dst = reinterpret_cast<uint4*>(p.Pd + ro + c0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < CW / 8; ++i)
               if (c0 + 8 * i < p.ldk)
                 dst[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
                                     pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
@@ -360,10 +383,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
         }
       } else {
         // dS = scale * P * (dPd * keep - D_i); P is 0 beyond kv, so no explicit mask is needed
+        float pr[CW];
+#pragma unroll
+        for (int i = 0; i < CW / 8; ++i) {
+          const uint32_t xw[4] = {pk[i].x, pk[i].y, pk[i].z, pk[i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[k]));
+            pr[8 * i + 2 * k] = f.x;
+            pr[8 * i + 2 * k + 1] = f.y;
+          }
+        }
+        load_p(j + 1);                                            // next block's P: a whole job of latency slack
         const float scale = p.scale;
         if (dc.p > 0.f) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < CW / 4; ++i) {
             const float4 k = drop_scale4(dc, (uint64_t)(ro + c0 + 4 * i) >> 2);
             v[4 * i] = scale * pr[4 * i] * fmaf(__uint_as_float(r[4 * i]), k.x, -dsum);
             v[4 * i + 1] = scale * pr[4 * i + 1] * fmaf(__uint_as_float(r[4 * i + 1]), k.y, -dsum);
@@ -372,34 +407,40 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = scale * pr[i] * (__uint_as_float(r[i]) - dsum);
+          for (int i = 0; i < CW; ++i) v[i] = scale * pr[i] * (__uint_as_float(r[i]) - dsum);
         }
         if (in_buf) {
           uint4* dst = reinterpret_cast<uint4*>(p.dS + ro + c0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < CW / 8; ++i)
             if (c0 + 8 * i < p.ldk)
               dst[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
                                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
         }
       }
       // the P tile in smem is free once the second contraction of block j-2 has completed
+      if (prof) { long long n = clock64(); w_cmp += n - tt; tt = n; }
       if (!mbar_wait(smem_u32(&pempty[pb]), ((j >> 1) & 1) ^ 1, err)) { ok = false; break; }
+      if (prof) { long long n = clock64(); w_pe += n - tt; tt = n; }
       // A operand of the second contraction: row `row`, 16-byte chunks XOR-swizzled inside the 128-byte row
       uint8_t* prow = sP + pb * P_BYTES + row * 128;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int chunk = ch * 4 + i;
+      for (int i = 0; i < CW / 8; ++i) {
+        const int chunk = ch * (CW / 8) + i;
         *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) =
             make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
                        pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA
       mbar_arrive(smem_u32(&pfull[pb]));
+      if (prof) w_st += clock64() - tt;
+    }
+    if (prof) {
+      p.dbg[8] = clock64() - t_all; p.dbg[9] = w_sf; p.dbg[10] = w_ld; p.dbg[11] = w_cmp; p.dbg[12] = w_pe; p.dbg[13] = w_st;
     }
     // columns of P / Pd / dS beyond the last processed key block are zero (the backward GEMMs read the full rows)
     if (row_valid) {
-      for (int c = nkb * AK + ch * 8; c < p.ldk; c += 16) {
+      for (int c = nkb * AK + ch * 8; c < p.ldk; c += 8 * NCH) {
         const uint4 z = make_uint4(0, 0, 0, 0);
         if (!BWD) {
           *reinterpret_cast<uint4*>(p.P + ro + c) = z;
@@ -409,19 +450,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
         }
       }
     }
-    // final accumulator: TMEM -> bf16 -> global; each thread writes 96 of the row's 192 columns
-    bf16* orow = p.out + (long long)(row_base + t) * p.out_ld + h * HD + ch * (HD / 2);
+    // final accumulator: TMEM -> bf16 -> global; each thread writes 48 of the row's 192 columns
+    bf16* orow = p.out + (long long)(row_base + t) * p.out_ld + h * HD + ch * (HD / NCH);
     if (nkb > 0) {
       if (ok && mbar_wait(smem_u32(ofull), 0, err)) {
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < HD / 64; ++c) {
-          uint32_t r[32];
-          tmem_ld32(lane_addr + (uint32_t)(TMEM_O + ch * (HD / 2) + c * 32), r);
+        for (int c = 0; c < HD / NCH / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + (uint32_t)(TMEM_O + ch * (HD / NCH) + c * 16), r);
           if (row_valid) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+            uint4* dst = reinterpret_cast<uint4*>(orow + c * 16);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
               dst[i] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1])),
                                   pack_bf16x2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])),
                                   pack_bf16x2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])),
@@ -430,7 +471,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
         }
       }
     } else if (row_valid) {
-      for (int c = 0; c < HD / 2; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < HD / NCH; c += 8) *reinterpret_cast<uint4*>(orow + c) = make_uint4(0, 0, 0, 0);
     }
   }
 
@@ -442,15 +483,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_kernel(const __grid_const
   }
 }
 
-template <bool BWD>
+template <bool BWD, int NCH>
 int launch_attn(const CUtensorMap& ta, const CUtensorMap& tkv, const AttnParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(attn_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(attn_kernel<BWD, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     configured = true;
   }
   const int nqb = (p.T + AQ - 1) / AQ;
-  attn_kernel<BWD><<<nqb * p.B * p.H, ATT_THREADS, ATT_SMEM, st>>>(ta, tkv, p);
+  attn_kernel<BWD, NCH><<<nqb * p.B * p.H, att_threads(NCH), ATT_SMEM, st>>>(ta, tkv, p);
   return fs2_check_launch();
 }
 
@@ -464,10 +505,19 @@ int attn_common(const void* qkv, const int* lens, int B, int H, int T, int D, in
   p.lens = lens;
   int rc = fs2_tc_error_ptr(&p.err);
   if (rc) return rc;
+  p.dbg = g_attn_dbg;
   return fs2_tc_make_map_2d(qkv, 3LL * D, (long long)B * p.TP, 3LL * D, 64, AK, tkv);
 }
 
 }  // namespace
+
+/* measurement hook: cycle breakdown of CTA 0 (MMA thread: [0] total, [1..4] waits on K tile / score buffer / P tile /
+ * V tile, [5] jobs; first softmax thread: [8] total, [9] wait scores, [10] tcgen05.ld, [11] math + global stores,
+ * [12] wait P buffer, [13] smem store + fence + arrive) */
+extern "C" int fs2_attn_set_debug(long long* dev_buf) {
+  g_attn_dbg = dev_buf;
+  return FS2_OK;
+}
 
 extern "C" int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int T, int D, int ldk, float scale, float drop_p,
                             unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd, void* O,
@@ -488,7 +538,7 @@ extern "C" int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int 
   p.Pd = drop_p > 0.f ? (bf16*)Pd : nullptr;
   p.out = (bf16*)O;
   p.out_ld = D;
-  return launch_attn<false>(tq, tkv, p, (cudaStream_t)stream);
+  return launch_attn<false, 2>(tq, tkv, p, (cudaStream_t)stream);
 }
 
 extern "C" int fs2_attn_bwd(const void* dO, const void* O, const void* qkv, const void* P, const int* lens, int B, int H,
@@ -512,5 +562,5 @@ extern "C" int fs2_attn_bwd(const void* dO, const void* O, const void* qkv, cons
   p.out_ld = 3LL * D;
   p.O = (const bf16*)O;
   p.dO = (const bf16*)dO;
-  return launch_attn<true>(ta, tkv, p, (cudaStream_t)stream);
+  return launch_attn<true, 4>(ta, tkv, p, (cudaStream_t)stream);
 }

@@ -673,65 +673,122 @@ __global__ void lr_finalize_kernel(const int* mel_lens, int B, int Tm_expected, 
   if (threadIdx.x == 0 && mx != Tm_expected) atomicExch(flag, mx == 0 ? -1 : mx);
 }
 
+// LengthRegulator expand / segment-sum kernels.  One CTA = LR_ROWS consecutive output rows of ONE item: the item's
+// duration prefix sums (`ends`, Tp ints) are staged in shared memory once, eight lanes of a warp binary-search eight
+// rows at the same time (so the dependent-load chain is paid once per 8 rows, out of smem), and the row copies are
+// issued four rows at a time so that every lane keeps >= 4 independent 16-byte loads in flight.
+constexpr int LR_RPW = 8;                    // rows per warp
+constexpr int LR_ROWS = WARPS * LR_RPW;      // rows per CTA
+
+// first p with e[p] > f  (e = inclusive prefix sums of the frame counts), -1 when f is outside [0, total)
+__device__ __forceinline__ int lr_search(const int* e, int Tp, int f, int total) {
+  if (f < 0 || f >= total) return -1;
+  int lo = 0, hi = Tp - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (e[mid] > f) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
 template <typename TA>
-__global__ void __launch_bounds__(THREADS) lr_expand_kernel(const float* in, int in_pitch, int in_off, const int* ends,
-                                                            const int* mel_lens, const float* pe, int B, int Tp, int Tm,
-                                                            int D, float* of, TA* oa, int out_pitch, int out_off,
-                                                            int* frame2ph) {
-  const int lane = threadIdx.x & 31;
-  const long long rows = (long long)B * out_pitch;
-  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
-    int b = (int)(r / out_pitch), f = (int)(r - (long long)b * out_pitch) - out_off;
-    const long long ro = r * D;
-    int idx = -1;
-    if (f >= 0 && f < Tm && f < mel_lens[b]) {
-      const int* e = ends + (long long)b * Tp;
-      int lo = 0, hi = Tp - 1;           // first p with ends[p] > f
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (e[mid] > f) hi = mid; else lo = mid + 1;
-      }
-      idx = lo;
+__global__ void __launch_bounds__(THREADS) lr_expand_kernel(const float* __restrict__ in, int in_pitch, int in_off,
+                                                            const int* __restrict__ ends, const int* __restrict__ mel_lens,
+                                                            const float* __restrict__ pe, int B, int Tp, int Tm, int D,
+                                                            float* __restrict__ of, TA* __restrict__ oa, int out_pitch,
+                                                            int out_off, int* __restrict__ frame2ph) {
+  extern __shared__ int s_ends[];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < Tp; i += THREADS) s_ends[i] = ends[(long long)b * Tp + i];
+  __syncthreads();
+  const int total = min(min(mel_lens[b], Tm), s_ends[Tp - 1]);
+  const int r0 = blockIdx.x * LR_ROWS + warp * LR_RPW;          // first row (inside the item's out_pitch rows)
+  int my_idx = -1;
+  if (lane < LR_RPW) {
+    const int f = r0 + lane - out_off;
+    my_idx = lr_search(s_ends, Tp, f, total);
+    if (frame2ph && r0 + lane < out_pitch && f >= 0 && f < Tm) frame2ph[(long long)b * Tm + f] = my_idx;
+  }
+  const float* in_b = in + ((long long)b * in_pitch + in_off) * D;
+  int idx[LR_RPW];
+#pragma unroll
+  for (int j = 0; j < LR_RPW; ++j) {
+    idx[j] = __shfl_sync(0xffffffffu, my_idx, j);
+    if (r0 + j >= out_pitch) idx[j] = -2;                       // row does not exist
+  }
+  if (idx[0] == -2) return;
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 v[LR_RPW];
+#pragma unroll
+    for (int j = 0; j < LR_RPW; ++j) {
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx[j] >= 0) v[j] = ld4(in_b + (long long)idx[j] * D + c);
     }
-    if (frame2ph && f >= 0 && f < Tm && lane == 0) frame2ph[(long long)b * Tm + f] = idx;
-    const float* src = idx >= 0 ? in + ((long long)b * in_pitch + in_off + idx) * D : nullptr;
-    for (int c = lane * 4; c < D; c += 128) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (src) {
-        v = ld4(src + c);
-        if (pe) {
-          float4 pv = ld4(pe + (long long)f * D + c);
-          v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+    if (pe) {
+#pragma unroll
+      for (int j = 0; j < LR_RPW; ++j) {
+        if (idx[j] >= 0) {
+          const float4 pv = ld4(pe + (long long)(r0 + j - out_off) * D + c);
+          v[j].x += pv.x; v[j].y += pv.y; v[j].z += pv.z; v[j].w += pv.w;
         }
       }
-      if (of) st4(of + ro + c, v);
-      if (oa) st4(oa + ro + c, v);
+    }
+#pragma unroll
+    for (int j = 0; j < LR_RPW; ++j) {
+      if (idx[j] == -2) continue;
+      const long long ro = ((long long)b * out_pitch + r0 + j) * D + c;
+      if (of) st4(of + ro, v[j]);
+      if (oa) st4(oa + ro, v[j]);
     }
   }
 }
 
-__global__ void __launch_bounds__(THREADS) lr_bwd_kernel(const float* df, const float* df2, int f_pitch, int f_off,
-                                                         const int* ends, const int* mel_lens, int B, int Tp, int Tm,
-                                                         int D, float* dphon, int p_pitch, int p_off) {
-  const int lane = threadIdx.x & 31;
-  const long long rows = (long long)B * p_pitch;
-  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
-    int b = (int)(r / p_pitch), p = (int)(r - (long long)b * p_pitch) - p_off;
-    int s = 0, e = 0;
-    if (p >= 0 && p < Tp) {
-      e = min(ends[(long long)b * Tp + p], Tm);
-      s = p ? min(ends[(long long)b * Tp + p - 1], Tm) : 0;
-    }
-    for (int c = lane * 4; c < D; c += 128) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int f = s; f < e; ++f) {
-        long long o = ((long long)b * f_pitch + f_off + f) * D + c;
-        float4 v = ld4(df + o);
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        if (df2) { v = ld4(df2 + o); a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+// backward of the expansion = per-phoneme sums over its frames.  Frame-parallel (a phoneme-parallel kernel waits on
+// its longest segment): every warp reads LR_RPW consecutive frame rows, merges neighbours that belong to the same
+// phoneme in registers and flushes each run with one 16-byte vector atomic.  dphon must be zero on entry.
+__global__ void __launch_bounds__(THREADS) lr_bwd_kernel(const float* __restrict__ df, const float* __restrict__ df2,
+                                                         int f_pitch, int f_off, const int* __restrict__ ends, int B, int Tp,
+                                                         int Tm, int D, float* __restrict__ dphon, int p_pitch, int p_off) {
+  extern __shared__ int s_ends[];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < Tp; i += THREADS) s_ends[i] = ends[(long long)b * Tp + i];
+  __syncthreads();
+  const int total = min(s_ends[Tp - 1], Tm);
+  const int f0 = blockIdx.x * LR_ROWS + warp * LR_RPW;
+  if (f0 >= total) return;
+  int my_idx = -1;
+  if (lane < LR_RPW) my_idx = lr_search(s_ends, Tp, f0 + lane, total);
+  int idx[LR_RPW];
+#pragma unroll
+  for (int j = 0; j < LR_RPW; ++j) idx[j] = __shfl_sync(0xffffffffu, my_idx, j);
+  const float* src = df + ((long long)b * f_pitch + f_off + f0) * D;
+  const float* src2 = df2 ? df2 + ((long long)b * f_pitch + f_off + f0) * D : nullptr;
+  float* dst = dphon + ((long long)b * p_pitch + p_off) * D;
+  for (int c = lane * 4; c < D; c += 128) {
+    float4 v[LR_RPW];
+#pragma unroll
+    for (int j = 0; j < LR_RPW; ++j) {
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx[j] >= 0) {
+        v[j] = ld4(src + (long long)j * D + c);
+        if (src2) { const float4 w = ld4(src2 + (long long)j * D + c); v[j].x += w.x; v[j].y += w.y; v[j].z += w.z; v[j].w += w.w; }
       }
-      st4(dphon + r * D + c, a);
     }
+    float4 acc = v[0];
+    int cur = idx[0];
+#pragma unroll
+    for (int j = 1; j < LR_RPW; ++j) {
+      if (idx[j] != cur) {
+        if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(dst + (long long)cur * D + c), acc);
+        cur = idx[j];
+        acc = v[j];
+      } else {
+        acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+      }
+    }
+    if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(dst + (long long)cur * D + c), acc);
   }
 }
 
@@ -837,18 +894,44 @@ __global__ void __launch_bounds__(THREADS) pad_rows_kernel(const float* a, const
 
 // Weight packing: dst[co, j, ci] = src[co*src_ld + ci*k + j]  (torch Conv1d (Cout,Cin,k) -> tap-major K),
 // one launch for the whole parameter set driven by a device-side table.
+// Blocks of grid row y walk the output channels of item y; a channel's (Cin, k) slab is read contiguously into
+// shared memory and written back tap-major, so both the fp32 reads and the operand-dtype writes are coalesced.
+constexpr int PACK_MAX = 4608;      // floats of one output channel's slab staged in smem (18 KB)
 template <typename TD>
-__global__ void pack_weights_kernel(const Fs2PackItem* items, const float* src_base, TD* dst_base) {
+__global__ void __launch_bounds__(256) pack_weights_kernel(const Fs2PackItem* items, const float* __restrict__ src_base,
+                                                           TD* __restrict__ dst_base) {
+  __shared__ float slab[PACK_MAX];
   const Fs2PackItem it = items[blockIdx.y];
-  const long long n = (long long)it.cout * it.cin * it.k;
+  const int rk = it.cin * it.k;
   const float* src = src_base + it.src_off;
   TD* dst = dst_base + it.dst_off;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int ci = (int)(i % it.cin);
-    long long q = i / it.cin;
-    int j = (int)(q % it.k);
-    long long co = q / it.k;
-    ActT<TD>::st(dst + i, src[co * it.src_ld + (long long)ci * it.k + j]);
+  if (it.k == 1) {
+    for (int co = blockIdx.x; co < it.cout; co += gridDim.x) {
+      const float* s = src + (long long)co * it.src_ld;
+      TD* d = dst + (long long)co * it.cin;
+      for (int ci = threadIdx.x; ci < it.cin; ci += 256) ActT<TD>::st(d + ci, s[ci]);
+    }
+  } else if (rk <= PACK_MAX) {
+    for (int co = blockIdx.x; co < it.cout; co += gridDim.x) {
+      const float* s = src + (long long)co * it.src_ld;
+      TD* d = dst + (long long)co * rk;
+      for (int i = threadIdx.x; i < rk; i += 256) slab[i] = s[i];
+      __syncthreads();
+      for (int i = threadIdx.x; i < rk; i += 256) {
+        const int j = i / it.cin, ci = i - j * it.cin;
+        ActT<TD>::st(d + i, slab[ci * it.k + j]);
+      }
+      __syncthreads();
+    }
+  } else {
+    const long long n = (long long)it.cout * rk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      int ci = (int)(i % it.cin);
+      long long q = i / it.cin;
+      int j = (int)(q % it.k);
+      long long co = q / it.k;
+      ActT<TD>::st(dst + i, src[co * it.src_ld + (long long)ci * it.k + j]);
+    }
   }
 }
 
@@ -1064,9 +1147,11 @@ extern "C" int fs2_lr_expand(const float* in, int in_pitch, int in_off, const in
                              const float* pe, int B, int Tp, int Tm, int D, float* out_f32, void* out_act, int act_bf16,
                              int out_pitch, int out_off, int* frame2ph, void* stream) {
   REQUIRE(in && ends && mel_lens && D % 4 == 0, "fs2_lr_expand: bad arguments");
-  const long long rows = (long long)B * out_pitch;
-  if (act_bf16) lr_expand_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (bf16*)out_act, out_pitch, out_off, frame2ph);
-  else lr_expand_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (float*)out_act, out_pitch, out_off, frame2ph);
+  REQUIRE(B > 0 && B <= 65535 && Tp > 0 && Tp <= 12000 && out_pitch > 0, "fs2_lr_expand: B <= 65535 and 0 < Tp <= 12000 (prefix sums are staged in shared memory)");
+  const dim3 grid((out_pitch + LR_ROWS - 1) / LR_ROWS, B);
+  const size_t sm = (size_t)Tp * sizeof(int);
+  if (act_bf16) lr_expand_kernel<bf16><<<grid, THREADS, sm, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (bf16*)out_act, out_pitch, out_off, frame2ph);
+  else lr_expand_kernel<float><<<grid, THREADS, sm, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (float*)out_act, out_pitch, out_off, frame2ph);
   return fs2_check_launch();
 }
 
@@ -1074,7 +1159,11 @@ extern "C" int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pit
                           const int* mel_lens, int B, int Tp, int Tm, int D, float* dphon, int p_pitch, int p_off,
                           void* stream) {
   REQUIRE(dframes && ends && dphon && D % 4 == 0, "fs2_lr_bwd: bad arguments");
-  lr_bwd_kernel<<<grid_for_rows((long long)B * p_pitch), THREADS, 0, ST>>>(dframes, dframes2, f_pitch, f_off, ends, mel_lens, B, Tp, Tm, D, dphon, p_pitch, p_off);
+  REQUIRE(B > 0 && B <= 65535 && Tp > 0 && Tp <= 12000 && Tm > 0, "fs2_lr_bwd: B <= 65535 and 0 < Tp <= 12000 (prefix sums are staged in shared memory)");
+  (void)mel_lens;
+  CUDA_CHECK_RET(cudaMemsetAsync(dphon, 0, (size_t)B * p_pitch * D * sizeof(float), ST));
+  const dim3 grid((Tm + LR_ROWS - 1) / LR_ROWS, B);
+  lr_bwd_kernel<<<grid, THREADS, (size_t)Tp * sizeof(int), ST>>>(dframes, dframes2, f_pitch, f_off, ends, B, Tp, Tm, D, dphon, p_pitch, p_off);
   return fs2_check_launch();
 }
 
@@ -1119,7 +1208,7 @@ extern "C" int fs2_pad_rows(const float* src_plain, const float* src2_plain, int
 extern "C" int fs2_pack_weights(const Fs2PackItem* items_dev, int n_items, const float* src_base, void* dst_base,
                                 int dst_bf16, void* stream) {
   REQUIRE(items_dev && src_base && dst_base && n_items > 0, "fs2_pack_weights: bad arguments");
-  dim3 grid(64, n_items);
+  dim3 grid(128, n_items);
   if (dst_bf16) pack_weights_kernel<bf16><<<grid, 256, 0, ST>>>(items_dev, src_base, (bf16*)dst_base);
   else pack_weights_kernel<float><<<grid, 256, 0, ST>>>(items_dev, src_base, (float*)dst_base);
   return fs2_check_launch();

@@ -179,6 +179,14 @@ class FastSpeech2(nn.Module):
         self.replayed_launches = 0    # kernels launched through graph replays (fs2_launch_count only sees captures)
         self.trace = None        # set to a dict to collect unpadded intermediates (debug / parity tests)
         self._pin_lens = None
+        # weight-gradient GEMMs (+ bias column sums) are off the backward's critical path: with overlap_wgrad they are
+        # queued on a second stream (fork/join through events, also inside graph captures) and fill the SMs the
+        # dgrad chain leaves idle (short grids, wave tails, memory-bound LN kernels)
+        self.overlap_wgrad = True
+        self._side = None
+        self._side_stream = None
+        self._side_reads = {}
+        self._side_last = None
 
     # ------------------------------------------------------------------ nn.Module plumbing
     def _apply(self, fn, *a, **kw):
@@ -253,12 +261,51 @@ class FastSpeech2(nn.Module):
         w = self.store.pw(wname)
         rows = B * (T + 2 * PAD)
         p = (w.k - 1) // 2
+        self._wait_side(out)
         L.gemm(mode=1, M=rows, N=w.cin, K=w.cout, taps=w.k, A=dy, lda=w.cout, a_rows=rows, a_inner=w.cout,
                a_row_off=p, a_tap_step=-1, B=self.store.packed_buf, B_off=w.off, ldb=w.k * w.cin, b_rows=w.cout,
                b_inner=w.k * w.cin, b_tap_step=w.cin, Cout=out, ldc=w.cin, c_bf16=c_bf16, ab_bf16=self._bf16,
                relu_aux=relu_aux, aux_bf16=int(self._bf16))
 
+    def _side_begin(self, dev):
+        if not self.overlap_wgrad:
+            return
+        if self._side_stream is None or self._side_stream.device != dev:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        self._side = self._side_stream
+        self._side_reads = {}
+        self._side_last = None
+
+    def _side_join(self):
+        """Main stream waits for everything queued on the side stream (end of backward)."""
+        if self._side is not None and self._side_last is not None:
+            torch.cuda.current_stream().wait_event(self._side_last)
+        self._side = None
+        self._side_reads = {}
+        self._side_last = None
+
+    def _wait_side(self, buf):
+        """Call before the main stream overwrites a scratch buffer a side-stream GEMM may still be reading."""
+        if self._side is not None and buf is not None:
+            ev = self._side_reads.pop(buf.data_ptr(), None)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
     def _conv_wgrad(self, dy, x, B, T, wname, wkey, bkey=None):
+        side = self._side
+        if side is None:
+            return self._conv_wgrad_launch(dy, x, B, T, wname, wkey, bkey)
+        ready = torch.cuda.Event()
+        ready.record()                       # everything the main stream has queued so far (dy's producer included)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            self._conv_wgrad_launch(dy, x, B, T, wname, wkey, bkey)
+            done = torch.cuda.Event()
+            done.record()
+        self._side_reads[dy.data_ptr()] = done
+        self._side_last = done
+
+    def _conv_wgrad_launch(self, dy, x, B, T, wname, wkey, bkey=None):
         """dW[co, ci, j] += sum_r dy[r, co] * x[r + j - p, ci];  db[co] += sum_r dy[r, co]."""
         w = self.store.pw(wname)
         rows = B * (T + 2 * PAD)
@@ -299,6 +346,7 @@ class FastSpeech2(nn.Module):
     def _ln_bwd(self, B, T, C, x, gamma, beta, eps, mean, rstd, *, dy=None, dy2=None, dy2_fold=0, dhead=None,
                 head_w=None, head_scale=1.0, branch=None, drop_b=(0.0, 0), tanh=0, drop_a=(0.0, 0), lens=None,
                 relu_x=0, dx_f32=None, dact=None, dgamma=None, dbeta=None, dhead_w=None, dhead_b=None):
+        self._wait_side(dact)
         p = L.Fs2LnBwd()
         p.B, p.T, p.C = B, T, C
         p.dy = dy.data_ptr() if dy is not None else None
@@ -462,6 +510,7 @@ class FastSpeech2(nn.Module):
                        B=sv.qkv, B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld,
                        batch1=H, batch2=B, Cout=dPd, ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=bf)
             # dV = Pd^T dO
+            self._wait_side(dqkv)
             L.gemm(mode=2, M=T, N=hd, K=T, A=sv.Pd, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
                    B=dO_act, B_off=PAD * D, ldb=D, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * D, batch1=H, batch2=B,
                    Cout=dqkv, C_off=PAD * ld + 2 * D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
@@ -774,6 +823,7 @@ class FastSpeech2(nn.Module):
         dev = dmel.device
         dmel = dmel.contiguous().float()
         dpost = dpost.contiguous().float()
+        self._side_begin(dev)
 
         # ---- PostNet (postnet_output = LN3-drop(conv_post(...)) + mel_post)
         dpost_pad = self._f32(rowsM, n_mels)
@@ -796,6 +846,7 @@ class FastSpeech2(nn.Module):
             self._conv_wgrad(dE_act, pn.mid[i], B, Tm, wname + ".weight", wname + ".weight", wname + ".bias")
             self._conv_dgrad(dE_act, B, Tm, wname + ".weight", dE_c)
             if i > 0:
+                self._wait_side(dE_act)
                 L.call("fs2_fold_halo", dE_c, B, Tm, E, hp, None, None, None, None, dE_act, int(bf))
         d1_act = self._act(rowsM, E)
         self._ln_bwd(B, Tm, E, pn.c1, self._P("postnet.ln1.weight"), self._P("postnet.ln1.bias"), 1e-5, pn.mean1,
@@ -851,6 +902,7 @@ class FastSpeech2(nn.Module):
             L.call("fs2_add_", ea, eb, rowsP * D)
         L.call("fs2_embedding_bwd", ea, ctx.tokens, B, Tp, D, self.padding_idx,
                self._G("encPreNet.token_embedding.Embedding.weight"))
+        self._side_join()
 
 
     # ---------------------------------------------------------------------- CUDA graphs

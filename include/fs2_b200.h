@@ -144,6 +144,8 @@ int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int T, int D, i
 int fs2_attn_bwd(const void* dO, const void* O, const void* qkv, const void* P, const int* lens, int B, int H, int T,
                  int D, int ldk, float scale, float drop_p, unsigned long long seed,
                  const unsigned long long* seed_dev, void* dS, void* dqkv, void* stream);
+/* measurement hook: when non-NULL, CTA 0 of every fused-attention launch writes a 16-slot cycle breakdown (attention.cu) */
+int fs2_attn_set_debug(long long* dev_buf);
 /* *ctr += inc (the device-side dropout step counter; first node of a captured forward graph) */
 int fs2_counter_add(unsigned long long* ctr, unsigned long long inc, void* stream);
 

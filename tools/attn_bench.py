@@ -49,6 +49,19 @@ def main():
                    B=q, B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=HD, b_s1=HD, b_s2=TP * ld, batch1=H, batch2=B,
                    Cout=O[i % R], C_off=PAD * D, ldc=D, c_s1=HD, c_s2=TP * D, c_bf16=True, ab_bf16=True)
 
+        if os.environ.get("ATTN_DBG"):
+            lib = L.load()
+            dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+            lib.fs2_attn_set_debug.argtypes = [L.C.c_void_p]
+            lib.fs2_attn_set_debug(L.C.c_void_p(dbg.data_ptr()))
+            for name, fn in (("fwd", lambda: L.call("fs2_attn_fwd", qkv[0], lens, B, H, T, D, ldk, sc, 0.1, 5, None, P[0], Pd[0], O[0])),
+                             ("bwd", lambda: L.call("fs2_attn_bwd", dO[0], O[0], qkv[0], P[0], lens, B, H, T, D, ldk, sc, 0.1, 5, None, dS[0], dqkv[0]))):
+                fn(); fn()
+                torch.cuda.synchronize()
+                d = dbg.tolist()
+                print(f"  {name} CTA0: MMA thread total {d[0]} cyc over {d[5]} jobs; waits K {d[1]} S-free {d[2]} P-ready {d[3]} V {d[4]} | "
+                      f"softmax thread total {d[8]}: wait-S {d[9]} ld {d[10]} math+gst {d[11]} wait-Pbuf {d[12]} sts+fence+arrive {d[13]}")
+            lib.fs2_attn_set_debug(None)
         print(f"T={T}: unfused fwd (QK^T + softmax/dropout + PV) {timeit(unfused_fwd):8.1f} us", flush=True)
     print("flag", L.gemm_tc_error_flag())
 
