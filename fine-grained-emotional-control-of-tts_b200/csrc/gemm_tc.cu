@@ -43,6 +43,7 @@ struct TcParams {
   int* err;
   long long* dbg;     // optional: {SM cycles, nanoseconds} of unit 0's lifetime (clock probe for measurements)
   int dbg_mode;       // measurements only (results are garbage): 1 = MMA issue without TMA, 2 = TMA without MMA
+  int epi_transpose;  // 1: coalesced epilogue stores through the per-warp smem staging tile (epi_chunk_t)
 };
 
 __device__ int g_tc_error = 0;
@@ -216,6 +217,102 @@ __device__ __forceinline__ void epi_chunk(const Fs2Gemm& g, const EpiRow& er, co
   }
 }
 
+// Coalesced variant of the vector store path.  tcgen05.ld hands every lane one accumulator ROW, so a direct st.v4 per
+// lane touches 32 different 128-byte lines per instruction; for the short-K GEMMs (projections, 1x1 convs) the L1
+// tag stage then bounds the kernel (4-6 us of epilogue per 128 x N tile against ~1.5 us of MMA).  Here each warp bounces
+// its 32 x 64-byte slab through a private, XOR-swizzled 2 KB shared-memory tile and writes it back transposed: four
+// lanes cover 64 contiguous bytes of one row, one instruction covers 8 rows -- 4x fewer line visits, and the ReLU-mask
+// operand (relu_aux, bf16) is fetched with the same coalesced pattern.  Preconditions (warp-uniform, checked by the
+// caller): full 32-column chunk, unit column stride, no atomics, no halo mirrors in this warp's rows.
+constexpr int EPI_STAGE_BYTES = 2048;                      // per epilogue warp
+constexpr int EPI_STAGE_TOTAL = NUM_EPI_WARPS * EPI_STAGE_BYTES;
+
+template <int MODE>
+__device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, bool row_ok, const uint32_t* r, int nb0,
+                                            long long col0, bool out_bf16, uint8_t* stage) {
+  const int lane = threadIdx.x & 31;
+  const bool mine = row_ok && !er.skip;
+  const unsigned okmask = __ballot_sync(0xffffffffu, mine);
+  const long long mybase = mine ? er.base : 0;
+  const int tr = lane >> 2, tcq = lane & 3;                // transposed role: row tr (+8 per step), 16-byte quarter tcq
+  long long tb[4];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) tb[jj] = __shfl_sync(0xffffffffu, mybase, jj * 8 + tr);
+  const bool live = mine && er.live;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float x = __uint_as_float(r[i]) * g.alpha;
+    if (g.bias) x += g.bias[nb0 + i];
+    if (g.relu) x = fmaxf(x, 0.f);
+    v[i] = live ? x : 0.f;
+  }
+  const uint32_t wr = (uint32_t)lane * 64u, wsw = (uint32_t)((lane >> 1) & 3);
+  if (out_bf16) {
+    uint4 aux[4];
+    const bool has_aux = g.relu_aux != nullptr;
+    if (has_aux) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        aux[jj] = make_uint4(0, 0, 0, 0);
+        if ((okmask >> (jj * 8 + tr)) & 1u)
+          aux[jj] = *reinterpret_cast<const uint4*>((const bf16*)g.relu_aux + tb[jj] + col0 + tcq * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * k], v[8 * k + 1]);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * k + 2], v[8 * k + 3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * k + 4], v[8 * k + 5]);
+      __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * k + 6], v[8 * k + 7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2);
+      pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(stage + wr + (((uint32_t)k ^ wsw) << 4)) = pk;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int row = jj * 8 + tr;
+      uint4 x = *reinterpret_cast<const uint4*>(stage + row * 64 + (((uint32_t)tcq ^ (uint32_t)((row >> 1) & 3)) << 4));
+      if ((okmask >> row) & 1u) {
+        if (has_aux) {
+          // keep a value where the forward activation was > 0: bf16 sign clear and magnitude non-zero
+          const uint32_t a[4] = {aux[jj].x, aux[jj].y, aux[jj].z, aux[jj].w};
+          uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t lo = ((a[i] & 0x8000u) == 0 && (a[i] & 0x7FFFu) != 0) ? 0x0000FFFFu : 0u;
+            const uint32_t hi = ((a[i] & 0x80000000u) == 0 && (a[i] & 0x7FFF0000u) != 0) ? 0xFFFF0000u : 0u;
+            w[i] &= (lo | hi);
+          }
+          x = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        *reinterpret_cast<uint4*>((bf16*)g.C + tb[jj] + col0 + tcq * 8) = x;
+      }
+    }
+    __syncwarp();
+  } else {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(stage + wr + (((uint32_t)k ^ wsw) << 4)) =
+            make_float4(v[half * 16 + 4 * k], v[half * 16 + 4 * k + 1], v[half * 16 + 4 * k + 2], v[half * 16 + 4 * k + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int row = jj * 8 + tr;
+        const float4 x = *reinterpret_cast<const float4*>(stage + row * 64 + (((uint32_t)tcq ^ (uint32_t)((row >> 1) & 3)) << 4));
+        if ((okmask >> row) & 1u) st4((float*)g.C + tb[jj] + col0 + half * 16 + tcq * 4, x);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 template <int MODE, int BN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
@@ -353,6 +450,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     // ---------------- epilogue: 8 warps; TMEM lane quadrant = warp % 4, column half = (warp-2)/4 ----------------
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    uint8_t* stage = smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
     const bool atomic = p.nsplit > 1 || g.accumulate;
     const long long cstr = (MODE == 2 && g.c_col_stride > 1) ? g.c_col_stride : 1;
     const bool al4 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 4 == 0) && (((uintptr_t)g.C) % 16 == 0);
@@ -391,7 +489,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
           if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
         }
         const int nb0 = n0 + c * 32;
-        if (nb0 >= g.N || !row_ok || er.skip) continue;
+        if (nb0 >= g.N) continue;                               // warp-uniform
+        const bool t_ok = p.epi_transpose && nb0 + 32 <= g.N &&
+                          ((vec_f32 && g.relu_aux == nullptr) || (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
+        if (t_ok && __ballot_sync(0xffffffffu, row_ok && (er.mirror != 0 || er.mirror2 != 0)) == 0u) {
+          epi_chunk_t<MODE>(g, er, row_ok, r, nb0, colbase + (long long)c * 32, vec_bf16, stage);
+          continue;
+        }
+        if (!row_ok || er.skip) continue;
         epi_chunk<MODE>(g, er, r, nb0, colbase + (long long)c * 32 * cstr, cstr, atomic, vec_f32, vec_bf16);
       }
     }
@@ -590,6 +695,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
     // ------------------------------------------------------------ epilogue (both CTAs; own 128 rows of the tile)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    uint8_t* stage = smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
     const bool atomic = p.nsplit > 1 || g.accumulate;
     const long long cstr = (MODE == 2 && g.c_col_stride > 1) ? g.c_col_stride : 1;
     const bool al4 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 4 == 0) && (((uintptr_t)g.C) % 16 == 0);
@@ -632,7 +738,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
           }
         }
         const int nb0 = n0 + c * 32;
-        if (nb0 >= g.N || !row_ok || er.skip) continue;
+        if (nb0 >= g.N) continue;                               // warp-uniform
+        const bool t_ok = p.epi_transpose && nb0 + 32 <= g.N &&
+                          ((vec_f32 && g.relu_aux == nullptr) || (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
+        if (t_ok && __ballot_sync(0xffffffffu, row_ok && (er.mirror != 0 || er.mirror2 != 0)) == 0u) {
+          epi_chunk_t<MODE>(g, er, row_ok, r, nb0, colbase + (long long)c * 32, vec_bf16, stage);
+          continue;
+        }
+        if (!row_ok || er.skip) continue;
         epi_chunk<MODE>(g, er, r, nb0, colbase + (long long)c * 32 * cstr, cstr, atomic, vec_f32, vec_bf16);
       }
     }
@@ -728,7 +841,7 @@ int g_num_sms = 0;
 
 template <int MODE, int BN, int STAGES>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256 + EPI_STAGE_TOTAL;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
@@ -778,7 +891,7 @@ int pick_bn(int N, long long m_tiles_x_batch) {
 template <int MODE, int BNS, int NSUB, int STAGES, int NCTA>
 int launch_x(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
   constexpr int TILE_N = BNS * NSUB;
-  constexpr int SMEM = STAGES * (BM * BK * 2 + NSUB * (BNS / NCTA) * BK * 2) + 1024 + 256;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + NSUB * (BNS / NCTA) * BK * 2) + 1024 + 256 + EPI_STAGE_TOTAL;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static int units = 0;       // CTA pairs (or CTAs) that can be resident at once
   auto kern = tcx_gemm_kernel<MODE, BNS, NSUB, STAGES, NCTA>;
@@ -883,6 +996,7 @@ int pick_cfg(int N) {
 int g_dbg_mode = 0;
 int g_use_pair = -1;    // 0: single-CTA kernel only, 1: CTA-pair kernel wherever it applies, 2: heuristic (FS2_TC_PAIR)
 int g_force_cfg = -2;   // FS2_TC_CFG=0|1|2 forces a tile configuration
+int g_epi_transpose = 1;   // FS2_TC_EPIT=0 switches the coalesced (smem-transposed) epilogue off (A/B measurements)
 
 // heuristic kernel choice (measured on B200, tools/gemm_sweep.py): filled in from the sweep
 bool prefer_pair(const Fs2Gemm& g) {
@@ -980,7 +1094,10 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
     g_use_pair = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2;
     const char* c = getenv("FS2_TC_CFG");
     g_force_cfg = c ? atoi(c) : -1;
+    const char* t = getenv("FS2_TC_EPIT");
+    if (t) g_epi_transpose = atoi(t) != 0;
   }
+  p.epi_transpose = g_epi_transpose;
   const bool pair_ok = g.batch1 * g.batch2 == 1 && g.M > BM;
   if (pair_ok && (g_use_pair == 1 || g_use_pair == 3 || (g_use_pair == 2 && prefer_pair(g)))) {
     const int cfg = (g_force_cfg >= 0 && g_force_cfg <= 2) ? g_force_cfg : pick_cfg(g.N);

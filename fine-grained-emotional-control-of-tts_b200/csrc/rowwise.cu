@@ -189,11 +189,12 @@ __global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p) {
 }
 
 // ----------------------------------------------------------------------- LayerNorm bwd --
-__device__ __forceinline__ void block_reduce_cols(float4 (&a)[MAXV], float* out, int C, float (*red)[128], int warp,
+template <int NV>
+__device__ __forceinline__ void block_reduce_cols(float4 (&a)[NV], float* out, int C, float (*red)[128], int warp,
                                                   int lane) {
   if (!out) return;   // uniform across the block
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     __syncthreads();
     red[warp][lane * 4 + 0] = a[i].x;
     red[warp][lane * 4 + 1] = a[i].y;
@@ -214,7 +215,9 @@ __device__ __forceinline__ void block_reduce_cols(float4 (&a)[MAXV], float* out,
 
 // grad wrt the kernel's `out` for row (b,t): dy + fold(dy2) + dhead*head_w*scale, then back through
 // mask, drop_a, tanh, affine, normalisation, (ReLU of x), and the branch dropout.
-template <typename TA>
+// NV = float4 per lane (ceil(C / 128)): 3 for the 384-wide model rows, 4 for the PostNet (512), 1 for n_mels (80);
+// HEAD = the variance predictors' 384 -> 1 output layer is folded in.  Both only size the register arrays.
+template <typename TA, int NV, bool HEAD>
 __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
   __shared__ float red[WARPS][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -224,9 +227,11 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
   TA* da_out = (TA*)p.dact;
   const unsigned long long bump = p.seed_dev ? mix64(*p.seed_dev) : 0ull;
   const DropCfg db{p.drop_b_p, p.drop_b_seed ^ bump}, da{p.drop_a_p, p.drop_a_seed ^ bump};
-  float4 dg[MAXV], dbt[MAXV], dhw[MAXV];
+  float4 dg[NV], dbt[NV], dhw[HEAD ? NV : 1];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) dg[i] = dbt[i] = dhw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) dg[i] = dbt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < (HEAD ? NV : 1); ++i) dhw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float dhb = 0.f;
   for (long long r = (long long)blockIdx.x * WARPS + warp; r < rows; r += (long long)gridDim.x * WARPS) {
     int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
@@ -244,10 +249,10 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
     const int f = p.dy2_fold;
     const long long m1 = (f > 0 && t >= 1 && t <= f) ? -2LL * t * C : 0;
     const long long m2 = (f > 0 && t >= T - 1 - f && t <= T - 2) ? 2LL * (T - 1 - t) * C : 0;
-    float4 xh[MAXV], gx[MAXV];
+    float4 xh[NV], gx[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       int c = lane * 4 + i * 128;
       xh[i] = gx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < C) {
@@ -271,11 +276,11 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
         float4 u = make_float4(h.x * gam.x + bet.x, h.y * gam.y + bet.y, h.z * gam.z + bet.z, h.w * gam.w + bet.w);
         if (p.tanh_act) { u.x = tanhf(u.x); u.y = tanhf(u.y); u.z = tanhf(u.z); u.w = tanhf(u.w); }
         float4 k = drop_scale4(da, (uint64_t)(ro + c) >> 2);
-        if (p.head_w) {
+        if (HEAD && p.head_w) {
           float4 hw = ld4(p.head_w + c);
           g.x += dh * hw.x; g.y += dh * hw.y; g.z += dh * hw.z; g.w += dh * hw.w;
           if (live) {   // d head_w = dhead * out, out = u * drop_a (masked rows contribute 0)
-            dhw[i].x += dh * u.x * k.x; dhw[i].y += dh * u.y * k.y; dhw[i].z += dh * u.z * k.z; dhw[i].w += dh * u.w * k.w;
+            dhw[HEAD ? i : 0].x += dh * u.x * k.x; dhw[HEAD ? i : 0].y += dh * u.y * k.y; dhw[HEAD ? i : 0].z += dh * u.z * k.z; dhw[HEAD ? i : 0].w += dh * u.w * k.w;
           }
         }
         if (!live) g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -292,11 +297,11 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
         gx[i] = g;
       }
     }
-    if (p.head_w && lane == 0) dhb += dh;
+    if (HEAD && p.head_w && lane == 0) dhb += dh;
     s1 = warp_sum(s1) * invC;
     s2 = warp_sum(s2) * invC;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       int c = lane * 4 + i * 128;
       if (c < C) {
         float4 dz;
@@ -325,8 +330,8 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
   // block reduction of the parameter gradients, one atomicAdd per column per block
   block_reduce_cols(dg, p.dgamma, C, red, warp, lane);
   block_reduce_cols(dbt, p.dbeta, C, red, warp, lane);
-  block_reduce_cols(dhw, p.dhead_w, C, red, warp, lane);
-  if (p.dhead_b) {
+  if (HEAD) block_reduce_cols(dhw, p.dhead_w, C, red, warp, lane);
+  if (HEAD && p.dhead_b) {
     __syncthreads();
     if (lane == 0) red[warp][0] = dhb;
     __syncthreads();
@@ -691,7 +696,7 @@ __device__ __forceinline__ int lr_search(const int* e, int Tp, int f, int total)
   return lo;
 }
 
-template <typename TA>
+template <typename TA, int RB>
 __global__ void __launch_bounds__(THREADS) lr_expand_kernel(const float* __restrict__ in, int in_pitch, int in_off,
                                                             const int* __restrict__ ends, const int* __restrict__ mel_lens,
                                                             const float* __restrict__ pe, int B, int Tp, int Tm, int D,
@@ -711,35 +716,35 @@ __global__ void __launch_bounds__(THREADS) lr_expand_kernel(const float* __restr
     if (frame2ph && r0 + lane < out_pitch && f >= 0 && f < Tm) frame2ph[(long long)b * Tm + f] = my_idx;
   }
   const float* in_b = in + ((long long)b * in_pitch + in_off) * D;
-  int idx[LR_RPW];
+  // RB rows in flight per warp (RB = 4: 78 registers -> 3 CTAs / SM; selected by measurement, see fs2_lr_tune)
 #pragma unroll
-  for (int j = 0; j < LR_RPW; ++j) {
-    idx[j] = __shfl_sync(0xffffffffu, my_idx, j);
-    if (r0 + j >= out_pitch) idx[j] = -2;                       // row does not exist
-  }
-  if (idx[0] == -2) return;
-  for (int c = lane * 4; c < D; c += 128) {
-    float4 v[LR_RPW];
+  for (int j0 = 0; j0 < LR_RPW; j0 += RB) {
+    int idx[RB];
 #pragma unroll
-    for (int j = 0; j < LR_RPW; ++j) {
-      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx[j] >= 0) v[j] = ld4(in_b + (long long)idx[j] * D + c);
+    for (int j = 0; j < RB; ++j) {
+      idx[j] = __shfl_sync(0xffffffffu, my_idx, j0 + j);
+      if (r0 + j0 + j >= out_pitch) idx[j] = -2;                // row does not exist
     }
-    if (pe) {
+    if (idx[0] == -2) break;
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 v[RB], pv[RB];
 #pragma unroll
-      for (int j = 0; j < LR_RPW; ++j) {
+      for (int j = 0; j < RB; ++j) {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pv[j] = v[j];
         if (idx[j] >= 0) {
-          const float4 pv = ld4(pe + (long long)(r0 + j - out_off) * D + c);
-          v[j].x += pv.x; v[j].y += pv.y; v[j].z += pv.z; v[j].w += pv.w;
+          v[j] = ld4(in_b + (long long)idx[j] * D + c);
+          if (pe) pv[j] = ld4(pe + (long long)(r0 + j0 + j - out_off) * D + c);
         }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < LR_RPW; ++j) {
-      if (idx[j] == -2) continue;
-      const long long ro = ((long long)b * out_pitch + r0 + j) * D + c;
-      if (of) st4(of + ro, v[j]);
-      if (oa) st4(oa + ro, v[j]);
+      for (int j = 0; j < RB; ++j) {
+        if (idx[j] == -2) continue;
+        v[j].x += pv[j].x; v[j].y += pv[j].y; v[j].z += pv[j].z; v[j].w += pv[j].w;
+        const long long ro = ((long long)b * out_pitch + r0 + j0 + j) * D + c;
+        if (of) st4(of + ro, v[j]);
+        if (oa) st4(oa + ro, v[j]);
+      }
     }
   }
 }
@@ -747,6 +752,7 @@ __global__ void __launch_bounds__(THREADS) lr_expand_kernel(const float* __restr
 // backward of the expansion = per-phoneme sums over its frames.  Frame-parallel (a phoneme-parallel kernel waits on
 // its longest segment): every warp reads LR_RPW consecutive frame rows, merges neighbours that belong to the same
 // phoneme in registers and flushes each run with one 16-byte vector atomic.  dphon must be zero on entry.
+template <int RB>
 __global__ void __launch_bounds__(THREADS) lr_bwd_kernel(const float* __restrict__ df, const float* __restrict__ df2,
                                                          int f_pitch, int f_off, const int* __restrict__ ends, int B, int Tp,
                                                          int Tm, int D, float* __restrict__ dphon, int p_pitch, int p_off) {
@@ -756,41 +762,47 @@ __global__ void __launch_bounds__(THREADS) lr_bwd_kernel(const float* __restrict
   for (int i = threadIdx.x; i < Tp; i += THREADS) s_ends[i] = ends[(long long)b * Tp + i];
   __syncthreads();
   const int total = min(s_ends[Tp - 1], Tm);
-  const int f0 = blockIdx.x * LR_ROWS + warp * LR_RPW;
-  if (f0 >= total) return;
+  const int fw = blockIdx.x * LR_ROWS + warp * LR_RPW;
+  if (fw >= total) return;
   int my_idx = -1;
-  if (lane < LR_RPW) my_idx = lr_search(s_ends, Tp, f0 + lane, total);
-  int idx[LR_RPW];
-#pragma unroll
-  for (int j = 0; j < LR_RPW; ++j) idx[j] = __shfl_sync(0xffffffffu, my_idx, j);
-  const float* src = df + ((long long)b * f_pitch + f_off + f0) * D;
-  const float* src2 = df2 ? df2 + ((long long)b * f_pitch + f_off + f0) * D : nullptr;
+  if (lane < LR_RPW) my_idx = lr_search(s_ends, Tp, fw + lane, total);
   float* dst = dphon + ((long long)b * p_pitch + p_off) * D;
-  for (int c = lane * 4; c < D; c += 128) {
-    float4 v[LR_RPW];
 #pragma unroll
-    for (int j = 0; j < LR_RPW; ++j) {
-      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx[j] >= 0) {
-        v[j] = ld4(src + (long long)j * D + c);
-        if (src2) { const float4 w = ld4(src2 + (long long)j * D + c); v[j].x += w.x; v[j].y += w.y; v[j].z += w.z; v[j].w += w.w; }
-      }
-    }
-    float4 acc = v[0];
-    int cur = idx[0];
+  for (int j0 = 0; j0 < LR_RPW; j0 += RB) {
+    int idx[RB];
 #pragma unroll
-    for (int j = 1; j < LR_RPW; ++j) {
-      if (idx[j] != cur) {
-        if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(dst + (long long)cur * D + c), acc);
-        cur = idx[j];
-        acc = v[j];
-      } else {
-        acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+    for (int j = 0; j < RB; ++j) idx[j] = __shfl_sync(0xffffffffu, my_idx, j0 + j);
+    if (idx[0] < 0) break;                                       // frames are valid up to `total`, then never again
+    const float* src = df + ((long long)b * f_pitch + f_off + fw + j0) * D;
+    const float* src2 = df2 ? df2 + ((long long)b * f_pitch + f_off + fw + j0) * D : nullptr;
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 v[RB];
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx[j] >= 0) {
+          v[j] = ld4(src + (long long)j * D + c);
+          if (src2) { const float4 w = ld4(src2 + (long long)j * D + c); v[j].x += w.x; v[j].y += w.y; v[j].z += w.z; v[j].w += w.w; }
+        }
       }
+      float4 acc = v[0];
+      int cur = idx[0];
+#pragma unroll
+      for (int j = 1; j < RB; ++j) {
+        if (idx[j] != cur) {
+          if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(dst + (long long)cur * D + c), acc);
+          cur = idx[j];
+          acc = v[j];
+        } else {
+          acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+        }
+      }
+      if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(dst + (long long)cur * D + c), acc);
     }
-    if (cur >= 0) atomicAdd(reinterpret_cast<float4*>(dst + (long long)cur * D + c), acc);
   }
 }
+
+int g_lr_rb = 4;      // rows in flight per warp in lr_expand / lr_bwd: 2, 4 or 8 (fs2_lr_tune)
 
 // -------------------------------------------------------------------- row-space utilities --
 template <typename TA>
@@ -830,7 +842,18 @@ __global__ void colsum_kernel(const TX* x, long long rows, int C, long long ld, 
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < C) {
-    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+    // eight independent row loads in flight per thread (the plain loop was latency-bound: 18 % of HBM peak at C = 384)
+    const long long step = (long long)gridDim.y * 8;
+    long long r = (long long)blockIdx.y * 8 + threadIdx.y;
+    for (; r + 7 * step < rows; r += 8 * step) {
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ld4(x + (r + i * step) * ld + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a.x += v[i].x; a.y += v[i].y; a.z += v[i].z; a.w += v[i].w; }
+    }
+#pragma unroll 4
+    for (; r < rows; r += step) {
       float4 v = ld4(x + r * ld + c);
       a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
@@ -1044,8 +1067,16 @@ extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
   const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
   int grid = grid_for_rows(rows);
   if (grid > 148 * 4) grid = 148 * 4;
-  if (p->act_bf16) ln_bwd_kernel<bf16><<<grid, THREADS, 0, ST>>>(*p);
-  else ln_bwd_kernel<float><<<grid, THREADS, 0, ST>>>(*p);
+  const int nv = (p->C + 127) / 128;
+  const bool head = p->head_w != nullptr || p->dhead_w != nullptr || p->dhead_b != nullptr;
+#define LN_BWD_LAUNCH(TA, NV, HEAD) ln_bwd_kernel<TA, NV, HEAD><<<grid, THREADS, 0, ST>>>(*p)
+#define LN_BWD_NV(TA, NV) do { if (head) LN_BWD_LAUNCH(TA, NV, true); else LN_BWD_LAUNCH(TA, NV, false); } while (0)
+#define LN_BWD_TA(TA) do { if (nv == 1) LN_BWD_NV(TA, 1); else if (nv == 2) LN_BWD_NV(TA, 2); else if (nv == 3) LN_BWD_NV(TA, 3); else LN_BWD_NV(TA, 4); } while (0)
+  if (p->act_bf16) LN_BWD_TA(bf16);
+  else LN_BWD_TA(float);
+#undef LN_BWD_TA
+#undef LN_BWD_NV
+#undef LN_BWD_LAUNCH
   return fs2_check_launch();
 }
 
@@ -1150,8 +1181,10 @@ extern "C" int fs2_lr_expand(const float* in, int in_pitch, int in_off, const in
   REQUIRE(B > 0 && B <= 65535 && Tp > 0 && Tp <= 12000 && out_pitch > 0, "fs2_lr_expand: B <= 65535 and 0 < Tp <= 12000 (prefix sums are staged in shared memory)");
   const dim3 grid((out_pitch + LR_ROWS - 1) / LR_ROWS, B);
   const size_t sm = (size_t)Tp * sizeof(int);
-  if (act_bf16) lr_expand_kernel<bf16><<<grid, THREADS, sm, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (bf16*)out_act, out_pitch, out_off, frame2ph);
-  else lr_expand_kernel<float><<<grid, THREADS, sm, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (float*)out_act, out_pitch, out_off, frame2ph);
+#define LR_EXP(TA, RB) lr_expand_kernel<TA, RB><<<grid, THREADS, sm, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (TA*)out_act, out_pitch, out_off, frame2ph)
+  if (act_bf16) { if (g_lr_rb == 2) LR_EXP(bf16, 2); else if (g_lr_rb == 8) LR_EXP(bf16, 8); else LR_EXP(bf16, 4); }
+  else { if (g_lr_rb == 2) LR_EXP(float, 2); else if (g_lr_rb == 8) LR_EXP(float, 8); else LR_EXP(float, 4); }
+#undef LR_EXP
   return fs2_check_launch();
 }
 
@@ -1163,8 +1196,17 @@ extern "C" int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pit
   (void)mel_lens;
   CUDA_CHECK_RET(cudaMemsetAsync(dphon, 0, (size_t)B * p_pitch * D * sizeof(float), ST));
   const dim3 grid((Tm + LR_ROWS - 1) / LR_ROWS, B);
-  lr_bwd_kernel<<<grid, THREADS, (size_t)Tp * sizeof(int), ST>>>(dframes, dframes2, f_pitch, f_off, ends, B, Tp, Tm, D, dphon, p_pitch, p_off);
+#define LR_BWD(RB) lr_bwd_kernel<RB><<<grid, THREADS, (size_t)Tp * sizeof(int), ST>>>(dframes, dframes2, f_pitch, f_off, ends, B, Tp, Tm, D, dphon, p_pitch, p_off)
+  if (g_lr_rb == 2) LR_BWD(2); else if (g_lr_rb == 8) LR_BWD(8); else LR_BWD(4);
+#undef LR_BWD
   return fs2_check_launch();
+}
+
+/* measurement hook: rows in flight per warp (2, 4 or 8) of the LengthRegulator kernels */
+extern "C" int fs2_lr_tune(int rows_in_flight) {
+  REQUIRE(rows_in_flight == 2 || rows_in_flight == 4 || rows_in_flight == 8, "fs2_lr_tune: 2, 4 or 8");
+  g_lr_rb = rows_in_flight;
+  return FS2_OK;
 }
 
 extern "C" int fs2_fold_halo(const float* src, int B, int T, int C, int p, const float* add, const float* add2,

@@ -36,6 +36,8 @@ def peak_gbs():
 
 
 def timeit(fn, ring, iters=40, warm=5):
+    iters = int(os.environ.get("HBM_ITERS", iters))
+    warm = int(os.environ.get("HBM_WARM", warm))
     for i in range(warm):
         fn(i % ring)
     torch.cuda.synchronize()
@@ -80,23 +82,31 @@ def main():
     outs = [torch.empty(B, Tm, D, device=dev) for _ in range(R)]
     us = timeit(lambda i: L.call("fs2_lr_prepare", dur_c, None, 1.0, B, Tp, ends, mel_lens), 1)
     report("lr_prepare (duration scan, B=64,Tp=128)", B * Tp * (8 + 4) + B * 4, us, "latency-bound: 98 KB")
-    us = timeit(lambda i: L.call("fs2_lr_expand", feats[i], Tp, 0, ends, mel_lens, None, B, Tp, Tm, D, outs[i], None, 0,
-                                 Tm, 0, None), R)
-    report("lr_expand fp32 (B=64,Tp=128,Tm=800,D=384)", B * Tp * D * 4 + B * Tm * D * 4 + B * Tp * 4, us,
-           "SURVEY 8d K10: read B*Tp*D*4 + write B*Tm*D*4")
-    # the fused form the model uses: padded rows, + pos-enc, fp32 residual stream + bf16 operand copy
     pe = torch.randn(Tm, D, device=dev)
     of = [torch.empty(B * (Tm + 8), D, device=dev) for _ in range(R)]
     oa = [torch.empty(B * (Tm + 8), D, device=dev, dtype=torch.bfloat16) for _ in range(R)]
     fin = [torch.randn(B * (Tp + 8), D, device=dev) for _ in range(R)]
-    us = timeit(lambda i: L.call("fs2_lr_expand", fin[i], Tp + 8, PAD, ends, mel_lens, pe, B, Tp, Tm, D, of[i], oa[i], 1,
-                                 Tm + 8, PAD, None), R)
-    report("lr_expand fused (+pos-enc, fp32 + bf16 outputs, padded rows)", B * Tp * D * 4 + B * (Tm + 8) * D * 6 + Tm * D * 4,
-           us, "model form: writes the fp32 stream and the bf16 GEMM operand in one pass")
     df = [torch.randn(B * (Tm + 8), D, device=dev) for _ in range(R)]
     dph = [torch.zeros(B * (Tp + 8), D, device=dev) for _ in range(R)]
-    us = timeit(lambda i: L.call("fs2_lr_bwd", df[i], None, Tm + 8, PAD, ends, mel_lens, B, Tp, Tm, D, dph[i], Tp + 8, PAD), R)
-    report("lr_bwd (segment sums, B=64)", B * Tm * D * 4 + B * Tp * D * 4, us, "read B*Tm*D*4, write B*Tp*D*4")
+    lib = L.load()
+    lib.fs2_lr_tune.argtypes = [L.C.c_int]
+    for rb in [int(x) for x in os.environ.get("LR_RB", "4").split(",")]:
+        lib.fs2_lr_tune(rb)
+        tag = f" [rows in flight {rb}]"
+        us = timeit(lambda i: L.call("fs2_lr_expand", feats[i], Tp, 0, ends, mel_lens, None, B, Tp, Tm, D, outs[i], None, 0,
+                                     Tm, 0, None), R)
+        report("lr_expand fp32 (B=64,Tp=128,Tm=800,D=384)" + tag, B * Tp * D * 4 + B * Tm * D * 4 + B * Tp * 4, us,
+               "SURVEY 8d K10: read B*Tp*D*4 + write B*Tm*D*4")
+        # the fused form the model uses: padded rows, + pos-enc, fp32 residual stream + bf16 operand copy
+        us = timeit(lambda i: L.call("fs2_lr_expand", fin[i], Tp + 8, PAD, ends, mel_lens, pe, B, Tp, Tm, D, of[i], oa[i], 1,
+                                     Tm + 8, PAD, None), R)
+        report("lr_expand fused (+pos-enc, fp32 + bf16 outputs, padded rows)" + tag,
+               B * Tp * D * 4 + B * (Tm + 8) * D * 6 + Tm * D * 4, us,
+               "model form: writes the fp32 stream and the bf16 GEMM operand in one pass")
+        us = timeit(lambda i: L.call("fs2_lr_bwd", df[i], None, Tm + 8, PAD, ends, mel_lens, B, Tp, Tm, D, dph[i], Tp + 8, PAD), R)
+        report("lr_bwd (segment sums, B=64)" + tag, B * Tm * D * 4 + B * Tp * D * 4, us,
+               "read B*Tm*D*4, write B*Tp*D*4 (+ the 13 MB memset of dphon inside the call)")
+    lib.fs2_lr_tune(4)
     del feats, outs, of, oa, fin, df, dph
 
     # ------------------------------------------------------------------------ average_over_durations (K8)
