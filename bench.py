@@ -106,8 +106,8 @@ def step_flops(B, Tp, Tm, cfg):
     return 3 * fwd
 
 
-def make_batches(data, rank, n, batch=BATCH):
-    return data.synthetic_batches(batch, n, seed=1234, rank=rank)
+def make_batches(data, rank, n, batch=BATCH, world=1):
+    return data.synthetic_batches(batch, n, seed=1234, rank=rank, world=world)
 
 
 def to_dev(batch, intensity, dev, pinned=False):
@@ -253,7 +253,7 @@ def main():
     crit = pkg.Loss(**pkg.DEFAULT_LOSS_CONFIG)
     opt = pkg.FusedAdamW(model, lr=1e-4)
     trainer = par.DataParallelStep(model, crit, opt)
-    host = [pin(*b) for b in make_batches(data, rank, N_DISTINCT)]
+    host = [pin(*b) for b in make_batches(data, rank, N_DISTINCT, world=world)]
     resident = [to_dev(b, i, dev) for b, i in host]
     frames = [int(b[7].sum()) for b, _ in host]
     shapes = [(b[0].shape[1], b[3].shape[1]) for b, _ in host]
@@ -320,7 +320,8 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "FastSpeech2 full training step (BASELINE configs[2]: fwd + 5xMSE + SSIM + bwd + AdamW"
-                               + (", + 1 NCCL flat-grad all-reduce" if world > 1 else "") + ")",
+                               + (", + NCCL all-reduce of the flat fp32 gradient in 2 pieces, the decoder/PostNet piece overlapped with "
+                                  "the rest of the backward" if world > 1 else "") + ")",
                    "batch_per_gpu": BATCH, "global_batch": BATCH * world, "max_phonemes": 128, "max_frames": 800,
                    "n_mels": 80, "params": 85295299, "distinct_batches": N_DISTINCT,
                    "padded_shapes_Tp_Tm": shapes, "parallelism": f"dp{world}",

@@ -83,19 +83,30 @@ def collate(utts):
 
 
 def synthetic_batches(batch_size, n_batches, seed=1234, rank=0, min_tp=24, max_tp=128,
-                      max_frames=800, pool_factor=8):
+                      max_frames=800, pool_factor=8, world=1):
     """Length-bucketed synthetic batches: draw a pool of pool_factor*B utterances,
-    sort by mel length, slice consecutive groups of B."""
+    sort by mel length, slice consecutive groups of B.
+
+    world == 1 (default): one rank's private stream of batches, seeded by (seed, rank, step).
+    world > 1 (data parallel): ONE pool of pool_factor*B*world utterances per draw, shared by all
+    ranks (same seed everywhere); the sorted pool is cut into pool_factor "length classes" of `world` consecutive
+    groups and rank r takes group r of a class, so the ranks of one step pad to (nearly) the same rectangle and
+    nobody waits at the gradient all-reduce.  The classes are visited in the order the single-GPU stream visits
+    its groups, so the mix of short and long batches per rank is the same at every world size."""
     out = []
     step = 0
     while len(out) < n_batches:
-        g = torch.Generator().manual_seed(seed + 1000 * rank + step)
+        g = torch.Generator().manual_seed(seed + 1000 * (rank if world == 1 else 0) + step)
         pool = [_one_utterance(g, min_tp, max_tp, max_frames) for _ in range(pool_factor * batch_size)]
+        n_groups = len(pool) // batch_size + (1 if len(pool) % batch_size else 0)
+        perm = torch.randperm(n_groups, generator=g).tolist()
+        if world > 1:
+            gw = torch.Generator().manual_seed(seed + step + 7919 * world)
+            pool = [_one_utterance(gw, min_tp, max_tp, max_frames) for _ in range(pool_factor * batch_size * world)]
         pool.sort(key=lambda u: u["mel"].shape[0])
         groups = [pool[i:i + batch_size] for i in range(0, len(pool), batch_size)]
-        perm = torch.randperm(len(groups), generator=g).tolist()
         for k in perm:
-            out.append(collate(groups[k]))
+            out.append(collate(groups[k * world + rank] if world > 1 else groups[k]))
             if len(out) == n_batches:
                 break
         step += 1

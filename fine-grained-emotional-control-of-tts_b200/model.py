@@ -183,6 +183,8 @@ class FastSpeech2(nn.Module):
         # queued on a second stream (fork/join through events, also inside graph captures) and fill the SMs the
         # dgrad chain leaves idle (short grids, wave tails, memory-bound LN kernels)
         self.overlap_wgrad = True
+        self._split_lo = None
+        self.grad_ready_hook = None   # callable(lo, hi): flat-gradient range [lo, hi) is final (set by DataParallelStep)
         self._side = None
         self._side_stream = None
         self._side_reads = {}
@@ -804,6 +806,32 @@ class FastSpeech2(nn.Module):
 
     # -------------------------------------------------------------------------- backward
     def _backward_impl(self, ctx, dmel, dpost, dpd, dpp, dpe, capturing=False):
+        """Whole backward = part A (PostNet, mel linear, decoder) then part B (LengthRegulator, variance adaptor,
+        conditioning, encoder).  After A the gradients of `decoder.* / linear.* / postnet.*` -- the tail
+        [grad_split_lo, numel) of the flat gradient buffer -- are final; `grad_ready_hook(lo, hi)` lets the data-parallel
+        step start their all-reduce while B still runs."""
+        mid = self._backward_a(ctx, dmel, dpost, capturing)
+        if not capturing:
+            self._grad_ready()
+        self._backward_b(ctx, mid, dpd, dpp, dpe)
+
+    @property
+    def grad_split_lo(self):
+        """First element of the flat buffers that belongs to decoder.* / linear.* / postnet.* (they are the tail of
+        the reference's state_dict order)."""
+        if self._split_lo is None:
+            tail = ("decoder.", "linear.", "postnet.")
+            lo = min(o for k, (o, _) in self.store.offsets.items() if k.startswith(tail))
+            if any(o >= lo and not k.startswith(tail) for k, (o, _) in self.store.offsets.items()):
+                lo = self.store.flat.numel()         # unexpected layout: nothing is declared ready early
+            self._split_lo = lo
+        return self._split_lo
+
+    def _grad_ready(self):
+        if self.grad_ready_hook is not None:
+            self.grad_ready_hook(self.grad_split_lo, self.store.flat.numel())
+
+    def _backward_a(self, ctx, dmel, dpost, capturing=False):
         if not capturing and ctx.generation != self._generation:
             raise RuntimeError("fs2_b200: backward() of a forward whose workspace has been reused by a later forward; "
                                "call backward before the next forward of the same model")
@@ -867,6 +895,17 @@ class FastSpeech2(nn.Module):
 
         # ---- decoder
         da, db_ = self._stack_bwd(self.dec, ctx.dec_saves, ctx.dec_fin, ddec, None, B, Tm, ctx.mel_lens, None)
+        self._side_join()        # decoder / linear / postnet gradients are complete on the main stream from here on
+        return da, db_
+
+    def _backward_b(self, ctx, mid, dpd, dpp, dpe):
+        da, db_ = mid
+        bf = self._bf16
+        D = self.D
+        B, Tp, Tm = ctx.B, ctx.Tp, ctx.Tm
+        rowsP = B * (Tp + 2 * PAD)
+        hv = (self.kd - 1) // 2
+        self._side_begin(da.device)
         # ---- LengthRegulator: segment sums (rows f >= mel_len are never inside a segment -> mask is implicit)
         dAE = self._f32(rowsP, D)
         L.call("fs2_lr_bwd", da, db_, Tm + 2 * PAD, PAD, ctx.ends, ctx.mel_lens, B, Tp, Tm, D, dAE, Tp + 2 * PAD, PAD)
@@ -990,10 +1029,13 @@ class FastSpeech2(nn.Module):
         n0 = L.launch_count()
         entry.arena_bufs = [a.buf for a in self._arenas]
         entry.grad_in = [torch.zeros_like(outs[i]) for i in (0, 1, 2, 3, 5)]
+        ga = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            mid = self._backward_a(ctx, entry.grad_in[0], entry.grad_in[1], capturing=True)
         gb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gb):
-            self._backward_impl(ctx, *entry.grad_in, capturing=True)
-        entry.bwd = gb
+            self._backward_b(ctx, mid, *entry.grad_in[2:])
+        entry.bwd_a, entry.bwd_b = ga, gb
         entry.n_bwd = L.launch_count() - n0
         self._graphs[key] = entry
         return entry
@@ -1031,6 +1073,8 @@ class _FS2Function(torch.autograd.Function):
             model.store.ensure_grads()
             for dst, src in zip(entry.grad_in, (dmel, dpost, dpd, dpp, dpe)):
                 dst.copy_(src.reshape(dst.shape), non_blocking=True)
-            entry.bwd.replay()
+            entry.bwd_a.replay()
+            model._grad_ready()
+            entry.bwd_b.replay()
             model.replayed_launches += entry.n_bwd
         return (torch.zeros(1, device=dmel.device),) + (None,) * 10

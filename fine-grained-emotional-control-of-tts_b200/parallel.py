@@ -47,24 +47,51 @@ def broadcast_flat_(flat, src=0, group=None):
 
 
 class DataParallelStep:
-    """forward + loss + backward + single flat-gradient all-reduce + fused AdamW.
+    """forward + loss + backward + flat-gradient all-reduce + fused AdamW.
+
+    The gradient is reduced in two pieces of ONE flat fp32 buffer: the tail that holds decoder / mel-linear / PostNet
+    gradients is final when the decoder's backward ends (about 75 % into the backward), so its all-reduce is issued
+    there (async, NCCL's own stream) and travels over NVLink while the variance adaptor and the encoder are still
+    back-propagating; the head follows after the backward.  No other collective exists on the path.
 
     DP semantics: the reduced gradient is the MEAN over ranks of each rank's local-batch gradient,
     which equals the reference's gradient on the concatenated batch for the MSE terms (SSIM and the attn-mask
     quirk depend on local batch composition)."""
 
-    def __init__(self, model, criterion, optimizer, group=None):
+    def __init__(self, model, criterion, optimizer, group=None, overlap=True):
         self.model, self.criterion, self.optimizer, self.group = model, criterion, optimizer, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.overlap = overlap
+        self._pending = []
+        self._early_lo = None
         if self.world > 1:
             broadcast_flat_(model.store.flat, 0, group)      # identical replicas
+
+    def _early_reduce(self, lo, hi):
+        g = self.model.store.flat_grad
+        if lo < hi:
+            self._pending.append(dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._early_lo = lo
 
     def __call__(self, batch, intensity, epoch=0):
         tokens, speakers, in_lens, mel, pitch, energy, dur, out_lens = batch[:8]
         self.optimizer.zero_grad()
         preds = self.model(tokens, speakers, dur, pitch, energy, intensity=intensity)
         losses = self.criterion(preds, (mel, dur, pitch, energy, out_lens, in_lens), epoch)
-        losses["total_loss"].backward()
-        allreduce_flat_(self.model.store.flat_grad, self.world, self.group)
+        self._pending, self._early_lo = [], None
+        hook = self.world > 1 and self.overlap
+        if hook:
+            self.model.grad_ready_hook = self._early_reduce
+        try:
+            losses["total_loss"].backward()
+        finally:
+            if hook:
+                self.model.grad_ready_hook = None
+        g = self.model.store.flat_grad
+        if self.world > 1:
+            head = g if self._early_lo is None else g[: self._early_lo]
+            allreduce_flat_(head, self.world, self.group)
+            for w in self._pending:
+                w.wait()
         self.optimizer.step(grad_scale=1.0 / self.world)
         return losses, preds

@@ -81,6 +81,22 @@ def test_synthetic_batch_recipe():
     assert not torch.equal(other[0][0][0], batches[0][0][0]) or other[0][0][0].shape != batches[0][0][0].shape
 
 
+def test_data_parallel_sharding_keeps_ranks_on_similar_rectangles():
+    """the ranks of one step draw neighbouring length buckets of one shared pool, so their padded
+    rectangles (= step cost) are close and the per-rank mix of short and long batches matches the 1-GPU stream."""
+    data = importlib.import_module(PKG + ".data")
+    world = 4
+    per_rank = [data.synthetic_batches(8, 4, seed=1234, rank=r, world=world) for r in range(world)]
+    for step in range(4):
+        tms = [per_rank[r][step][0][3].shape[1] for r in range(world)]
+        assert tms == sorted(tms)                                  # consecutive groups of the sorted pool
+        assert max(tms) - min(tms) <= 0.35 * max(tms) + 40
+    firsts = [per_rank[r][0][0][0] for r in range(world)]
+    assert any(firsts[0].shape != f.shape or not torch.equal(firsts[0], f) for f in firsts[1:])   # different utterances
+    again = data.synthetic_batches(8, 4, seed=1234, rank=2, world=world)
+    assert all(torch.equal(a[0][3], b[0][3]) for a, b in zip(again, per_rank[2]))                # deterministic
+
+
 def _dp_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
