@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(att_threads(NCH), 1) attn_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------ TMA producer
@@ -491,7 +492,7 @@ int launch_attn(const CUtensorMap& ta, const CUtensorMap& tkv, const AttnParams&
     configured = true;
   }
   const int nqb = (p.T + AQ - 1) / AQ;
-  attn_kernel<BWD, NCH><<<nqb * p.B * p.H, att_threads(NCH), ATT_SMEM, st>>>(ta, tkv, p);
+  FS2_LAUNCH((attn_kernel<BWD, NCH>), nqb * p.B * p.H, att_threads(NCH), ATT_SMEM, st, ta, tkv, p);
   return fs2_check_launch();
 }
 

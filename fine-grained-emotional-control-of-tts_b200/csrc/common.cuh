@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <string.h>
 
 #define FS2_OK 0
 #define FS2_ERR_ARG 1
@@ -25,6 +26,36 @@ typedef __nv_bfloat16 bf16;
 
 void fs2_set_error(const char* msg);
 int fs2_check_launch();
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// Every kernel of the library starts with pdl_wait(): it blocks until the preceding kernel of the stream has completed
+// and its writes are visible, then lets the NEXT kernel begin launching.  Together with the launch attribute set by
+// fs2_launch() this overlaps a kernel's launch latency, block scheduling and prologue (barrier init, TMEM allocation,
+// tensor-map prefetch) with the tail of its predecessor -- the step is ~400 short kernels, 3-6 us of ramp/tail each
+// (profiles/r01_summary.md).  Works inside CUDA-graph captures (programmatic edges).  FS2_PDL=0 switches it off.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+extern int g_fs2_pdl;      // core.cu
+
+template <typename... KArgs, typename... Args>
+inline void fs2_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_fs2_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface in fs2_check_launch()
+}
+#define FS2_LAUNCH(kern, grid, block, smem, stream, ...) fs2_launch(kern, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
 
 template <typename T> struct ActT;
 template <> struct ActT<float> {

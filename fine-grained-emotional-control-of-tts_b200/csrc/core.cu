@@ -4,6 +4,14 @@
 #include "common.cuh"
 #include "../../include/fs2_b200.h"
 
+#include <stdlib.h>
+
+static int pdl_from_env() {
+  const char* e = getenv("FS2_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}
+int g_fs2_pdl = pdl_from_env();
+
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 

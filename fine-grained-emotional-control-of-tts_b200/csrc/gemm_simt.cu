@@ -17,6 +17,7 @@ __device__ __forceinline__ float fetch(const TA* base, long long ld, int row, in
 
 template <typename TA>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(Fs2Gemm g) {
+  pdl_wait();
   __shared__ float As[TK][TM + 1];
   __shared__ float Bs[TK][TN + 1];
   const int z = blockIdx.z;
@@ -116,7 +117,7 @@ extern "C" int fs2_gemm_simt(const Fs2Gemm* g, void* stream) {
   int nsplit = g->split_k > 1 ? g->split_k : 1;
   if (nsplit > 1 && g->c_bf16) { fs2_set_error("fs2_gemm_simt: split_k needs fp32 C"); return FS2_ERR_ARG; }
   dim3 grid((Ntot + TN - 1) / TN, (g->M + TM - 1) / TM, g->batch1 * g->batch2 * nsplit);
-  if (g->ab_bf16) gemm_simt_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(*g);
-  else gemm_simt_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(*g);
+  if (g->ab_bf16) FS2_LAUNCH((gemm_simt_kernel<bf16>), grid, 256, 0, (cudaStream_t)stream, *g);
+  else FS2_LAUNCH((gemm_simt_kernel<float>), grid, 256, 0, (cudaStream_t)stream, *g);
   return fs2_check_launch();
 }

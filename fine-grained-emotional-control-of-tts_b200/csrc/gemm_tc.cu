@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   // Persistent tile loop: tile t -> (n-tile fastest so CTAs running together share the A rows in L2).
   // Every role walks the same sequence; smem stage / phase counters run across tiles.
@@ -584,6 +585,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs of the pair)
@@ -860,7 +862,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream
   if (total > 0x7FFFFFFF) { fs2_set_error("fs2_gemm_tc: too many tiles"); return FS2_ERR_ARG; }
   p.total_tiles = (int)total;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  tc_gemm_kernel<MODE, BN, STAGES><<<grid, NTHREADS, SMEM, st>>>(ta, tb, p);
+  FS2_LAUNCH((tc_gemm_kernel<MODE, BN, STAGES>), grid, NTHREADS, SMEM, st, ta, tb, p);
   return fs2_check_launch();
 }
 
@@ -902,16 +904,18 @@ int launch_x(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStre
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(NTHREADS, 1, 1);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_fs2_pdl ? 2 : 1;
   if (units == 0) {
     CUDA_CHECK_RET(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     if (NCTA == 2) {

@@ -32,6 +32,7 @@ struct MseArgs {
 };
 
 __global__ void __launch_bounds__(256) mse_kernel(MseArgs a) {
+  pdl_wait();
   __shared__ float sh[8];
   const int b = blockIdx.y;
   const int ml = (int)a.mel_len[b];
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(256) mse_kernel(MseArgs a) {
 
 __global__ void mse_finalize_kernel(const float* sums, const int64_t* mel_len, const int64_t* phon_len, int B, int Tp,
                                     int n_mels, float* out) {
+  pdl_wait();
   const int k = threadIdx.x;
   if (k >= 5) return;
   float acc = 0.f;
@@ -133,6 +135,7 @@ __device__ __forceinline__ float unorderable(unsigned u) {
 
 __global__ void __launch_bounds__(512) ssim_minmax_kernel(const float* pred, const float* tgt, const int64_t* mel_len,
                                                           int Tm, int W, SsimStats* stats) {
+  pdl_wait();
   __shared__ unsigned long long s_min[16], s_max[16];
   __shared__ float s_tmn[16], s_tmx[16];
   const int b = blockIdx.x;
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(512) ssim_minmax_kernel(const float* pred, con
 __global__ void __launch_bounds__(256) ssim_map_kernel(const float* pred, const float* tgt, const int64_t* mel_len,
                                                        int Tm, int W, const SsimStats* stats, float* fa, float* fb,
                                                        float* fc, double* total) {
+  pdl_wait();
   __shared__ float q[TR + KS - 1][MAXW], tn[TR + KS - 1][MAXW];
   __shared__ float hz[5][TR + KS - 1][MAXW - KS + 1];
   __shared__ float sh[8];
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(256) ssim_grad_kernel(const float* pred, const
                                                         int B, int Tm, int W, const SsimStats* stats, const float* fa,
                                                         const float* fb, const float* fc, const double* total,
                                                         float weight, float* S, float* dmel) {
+  pdl_wait();
   __shared__ float f[3][TR + KS - 1][MAXW - KS + 1];
   __shared__ float vz[3][TR][MAXW - KS + 1];
   __shared__ float sh[8];
@@ -325,6 +330,7 @@ __global__ void __launch_bounds__(256) ssim_grad_kernel(const float* pred, const
 
 __global__ void ssim_finalize_kernel(const double* total, const SsimStats* stats, const float* S, int B, int Tm, int W,
                                      float* out, float* dmel) {
+  pdl_wait();
   const int Hm = Tm - (KS - 1), Wm = W - (KS - 1);
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0) {
@@ -387,10 +393,10 @@ extern "C" int fs2_mse_losses(const float* mel_out, const float* post_out, const
   int gx = (int)((per / 4 + 255) / 256);
   if (gx > 64) gx = 64;
   if (gx < 1) gx = 1;
-  mse_kernel<<<dim3(gx, B), 256, 0, ST>>>(a);
+  FS2_LAUNCH((mse_kernel), dim3(gx, B), 256, 0, ST, a);
   int rc = fs2_check_launch();
   if (rc) return rc;
-  mse_finalize_kernel<<<1, 32, 0, ST>>>(sums_ws, mel_len, phon_len, B, Tp, n_mels, out);
+  FS2_LAUNCH((mse_finalize_kernel), 1, 32, 0, ST, sums_ws, mel_len, phon_len, B, Tp, n_mels, out);
   return fs2_check_launch();
 }
 
@@ -414,17 +420,17 @@ extern "C" int fs2_ssim_loss(const float* mel_out, const float* mel_tgt, const i
   float* fb = fa + (long long)B * Hm * Wm;
   float* fc = fb + (long long)B * Hm * Wm;
   CUDA_CHECK_RET(cudaMemsetAsync(ws, 0, sizeof(float) * (16 + 2LL * B), ST));
-  ssim_minmax_kernel<<<B, 512, 0, ST>>>(mel_out, mel_tgt, mel_len, Tm, n_mels, stats);
+  FS2_LAUNCH((ssim_minmax_kernel), B, 512, 0, ST, mel_out, mel_tgt, mel_len, Tm, n_mels, stats);
   if ((rc = fs2_check_launch())) return rc;
-  ssim_map_kernel<<<dim3((unsigned)((Hm + TR - 1) / TR), B), 256, 0, ST>>>(mel_out, mel_tgt, mel_len, Tm, n_mels, stats,
+  FS2_LAUNCH((ssim_map_kernel), dim3((unsigned)((Hm + TR - 1) / TR), B), 256, 0, ST, mel_out, mel_tgt, mel_len, Tm, n_mels, stats,
                                                                            fa, fb, fc, total);
   if ((rc = fs2_check_launch())) return rc;
   if (dmel_out) {
-    ssim_grad_kernel<<<dim3((unsigned)((Tm + TR - 1) / TR), B), 256, 0, ST>>>(mel_out, mel_tgt, mel_len, B, Tm, n_mels,
+    FS2_LAUNCH((ssim_grad_kernel), dim3((unsigned)((Tm + TR - 1) / TR), B), 256, 0, ST, mel_out, mel_tgt, mel_len, B, Tm, n_mels,
                                                                               stats, fa, fb, fc, total, weight, S,
                                                                               dmel_out);
     if ((rc = fs2_check_launch())) return rc;
   }
-  ssim_finalize_kernel<<<(B + 63) / 64, 64, 0, ST>>>(total, stats, S, B, Tm, n_mels, out, dmel_out);
+  FS2_LAUNCH((ssim_finalize_kernel), (B + 63) / 64, 64, 0, ST, total, stats, S, B, Tm, n_mels, out, dmel_out);
   return fs2_check_launch();
 }

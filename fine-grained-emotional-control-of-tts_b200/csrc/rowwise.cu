@@ -57,6 +57,7 @@ __device__ __forceinline__ bool halo_row_needs_zero(int t, int T, int halo) {
 
 // ------------------------------------------------------------------ embedding + posenc --
 __global__ void count_nonpad_kernel(const int64_t* tokens, int B, int Tp, int pad_idx, int* lens) {
+  pdl_wait();
   int b = blockIdx.x;
   int cnt = 0;
   for (int t = threadIdx.x; t < Tp; t += 32) cnt += (tokens[(long long)b * Tp + t] != pad_idx) ? 1 : 0;
@@ -67,6 +68,7 @@ __global__ void count_nonpad_kernel(const int64_t* tokens, int B, int Tp, int pa
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) embed_posenc_kernel(const int64_t* tokens, const float* emb, const float* pe,
                                                                int B, int Tp, int D, int pad_idx, float* of, TA* oa) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int TP = Tp + 2 * FS2_PAD;
   const long long rows = (long long)B * TP;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(THREADS) embed_posenc_kernel(const int64_t* to
 
 __global__ void embedding_bwd_kernel(const float* dx, const int64_t* tokens, int B, int Tp, int D, int pad_idx,
                                      float* demb) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long rows = (long long)B * Tp;
   const int TP = Tp + 2 * FS2_PAD;
@@ -104,6 +107,7 @@ __global__ void embedding_bwd_kernel(const float* dx, const int64_t* tokens, int
 // ----------------------------------------------------------------------- LayerNorm fwd --
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int T = p.T, C = p.C, TP = T + 2 * FS2_PAD;
   const long long rows = (long long)p.B * TP;
@@ -219,6 +223,7 @@ __device__ __forceinline__ void block_reduce_cols(float4 (&a)[NV], float* out, i
 // HEAD = the variance predictors' 384 -> 1 output layer is folded in.  Both only size the register arrays.
 template <typename TA, int NV, bool HEAD>
 __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
+  pdl_wait();
   __shared__ float red[WARPS][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = p.T, C = p.C, TP = T + 2 * FS2_PAD;
@@ -355,6 +360,7 @@ __device__ __forceinline__ int quirk_kv(const int* lens, int B, int H, int bh) {
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) softmax_fwd_kernel(const float* S, const int* lens, int B, int H, int T,
                                                               int ldk, float scale, DropCfg dc, const unsigned long long* seed_dev, TA* P, TA* Pd) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   if (seed_dev) dc.seed ^= mix64(*seed_dev);
   const long long rows = (long long)B * H * T;
@@ -402,6 +408,7 @@ template <typename TA>
 __global__ void __launch_bounds__(THREADS) softmax_bwd_kernel(const TA* P, const float* dPd, const int* lens, int B,
                                                               int H, int T, int ldk, float scale, DropCfg dc,
                                                               const unsigned long long* seed_dev, TA* dS) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   if (seed_dev) dc.seed ^= mix64(*seed_dev);
   const long long rows = (long long)B * H * T;
@@ -434,6 +441,7 @@ __global__ void __launch_bounds__(THREADS) softmax_bwd_kernel(const TA* P, const
 // ------------------------------------------------------------- speaker / intensity cond --
 __global__ void spk_proj_kernel(const float* Wcat, const float* spk_emb, const int64_t* speakers, int B, int D,
                                 float* sp) {
+  pdl_wait();
   // sp[b, c] = sum_e Wcat[c, D + e] * spk_emb[speakers[b], e]; one warp per (b, c)
   const int lane = threadIdx.x & 31;
   const long long n = (long long)B * D;
@@ -453,6 +461,7 @@ template <typename TA>
 __global__ void __launch_bounds__(THREADS) cond_finish_kernel(const float* G, const float* Wcat, const float* sp,
                                                               const float* intensity, const int* lens, int B, int Tp,
                                                               int D, float* yf, TA* ya, int halo) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int TP = Tp + 2 * FS2_PAD;
   const long long rows = (long long)B * TP;
@@ -493,6 +502,7 @@ __global__ void __launch_bounds__(THREADS) cond_finish_kernel(const float* G, co
 // dsum[b,c] = sum_t dy[b,t,c];  dWi[c,i] += sum_{b,t} dy[b,t,c] * int[b,t,i]     (dy already masked)
 __global__ void cond_bwd_rows_kernel(const float* dy, const float* intensity, int B, int Tp, int D, float* dsum,
                                      float* dWcat) {
+  pdl_wait();
   const int b = blockIdx.x;
   const int TP = Tp + 2 * FS2_PAD;
   const int ldw = 2 * D + 5;
@@ -513,6 +523,7 @@ __global__ void cond_bwd_rows_kernel(const float* dy, const float* intensity, in
 // dWs[c,e] += sum_b dsum[b,c]*emb[spk[b],e];   dspk_emb[spk[b],e] += sum_c Ws[c,e]*dsum[b,c]
 __global__ void cond_bwd_spk_kernel(const float* dsum, const float* Wcat, const float* spk_emb, const int64_t* speakers,
                                     int B, int D, float* dWcat, float* dspk_emb) {
+  pdl_wait();
   const int ldw = 2 * D + 5;
   const long long n = (long long)D * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -535,6 +546,7 @@ __global__ void cond_bwd_spk_kernel(const float* dsum, const float* Wcat, const 
 // rounds every prefix to fp32; segment sum = difference of two fp32 prefixes; mean over non-zero frames.
 __global__ void avg_over_durations_kernel(const float* values, const int64_t* durs, int B, int Tp, int Tm, float* avg,
                                           int* starts, int* ends, int* nz) {
+  pdl_wait();
   extern __shared__ unsigned char smraw[];
   float* vc = (float*)smraw;            // Tm+1 prefix sums
   int* nc = (int*)(vc + Tm + 1);        // Tm+1 non-zero counts
@@ -585,6 +597,7 @@ template <typename TA>
 __global__ void __launch_bounds__(THREADS) embed_add_kernel(const float* x, const float* contour, const float* w,
                                                             const float* bias, int ksize, const int* lens, int B, int Tp,
                                                             int D, float* yf, TA* ya, int halo) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int TP = Tp + 2 * FS2_PAD;
   const long long rows = (long long)B * TP;
@@ -618,6 +631,7 @@ __global__ void __launch_bounds__(THREADS) embed_add_kernel(const float* x, cons
 // dw[c,j] += sum_{b,t} dy[b,t,c]*contour_r[b,t+j-p]; dbias[c] += sum dy   (all rect rows, unmasked)
 __global__ void embed_add_bwd_kernel(const float* dy, const float* contour, int ksize, int B, int Tp, int D, float* dw,
                                      float* dbias) {
+  pdl_wait();
   const int TP = Tp + 2 * FS2_PAD;
   const int pad = (ksize - 1) / 2;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -637,12 +651,14 @@ __global__ void embed_add_bwd_kernel(const float* dy, const float* contour, int 
 
 // ---------------------------------------------------------------------- LengthRegulator --
 __global__ void dur_decode_kernel(const float* log_dur, long long n, float* fdur) {
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) fdur[i] = fmaxf(expm1f(log_dur[i]), 0.f);   // model.py:372-375
 }
 
 __global__ void lr_prepare_kernel(const int64_t* dur, const float* fdur, float pace, int B, int Tp, int* ends,
                                   int* mel_lens) {
+  pdl_wait();
   const int b = blockIdx.x, lane = threadIdx.x;
   int carry = 0;
   for (int base = 0; base < Tp; base += 32) {
@@ -668,6 +684,7 @@ __global__ void lr_prepare_kernel(const int64_t* dur, const float* fdur, float p
 
 // mel_lens -> int64 copy for the host + a check that the caller-supplied frame count equals max(mel_lens)
 __global__ void lr_finalize_kernel(const int* mel_lens, int B, int Tm_expected, long long* out_i64, int* flag) {
+  pdl_wait();
   int mx = 0;
   for (int b = threadIdx.x; b < B; b += 32) {
     int v = mel_lens[b];
@@ -702,6 +719,7 @@ __global__ void __launch_bounds__(THREADS) lr_expand_kernel(const float* __restr
                                                             const float* __restrict__ pe, int B, int Tp, int Tm, int D,
                                                             float* __restrict__ of, TA* __restrict__ oa, int out_pitch,
                                                             int out_off, int* __restrict__ frame2ph) {
+  pdl_wait();
   extern __shared__ int s_ends[];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -756,6 +774,7 @@ template <int RB>
 __global__ void __launch_bounds__(THREADS) lr_bwd_kernel(const float* __restrict__ df, const float* __restrict__ df2,
                                                          int f_pitch, int f_off, const int* __restrict__ ends, int B, int Tp,
                                                          int Tm, int D, float* __restrict__ dphon, int p_pitch, int p_off) {
+  pdl_wait();
   extern __shared__ int s_ends[];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -809,6 +828,7 @@ template <typename TA>
 __global__ void __launch_bounds__(THREADS) fold_halo_kernel(const float* src, int B, int T, int C, int pw,
                                                             const float* add, const float* add2, const int* lens,
                                                             float* of, TA* oa) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int TP = T + 2 * FS2_PAD;
   const long long rows = (long long)B * TP;
@@ -838,6 +858,7 @@ __global__ void __launch_bounds__(THREADS) fold_halo_kernel(const float* src, in
 
 template <typename TX>
 __global__ void colsum_kernel(const TX* x, long long rows, int C, long long ld, float* out) {
+  pdl_wait();
   __shared__ float4 red[8][32];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -872,6 +893,7 @@ __global__ void colsum_kernel(const TX* x, long long rows, int C, long long ld, 
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) unpad_mask_kernel(const float* src, const int* lens, int B, int T, int C,
                                                              float* plain, TA* oa, int halo) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int TP = T + 2 * FS2_PAD;
   const long long rows = (long long)B * TP;
@@ -895,6 +917,7 @@ __global__ void __launch_bounds__(THREADS) unpad_mask_kernel(const float* src, c
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) pad_rows_kernel(const float* a, const float* a2, int B, int T, int C,
                                                            float scale, float* of, TA* oa) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int TP = T + 2 * FS2_PAD;
   const long long rows = (long long)B * TP;
@@ -923,6 +946,7 @@ constexpr int PACK_MAX = 4608;      // floats of one output channel's slab stage
 template <typename TD>
 __global__ void __launch_bounds__(256) pack_weights_kernel(const Fs2PackItem* items, const float* __restrict__ src_base,
                                                            TD* __restrict__ dst_base) {
+  pdl_wait();
   __shared__ float slab[PACK_MAX];
   const Fs2PackItem it = items[blockIdx.y];
   const int rk = it.cin * it.k;
@@ -958,14 +982,17 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const Fs2PackItem* it
   }
 }
 
-__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
+__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) {
+  pdl_wait(); *ctr += inc; }
 
 __global__ void cast_bf16_kernel(const float* s, bf16* d, long long n) {
+  pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) st4(d + i, ld4(s + i));
   else for (; i < n; ++i) d[i] = __float2bfloat16_rn(s[i]);
 }
 __global__ void add_kernel(float* d, const float* s, long long n) {
+  pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 a = ld4(d + i), b = ld4(s + i);
@@ -975,6 +1002,7 @@ __global__ void add_kernel(float* d, const float* s, long long n) {
 
 __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
                              float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 3 < n) {
@@ -1005,6 +1033,7 @@ __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, long 
 // train.py:16-51: per-phoneme mean of frame intensities (plain mean, zero-duration phonemes -> 0)
 __global__ void intensity_segment_mean_kernel(const float* I, const int64_t* dur, const int64_t* phon_len, int B, int Tp,
                                               int Tm, int D, float* out) {
+  pdl_wait();
   extern __shared__ int ends_s[];
   const int b = blockIdx.x;
   const int pl = (int)phon_len[b];
@@ -1035,19 +1064,19 @@ __global__ void intensity_segment_mean_kernel(const float* I, const int64_t* dur
 extern "C" int fs2_embed_posenc(const int64_t* tokens, const float* emb, const float* pe, int B, int Tp, int D,
                                 int pad_idx, float* out_f32, void* out_act, int act_bf16, int* src_lens, void* stream) {
   REQUIRE(tokens && emb && pe && src_lens && D % 4 == 0, "fs2_embed_posenc: bad arguments");
-  count_nonpad_kernel<<<B, 32, 0, ST>>>(tokens, B, Tp, pad_idx, src_lens);
+  FS2_LAUNCH((count_nonpad_kernel), B, 32, 0, ST, tokens, B, Tp, pad_idx, src_lens);
   int rc = fs2_check_launch();
   if (rc) return rc;
   const long long rows = (long long)B * (Tp + 2 * FS2_PAD);
-  if (act_bf16) embed_posenc_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(tokens, emb, pe, B, Tp, D, pad_idx, out_f32, (bf16*)out_act);
-  else embed_posenc_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(tokens, emb, pe, B, Tp, D, pad_idx, out_f32, (float*)out_act);
+  if (act_bf16) FS2_LAUNCH((embed_posenc_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, tokens, emb, pe, B, Tp, D, pad_idx, out_f32, (bf16*)out_act);
+  else FS2_LAUNCH((embed_posenc_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, tokens, emb, pe, B, Tp, D, pad_idx, out_f32, (float*)out_act);
   return fs2_check_launch();
 }
 
 extern "C" int fs2_embedding_bwd(const float* dx, const int64_t* tokens, int B, int Tp, int D, int pad_idx, float* demb,
                                  void* stream) {
   REQUIRE(dx && tokens && demb, "fs2_embedding_bwd: null pointer");
-  embedding_bwd_kernel<<<grid_for_rows((long long)B * Tp), THREADS, 0, ST>>>(dx, tokens, B, Tp, D, pad_idx, demb);
+  FS2_LAUNCH((embedding_bwd_kernel), grid_for_rows((long long)B * Tp), THREADS, 0, ST, dx, tokens, B, Tp, D, pad_idx, demb);
   return fs2_check_launch();
 }
 
@@ -1056,8 +1085,8 @@ extern "C" int fs2_ln_fwd(const Fs2LnFwd* p, void* stream) {
   REQUIRE(p->C % 4 == 0 && p->C <= 128 * MAXV, "fs2_ln_fwd: C must be a multiple of 4 and <= 512");
   REQUIRE(p->halo <= FS2_PAD && (p->halo == 0 || p->T > p->halo), "fs2_ln_fwd: halo too wide for T");
   const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
-  if (p->act_bf16) ln_fwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(*p);
-  else ln_fwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(*p);
+  if (p->act_bf16) FS2_LAUNCH((ln_fwd_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, *p);
+  else FS2_LAUNCH((ln_fwd_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, *p);
   return fs2_check_launch();
 }
 
@@ -1069,7 +1098,7 @@ extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
   if (grid > 148 * 4) grid = 148 * 4;
   const int nv = (p->C + 127) / 128;
   const bool head = p->head_w != nullptr || p->dhead_w != nullptr || p->dhead_b != nullptr;
-#define LN_BWD_LAUNCH(TA, NV, HEAD) ln_bwd_kernel<TA, NV, HEAD><<<grid, THREADS, 0, ST>>>(*p)
+#define LN_BWD_LAUNCH(TA, NV, HEAD) FS2_LAUNCH((ln_bwd_kernel<TA, NV, HEAD>), grid, THREADS, 0, ST, *p)
 #define LN_BWD_NV(TA, NV) do { if (head) LN_BWD_LAUNCH(TA, NV, true); else LN_BWD_LAUNCH(TA, NV, false); } while (0)
 #define LN_BWD_TA(TA) do { if (nv == 1) LN_BWD_NV(TA, 1); else if (nv == 2) LN_BWD_NV(TA, 2); else if (nv == 3) LN_BWD_NV(TA, 3); else LN_BWD_NV(TA, 4); } while (0)
   if (p->act_bf16) LN_BWD_TA(bf16);
@@ -1087,8 +1116,8 @@ extern "C" int fs2_softmax_fwd(const float* S, const int* lens, int B, int H, in
   DropCfg dc{drop_p, seed};
   if (drop_p <= 0.f) Pd = nullptr;
   const long long rows = (long long)B * H * T;
-  if (act_bf16) softmax_fwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(S, lens, B, H, T, ldk, scale, dc, seed_dev, (bf16*)P, (bf16*)Pd);
-  else softmax_fwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(S, lens, B, H, T, ldk, scale, dc, seed_dev, (float*)P, (float*)Pd);
+  if (act_bf16) FS2_LAUNCH((softmax_fwd_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, S, lens, B, H, T, ldk, scale, dc, seed_dev, (bf16*)P, (bf16*)Pd);
+  else FS2_LAUNCH((softmax_fwd_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, S, lens, B, H, T, ldk, scale, dc, seed_dev, (float*)P, (float*)Pd);
   return fs2_check_launch();
 }
 
@@ -1098,8 +1127,8 @@ extern "C" int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens,
   REQUIRE(P && dPd && lens && dS && ldk % 4 == 0, "fs2_softmax_bwd: bad arguments");
   DropCfg dc{drop_p, seed};
   const long long rows = (long long)B * H * T;
-  if (act_bf16) softmax_bwd_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>((const bf16*)P, dPd, lens, B, H, T, ldk, scale, dc, seed_dev, (bf16*)dS);
-  else softmax_bwd_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>((const float*)P, dPd, lens, B, H, T, ldk, scale, dc, seed_dev, (float*)dS);
+  if (act_bf16) FS2_LAUNCH((softmax_bwd_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, (const bf16*)P, dPd, lens, B, H, T, ldk, scale, dc, seed_dev, (bf16*)dS);
+  else FS2_LAUNCH((softmax_bwd_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, (const float*)P, dPd, lens, B, H, T, ldk, scale, dc, seed_dev, (float*)dS);
   return fs2_check_launch();
 }
 
@@ -1107,12 +1136,12 @@ extern "C" int fs2_cond_finish(const float* G, const float* Wcat, const float* s
                                const float* intensity, const int* lens, int B, int Tp, int D, float* sp_ws, float* y_f32,
                                void* y_act, int act_bf16, int halo, void* stream) {
   REQUIRE(G && Wcat && spk_emb && speakers && intensity && lens && sp_ws && D % 4 == 0, "fs2_cond_finish: bad arguments");
-  spk_proj_kernel<<<grid_for_rows((long long)B * D), THREADS, 0, ST>>>(Wcat, spk_emb, speakers, B, D, sp_ws);
+  FS2_LAUNCH((spk_proj_kernel), grid_for_rows((long long)B * D), THREADS, 0, ST, Wcat, spk_emb, speakers, B, D, sp_ws);
   int rc = fs2_check_launch();
   if (rc) return rc;
   const long long rows = (long long)B * (Tp + 2 * FS2_PAD);
-  if (act_bf16) cond_finish_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(G, Wcat, sp_ws, intensity, lens, B, Tp, D, y_f32, (bf16*)y_act, halo);
-  else cond_finish_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(G, Wcat, sp_ws, intensity, lens, B, Tp, D, y_f32, (float*)y_act, halo);
+  if (act_bf16) FS2_LAUNCH((cond_finish_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, G, Wcat, sp_ws, intensity, lens, B, Tp, D, y_f32, (bf16*)y_act, halo);
+  else FS2_LAUNCH((cond_finish_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, G, Wcat, sp_ws, intensity, lens, B, Tp, D, y_f32, (float*)y_act, halo);
   return fs2_check_launch();
 }
 
@@ -1120,10 +1149,10 @@ extern "C" int fs2_cond_bwd(const float* dy, const float* Wcat, const float* spk
                             const float* intensity, int B, int Tp, int D, float* dsum_ws, float* dWcat, float* dspk_emb,
                             void* stream) {
   REQUIRE(dy && Wcat && spk_emb && speakers && intensity && dsum_ws && dWcat && dspk_emb, "fs2_cond_bwd: null pointer");
-  cond_bwd_rows_kernel<<<B, 128, 0, ST>>>(dy, intensity, B, Tp, D, dsum_ws, dWcat);
+  FS2_LAUNCH((cond_bwd_rows_kernel), B, 128, 0, ST, dy, intensity, B, Tp, D, dsum_ws, dWcat);
   int rc = fs2_check_launch();
   if (rc) return rc;
-  cond_bwd_spk_kernel<<<148, 256, 0, ST>>>(dsum_ws, Wcat, spk_emb, speakers, B, D, dWcat, dspk_emb);
+  FS2_LAUNCH((cond_bwd_spk_kernel), 148, 256, 0, ST, dsum_ws, Wcat, spk_emb, speakers, B, D, dWcat, dspk_emb);
   return fs2_check_launch();
 }
 
@@ -1132,7 +1161,7 @@ extern "C" int fs2_avg_over_durations(const float* values, const int64_t* durs, 
   REQUIRE(values && durs && avg, "fs2_avg_over_durations: null pointer");
   size_t smem = (size_t)(Tm + 1) * 8 + (size_t)Tp * 4;
   REQUIRE(smem <= 48 * 1024, "fs2_avg_over_durations: Tm too large for the shared-memory scan");
-  avg_over_durations_kernel<<<B, 128, smem, ST>>>(values, durs, B, Tp, Tm, avg, starts, ends, nz);
+  FS2_LAUNCH((avg_over_durations_kernel), B, 128, smem, ST, values, durs, B, Tp, Tm, avg, starts, ends, nz);
   return fs2_check_launch();
 }
 
@@ -1142,8 +1171,8 @@ extern "C" int fs2_embed_add(const float* x, const float* contour, const float* 
   REQUIRE(x && contour && w && bias && lens && ksize >= 1 && ksize <= 9 && (ksize & 1) && Tp > (ksize - 1) / 2,
           "fs2_embed_add: bad arguments");
   const long long rows = (long long)B * (Tp + 2 * FS2_PAD);
-  if (act_bf16) embed_add_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(x, contour, w, bias, ksize, lens, B, Tp, D, y_f32, (bf16*)y_act, halo);
-  else embed_add_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(x, contour, w, bias, ksize, lens, B, Tp, D, y_f32, (float*)y_act, halo);
+  if (act_bf16) FS2_LAUNCH((embed_add_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, x, contour, w, bias, ksize, lens, B, Tp, D, y_f32, (bf16*)y_act, halo);
+  else FS2_LAUNCH((embed_add_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, x, contour, w, bias, ksize, lens, B, Tp, D, y_f32, (float*)y_act, halo);
   return fs2_check_launch();
 }
 
@@ -1151,26 +1180,26 @@ extern "C" int fs2_embed_add_bwd(const float* dy, const float* contour, int ksiz
                                  float* dbias, void* stream) {
   REQUIRE(dy && contour && dw && dbias && ksize <= 9, "fs2_embed_add_bwd: bad arguments");
   dim3 grid((D + 127) / 128, 64);
-  embed_add_bwd_kernel<<<grid, 128, 0, ST>>>(dy, contour, ksize, B, Tp, D, dw, dbias);
+  FS2_LAUNCH((embed_add_bwd_kernel), grid, 128, 0, ST, dy, contour, ksize, B, Tp, D, dw, dbias);
   return fs2_check_launch();
 }
 
 extern "C" int fs2_dur_decode(const float* log_dur, long long n, float* fdur, void* stream) {
   REQUIRE(log_dur && fdur, "fs2_dur_decode: null pointer");
-  dur_decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST>>>(log_dur, n, fdur);
+  FS2_LAUNCH((dur_decode_kernel), (unsigned)((n + 255) / 256), 256, 0, ST, log_dur, n, fdur);
   return fs2_check_launch();
 }
 
 extern "C" int fs2_lr_prepare(const int64_t* dur, const float* fdur, float pace, int B, int Tp, int* ends, int* mel_lens,
                               void* stream) {
   REQUIRE((dur || fdur) && ends && mel_lens, "fs2_lr_prepare: null pointer");
-  lr_prepare_kernel<<<B, 32, 0, ST>>>(dur, fdur, pace, B, Tp, ends, mel_lens);
+  FS2_LAUNCH((lr_prepare_kernel), B, 32, 0, ST, dur, fdur, pace, B, Tp, ends, mel_lens);
   return fs2_check_launch();
 }
 
 extern "C" int fs2_lr_finalize(const int* mel_lens, int B, int Tm_expected, long long* out_i64, int* flag, void* stream) {
   REQUIRE(mel_lens && out_i64 && flag, "fs2_lr_finalize: null pointer");
-  lr_finalize_kernel<<<1, 32, 0, ST>>>(mel_lens, B, Tm_expected, out_i64, flag);
+  FS2_LAUNCH((lr_finalize_kernel), 1, 32, 0, ST, mel_lens, B, Tm_expected, out_i64, flag);
   return fs2_check_launch();
 }
 
@@ -1181,7 +1210,7 @@ extern "C" int fs2_lr_expand(const float* in, int in_pitch, int in_off, const in
   REQUIRE(B > 0 && B <= 65535 && Tp > 0 && Tp <= 12000 && out_pitch > 0, "fs2_lr_expand: B <= 65535 and 0 < Tp <= 12000 (prefix sums are staged in shared memory)");
   const dim3 grid((out_pitch + LR_ROWS - 1) / LR_ROWS, B);
   const size_t sm = (size_t)Tp * sizeof(int);
-#define LR_EXP(TA, RB) lr_expand_kernel<TA, RB><<<grid, THREADS, sm, ST>>>(in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (TA*)out_act, out_pitch, out_off, frame2ph)
+#define LR_EXP(TA, RB) FS2_LAUNCH((lr_expand_kernel<TA, RB>), grid, THREADS, sm, ST, in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (TA*)out_act, out_pitch, out_off, frame2ph)
   if (act_bf16) { if (g_lr_rb == 2) LR_EXP(bf16, 2); else if (g_lr_rb == 8) LR_EXP(bf16, 8); else LR_EXP(bf16, 4); }
   else { if (g_lr_rb == 2) LR_EXP(float, 2); else if (g_lr_rb == 8) LR_EXP(float, 8); else LR_EXP(float, 4); }
 #undef LR_EXP
@@ -1196,7 +1225,7 @@ extern "C" int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pit
   (void)mel_lens;
   CUDA_CHECK_RET(cudaMemsetAsync(dphon, 0, (size_t)B * p_pitch * D * sizeof(float), ST));
   const dim3 grid((Tm + LR_ROWS - 1) / LR_ROWS, B);
-#define LR_BWD(RB) lr_bwd_kernel<RB><<<grid, THREADS, (size_t)Tp * sizeof(int), ST>>>(dframes, dframes2, f_pitch, f_off, ends, B, Tp, Tm, D, dphon, p_pitch, p_off)
+#define LR_BWD(RB) FS2_LAUNCH((lr_bwd_kernel<RB>), grid, THREADS, (size_t)Tp * sizeof(int), ST, dframes, dframes2, f_pitch, f_off, ends, B, Tp, Tm, D, dphon, p_pitch, p_off)
   if (g_lr_rb == 2) LR_BWD(2); else if (g_lr_rb == 8) LR_BWD(8); else LR_BWD(4);
 #undef LR_BWD
   return fs2_check_launch();
@@ -1213,8 +1242,8 @@ extern "C" int fs2_fold_halo(const float* src, int B, int T, int C, int p, const
                              const int* lens, float* out_f32, void* out_act, int act_bf16, void* stream) {
   REQUIRE(C % 4 == 0 && p <= FS2_PAD, "fs2_fold_halo: bad arguments");
   const long long rows = (long long)B * (T + 2 * FS2_PAD);
-  if (act_bf16) fold_halo_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(src, B, T, C, p, add, add2, lens, out_f32, (bf16*)out_act);
-  else fold_halo_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(src, B, T, C, p, add, add2, lens, out_f32, (float*)out_act);
+  if (act_bf16) FS2_LAUNCH((fold_halo_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, src, B, T, C, p, add, add2, lens, out_f32, (bf16*)out_act);
+  else FS2_LAUNCH((fold_halo_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, src, B, T, C, p, add, add2, lens, out_f32, (float*)out_act);
   return fs2_check_launch();
 }
 
@@ -1224,8 +1253,8 @@ extern "C" int fs2_colsum(const void* x, int x_bf16, long long rows, int C, long
   if (gy > 296) gy = 296;
   if (gy < 1) gy = 1;
   dim3 grid((C + 127) / 128, (unsigned)gy), block(32, 8);
-  if (x_bf16) colsum_kernel<bf16><<<grid, block, 0, ST>>>((const bf16*)x, rows, C, ld, out);
-  else colsum_kernel<float><<<grid, block, 0, ST>>>((const float*)x, rows, C, ld, out);
+  if (x_bf16) FS2_LAUNCH((colsum_kernel<bf16>), grid, block, 0, ST, (const bf16*)x, rows, C, ld, out);
+  else FS2_LAUNCH((colsum_kernel<float>), grid, block, 0, ST, (const float*)x, rows, C, ld, out);
   return fs2_check_launch();
 }
 
@@ -1233,8 +1262,8 @@ extern "C" int fs2_unpad_mask(const float* src, const int* lens, int B, int T, i
                               int act_bf16, int halo, void* stream) {
   REQUIRE(src && C % 4 == 0, "fs2_unpad_mask: bad arguments");
   const long long rows = (long long)B * (T + 2 * FS2_PAD);
-  if (act_bf16) unpad_mask_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(src, lens, B, T, C, out_plain, (bf16*)out_act, halo);
-  else unpad_mask_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(src, lens, B, T, C, out_plain, (float*)out_act, halo);
+  if (act_bf16) FS2_LAUNCH((unpad_mask_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, src, lens, B, T, C, out_plain, (bf16*)out_act, halo);
+  else FS2_LAUNCH((unpad_mask_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, src, lens, B, T, C, out_plain, (float*)out_act, halo);
   return fs2_check_launch();
 }
 
@@ -1242,8 +1271,8 @@ extern "C" int fs2_pad_rows(const float* src_plain, const float* src2_plain, int
                             float* out_f32, void* out_act, int act_bf16, void* stream) {
   REQUIRE(src_plain && C % 4 == 0, "fs2_pad_rows: bad arguments");
   const long long rows = (long long)B * (T + 2 * FS2_PAD);
-  if (act_bf16) pad_rows_kernel<bf16><<<grid_for_rows(rows), THREADS, 0, ST>>>(src_plain, src2_plain, B, T, C, scale, out_f32, (bf16*)out_act);
-  else pad_rows_kernel<float><<<grid_for_rows(rows), THREADS, 0, ST>>>(src_plain, src2_plain, B, T, C, scale, out_f32, (float*)out_act);
+  if (act_bf16) FS2_LAUNCH((pad_rows_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, src_plain, src2_plain, B, T, C, scale, out_f32, (bf16*)out_act);
+  else FS2_LAUNCH((pad_rows_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, src_plain, src2_plain, B, T, C, scale, out_f32, (float*)out_act);
   return fs2_check_launch();
 }
 
@@ -1251,26 +1280,26 @@ extern "C" int fs2_pack_weights(const Fs2PackItem* items_dev, int n_items, const
                                 int dst_bf16, void* stream) {
   REQUIRE(items_dev && src_base && dst_base && n_items > 0, "fs2_pack_weights: bad arguments");
   dim3 grid(128, n_items);
-  if (dst_bf16) pack_weights_kernel<bf16><<<grid, 256, 0, ST>>>(items_dev, src_base, (bf16*)dst_base);
-  else pack_weights_kernel<float><<<grid, 256, 0, ST>>>(items_dev, src_base, (float*)dst_base);
+  if (dst_bf16) FS2_LAUNCH((pack_weights_kernel<bf16>), grid, 256, 0, ST, items_dev, src_base, (bf16*)dst_base);
+  else FS2_LAUNCH((pack_weights_kernel<float>), grid, 256, 0, ST, items_dev, src_base, (float*)dst_base);
   return fs2_check_launch();
 }
 
 extern "C" int fs2_cast_bf16(const float* src, void* dst, long long n, void* stream) {
   REQUIRE(src && dst, "fs2_cast_bf16: null pointer");
-  cast_bf16_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ST>>>(src, (bf16*)dst, n);
+  FS2_LAUNCH((cast_bf16_kernel), (unsigned)((n / 4 + 256) / 256), 256, 0, ST, src, (bf16*)dst, n);
   return fs2_check_launch();
 }
 
 extern "C" int fs2_add_(float* dst, const float* src, long long n, void* stream) {
   REQUIRE(src && dst, "fs2_add_: null pointer");
-  add_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ST>>>(dst, src, n);
+  FS2_LAUNCH((add_kernel), (unsigned)((n / 4 + 256) / 256), 256, 0, ST, dst, src, n);
   return fs2_check_launch();
 }
 
 extern "C" int fs2_counter_add(unsigned long long* ctr, unsigned long long inc, void* stream) {
   REQUIRE(ctr, "fs2_counter_add: null pointer");
-  counter_add_kernel<<<1, 1, 0, ST>>>(ctr, inc);
+  FS2_LAUNCH((counter_add_kernel), 1, 1, 0, ST, ctr, inc);
   return fs2_check_launch();
 }
 
@@ -1284,13 +1313,13 @@ extern "C" int fs2_adamw(float* p, const float* g, float* m, float* v, long long
   REQUIRE(p && g && m && v && step >= 1, "fs2_adamw: bad arguments");
   float bc1 = 1.0f - powf(beta1, (float)step);
   float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
-  adamw_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale);
+  FS2_LAUNCH((adamw_kernel), (unsigned)((n / 4 + 256) / 256), 256, 0, ST, p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale);
   return fs2_check_launch();
 }
 
 extern "C" int fs2_intensity_segment_mean(const float* I, const int64_t* dur, const int64_t* phon_len, int B, int Tp,
                                           int Tm, int D, float* out, void* stream) {
   REQUIRE(I && dur && phon_len && out, "fs2_intensity_segment_mean: null pointer");
-  intensity_segment_mean_kernel<<<B, 256, (size_t)Tp * 4, ST>>>(I, dur, phon_len, B, Tp, Tm, D, out);
+  FS2_LAUNCH((intensity_segment_mean_kernel), B, 256, (size_t)Tp * 4, ST, I, dur, phon_len, B, Tp, Tm, D, out);
   return fs2_check_launch();
 }
