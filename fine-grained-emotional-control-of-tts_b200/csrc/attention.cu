@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(att_threads(NCH), 1) attn_kernel(const __grid_
             v[i] = (c0 + i < kv) ? e : 0.f;
           }
         }
-        if (in_buf) {
+        if (in_buf && p.P) {          // P is kept for the backward only (NULL in inference)
           uint4* dst = reinterpret_cast<uint4*>(p.P + ro + c0);
 #pragma unroll
           for (int i = 0; i < CW / 8; ++i)
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(att_threads(NCH), 1) attn_kernel(const __grid_
       for (int c = nkb * AK + ch * 8; c < p.ldk; c += 8 * NCH) {
         const uint4 z = make_uint4(0, 0, 0, 0);
         if (!BWD) {
-          *reinterpret_cast<uint4*>(p.P + ro + c) = z;
+          if (p.P) *reinterpret_cast<uint4*>(p.P + ro + c) = z;
           if (p.Pd && dc.p > 0.f) *reinterpret_cast<uint4*>(p.Pd + ro + c) = z;
         } else {
           *reinterpret_cast<uint4*>(p.dS + ro + c) = z;
@@ -527,7 +527,7 @@ extern "C" int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int 
   CUtensorMap tq, tkv;
   int rc = attn_common(qkv, lens, B, H, T, D, ldk, p, &tkv);
   if (rc) return rc;
-  if (!P || !O || (drop_p > 0.f && !Pd)) { fs2_set_error("fs2_attn_fwd: null pointer"); return FS2_ERR_ARG; }
+  if (!O) { fs2_set_error("fs2_attn_fwd: null pointer"); return FS2_ERR_ARG; }
   rc = fs2_tc_make_map_2d(qkv, 3LL * D, (long long)B * p.TP, 3LL * D, 64, AQ, &tq);
   if (rc) return rc;
   p.b1_col = D;          // K

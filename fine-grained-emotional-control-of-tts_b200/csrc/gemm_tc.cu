@@ -227,6 +227,15 @@ __device__ __forceinline__ void epi_chunk(const Fs2Gemm& g, const EpiRow& er, co
 constexpr int EPI_STAGE_BYTES = 2048;                      // per epilogue warp
 constexpr int EPI_STAGE_TOTAL = NUM_EPI_WARPS * EPI_STAGE_BYTES;
 
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
 template <int MODE>
 __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, bool row_ok, const uint32_t* r, int nb0,
                                             long long col0, bool out_bf16, uint8_t* stage) {
@@ -247,7 +256,8 @@ __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, 
     if (g.relu) x = fmaxf(x, 0.f);
     v[i] = live ? x : 0.f;
   }
-  const uint32_t wr = (uint32_t)lane * 64u, wsw = (uint32_t)((lane >> 1) & 3);
+  const uint32_t sbase = smem_u32(stage);
+  const uint32_t wr = sbase + (uint32_t)lane * 64u, wsw = (uint32_t)((lane >> 1) & 3);
   if (out_bf16) {
     uint4 aux[4];
     const bool has_aux = g.relu_aux != nullptr;
@@ -270,13 +280,13 @@ __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, 
       pk.y = *reinterpret_cast<uint32_t*>(&h1);
       pk.z = *reinterpret_cast<uint32_t*>(&h2);
       pk.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(stage + wr + (((uint32_t)k ^ wsw) << 4)) = pk;
+      sts128(wr + (((uint32_t)k ^ wsw) << 4), pk.x, pk.y, pk.z, pk.w);
     }
     __syncwarp();
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int row = jj * 8 + tr;
-      uint4 x = *reinterpret_cast<const uint4*>(stage + row * 64 + (((uint32_t)tcq ^ (uint32_t)((row >> 1) & 3)) << 4));
+      uint4 x = lds128(sbase + row * 64 + (((uint32_t)tcq ^ (uint32_t)((row >> 1) & 3)) << 4));
       if ((okmask >> row) & 1u) {
         if (has_aux) {
           // keep a value where the forward activation was > 0: bf16 sign clear and magnitude non-zero
@@ -299,14 +309,16 @@ __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, 
     for (int half = 0; half < 2; ++half) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        *reinterpret_cast<float4*>(stage + wr + (((uint32_t)k ^ wsw) << 4)) =
-            make_float4(v[half * 16 + 4 * k], v[half * 16 + 4 * k + 1], v[half * 16 + 4 * k + 2], v[half * 16 + 4 * k + 3]);
+        sts128(wr + (((uint32_t)k ^ wsw) << 4), __float_as_uint(v[half * 16 + 4 * k]), __float_as_uint(v[half * 16 + 4 * k + 1]),
+               __float_as_uint(v[half * 16 + 4 * k + 2]), __float_as_uint(v[half * 16 + 4 * k + 3]));
       __syncwarp();
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int row = jj * 8 + tr;
-        const float4 x = *reinterpret_cast<const float4*>(stage + row * 64 + (((uint32_t)tcq ^ (uint32_t)((row >> 1) & 3)) << 4));
-        if ((okmask >> row) & 1u) st4((float*)g.C + tb[jj] + col0 + half * 16 + tcq * 4, x);
+        const uint4 x = lds128(sbase + row * 64 + (((uint32_t)tcq ^ (uint32_t)((row >> 1) & 3)) << 4));
+        if ((okmask >> row) & 1u)
+          st4((float*)g.C + tb[jj] + col0 + half * 16 + tcq * 4,
+              make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)));
       }
       __syncwarp();
     }

@@ -381,12 +381,12 @@ class FastSpeech2(nn.Module):
         hd = D // H
         TP = T + 2 * PAD
         ld = 3 * D
-        ldk = P.shape[-1]
+        ldk = _rup(T, 8)
         bf = self._bf16
         if S is None:
             # fused tcgen05 attention: scores, softmax, dropout and PV in one kernel (attention.cu)
             L.call("fs2_attn_fwd", qkv, lens, B, H, T, D, ldk, 1.0 / math.sqrt(hd), p_drop, seed, self._ctr, P,
-                   Pd if p_drop > 0 else None, O)
+                   Pd if (p_drop > 0 and P is not None) else None, O)
             return
         # S[b,h] = Q K^T
         L.gemm(mode=0, M=T, N=T, K=hd, A=qkv, A_off=PAD * ld, lda=ld, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * ld,
@@ -399,7 +399,7 @@ class FastSpeech2(nn.Module):
                B=qkv, B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
                Cout=O, C_off=PAD * D, ldc=D, c_s1=hd, c_s2=TP * D, c_bf16=bf, ab_bf16=bf)
 
-    def _stack_fwd(self, cfg, x_f32, x_act, B, T, lens, final_lens, final_halo, base_seed, site0, training):
+    def _stack_fwd(self, cfg, x_f32, x_act, B, T, lens, final_lens, final_halo, base_seed, site0, training, keep_p=True):
         D, F, H, nl = self.D, cfg["F"], cfg["H"], cfg["nl"]
         name = cfg["name"]
         rows = B * (T + 2 * PAD)
@@ -418,8 +418,11 @@ class FastSpeech2(nn.Module):
             sv.qkv = self._act(rows, 3 * D)
             self._conv(x_act, B, T, f"{pre}.self_att.att.in_proj_weight", sv.qkv, c_bf16=bf,
                        bias=self._P(f"{pre}.self_att.att.in_proj_bias"))
-            sv.P = self._act(B * H, T, ldk)
-            sv.Pd = self._act(B * H, T, ldk) if p > 0 else sv.P
+            if fused and not keep_p:
+                sv.P = sv.Pd = None             # no backward can follow (inference): the probabilities stay on chip
+            else:
+                sv.P = self._act(B * H, T, ldk)
+                sv.Pd = self._act(B * H, T, ldk) if p > 0 else sv.P
             sv.O = self._act(rows, D)
             self._attn_gemms_fwd(sv.qkv, B, T, H, S, lens, sv.P, sv.Pd, sv.O, p, sv.seeds[0])
             sv.proj = self._f32(rows, D)
@@ -641,6 +644,7 @@ class FastSpeech2(nn.Module):
         ctx.B, ctx.Tp = B, Tp
         ctx.tokens, ctx.speakers, ctx.intensity = tokens, speakers, intensity
         ctx.teacher = durations is not None
+        can_bwd = durations is not None and pitch is not None and energy is not None    # the training call (train.py:72)
         pe_enc = self.sinusoidal_positional_embed_encoder.pe
         pe_dec = self.sinusoidal_positional_embed_decoder.pe
 
@@ -673,7 +677,7 @@ class FastSpeech2(nn.Module):
                self.padding_idx, x_f32, x_act, int(bf), src_lens)
         self._tr("enc_in", x_f32, B, Tp, D)
         enc_f32, enc_act, ctx.enc_saves, ctx.enc_fin = self._stack_fwd(
-            self.enc, x_f32, x_act, B, Tp, src_lens, src_lens, 0, base_seed, 100, training)
+            self.enc, x_f32, x_act, B, Tp, src_lens, src_lens, 0, base_seed, 100, training, keep_p=can_bwd)
         ctx.enc_act = enc_act
         self._tr("enc_out", enc_f32, B, Tp, D)
 
@@ -747,7 +751,7 @@ class FastSpeech2(nn.Module):
 
         # ---- decoder + mel projection + PostNet (model.py:425-431)
         dec_f32, dec_act, ctx.dec_saves, ctx.dec_fin = self._stack_fwd(
-            self.dec, d0_f32, d0_act, B, Tm, mel_lens, None, 0, base_seed, 200, training)
+            self.dec, d0_f32, d0_act, B, Tm, mel_lens, None, 0, base_seed, 200, training, keep_p=can_bwd)
         ctx.dec_act = dec_act
         self._tr("dec_out", dec_f32, B, Tm, D)
         hp = (self.kpn - 1) // 2

@@ -135,7 +135,8 @@ int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens, int B, int
 /* Fused attention for head_dim 192, bf16 (tcgen05: scores and the output accumulator live in TMEM; the fp32 score
  * matrix never reaches HBM).  Replaces the QK^T GEMM + fs2_softmax_fwd + PV GEMM sequence; same mask quirk, same
  * counter-based dropout stream (keyed by the element index in P), so it can be mixed with the unfused kernels.
- * qkv: (B*(T+8), 3D) bf16 padded rows [Q | K | V]; P, Pd: (B*H, T, ldk) bf16 (Pd only when drop_p > 0);
+ * qkv: (B*(T+8), 3D) bf16 padded rows [Q | K | V]; P, Pd: (B*H, T, ldk) bf16, kept for the backward only -- either
+ * may be NULL (inference: nothing but O is written; Pd is only meaningful when drop_p > 0);
  * O: (B*(T+8), D) bf16 padded rows, rows t < T written. */
 int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int T, int D, int ldk, float scale, float drop_p,
                  unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd, void* O, void* stream);
