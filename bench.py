@@ -200,7 +200,9 @@ def dominant_kernel_roofline(pkg, model, peaks, B=BATCH, Tm=800, iters=12):
             traffic = None
     return {"bound": "tensor", "kernel": "tc_gemm_kernel<mode0> decoder FFN Conv1d k=9 384->1536 (+bias+ReLU), "
             f"M={rows} N={F} K={D}x{model.k0}", "achieved": achieved, "peak": peaks["tc_burst"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tc_burst"], "traffic": traffic, "ms_per_launch": ms,
+            "frac": achieved / peaks["tc_burst"], "traffic": traffic,
+            "traffic_note": "DRAM read+write bytes of one launch, ncu --set full (profiles/dominant_kernel_traffic.json)",
+            "algorithmic_bytes_per_launch": rows * D * 2 + F * D * model.k0 * 2 + rows * F * 2, "ms_per_launch": ms,
             "flops_per_launch": flops, "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
 
 
@@ -222,7 +224,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 6))
+        steps = max(1, min(args.steps, 12))
         r = cpu_reference_run(steps, max(1, min(args.warmup, 1)))
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
@@ -340,7 +342,7 @@ def main():
                              "flops_per_step_per_gpu": fl, "peak_source": peaks["src"] + " (sustained)"},
     }
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(2, 1)
+        r = cpu_reference_run(8, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     print(json.dumps(line))
     if world > 1:

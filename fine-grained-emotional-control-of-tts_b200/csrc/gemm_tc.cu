@@ -42,7 +42,7 @@ struct TcParams {
   int pa[4], pb[4];   // tensor-map dim slot of (inner,row,i1,i2) for A and B
   int* err;
   long long* dbg;     // optional: {SM cycles, nanoseconds} of unit 0's lifetime (clock probe for measurements)
-  int dbg_mode;       // measurements only (results are garbage): 1 = MMA issue without TMA, 2 = TMA without MMA
+  int dbg_mode;       // measurements only (results are garbage): 1 = MMA issue without TMA, 2 = TMA without MMA, 3 = no epilogue stores
   int epi_transpose;  // 1: coalesced epilogue stores through the per-warp smem staging tile (epi_chunk_t)
 };
 
@@ -236,25 +236,60 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   return v;
 }
 
-template <int MODE>
-__device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, bool row_ok, const uint32_t* r, int nb0,
-                                            long long col0, bool out_bf16, uint8_t* stage) {
+// per-tile data of the transposed store path: computed once per tile, used by every 32-column chunk of the tile
+struct EpiT {
+  long long tb[4];      // C offsets of rows tr, tr+8, tr+16, tr+24 of this warp's 32 rows (tr = lane / 4)
+  unsigned okmask;      // rows that exist and are written
+  bool any_dead;        // some written row is masked (t >= lens[b]): the value path has to select zeros
+  bool mirrors;         // some row needs a halo mirror store -> the chunk takes the row-per-thread path
+};
+
+__device__ __forceinline__ void epi_t_setup(const EpiRow& er, bool row_ok, EpiT& et) {
   const int lane = threadIdx.x & 31;
   const bool mine = row_ok && !er.skip;
-  const unsigned okmask = __ballot_sync(0xffffffffu, mine);
+  et.okmask = __ballot_sync(0xffffffffu, mine);
+  et.any_dead = __ballot_sync(0xffffffffu, mine && !er.live) != 0u;
+  et.mirrors = __ballot_sync(0xffffffffu, row_ok && (er.mirror != 0 || er.mirror2 != 0)) != 0u;
   const long long mybase = mine ? er.base : 0;
-  const int tr = lane >> 2, tcq = lane & 3;                // transposed role: row tr (+8 per step), 16-byte quarter tcq
-  long long tb[4];
 #pragma unroll
-  for (int jj = 0; jj < 4; ++jj) tb[jj] = __shfl_sync(0xffffffffu, mybase, jj * 8 + tr);
-  const bool live = mine && er.live;
+  for (int jj = 0; jj < 4; ++jj) et.tb[jj] = __shfl_sync(0xffffffffu, mybase, jj * 8 + (lane >> 2));
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, bool row_ok, const EpiT& et, const uint32_t* r,
+                                            int nb0, long long col0, bool out_bf16, uint8_t* stage, bool no_stg = false) {
+  const int lane = threadIdx.x & 31;
+  const unsigned okmask = no_stg ? 0u : et.okmask;
+  const int tr = lane >> 2, tcq = lane & 3;                // transposed role: row tr (+8 per step), 16-byte quarter tcq
+  const long long* tb = et.tb;
   float v[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = __uint_as_float(r[i]) * g.alpha;
-    if (g.bias) x += g.bias[nb0 + i];
-    if (g.relu) x = fmaxf(x, 0.f);
-    v[i] = live ? x : 0.f;
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (g.alpha != 1.f) {                                    // every branch below is warp-uniform
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= g.alpha;
+  }
+  if (g.bias) {
+    const float4* bp = reinterpret_cast<const float4*>(g.bias + nb0);     // nb0 % 32 == 0, cudaMalloc-aligned base
+    if ((reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b4 = __ldg(bp + i);
+        v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += g.bias[nb0 + i];
+    }
+  }
+  if (g.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (et.any_dead) {
+    const bool live = row_ok && !er.skip && er.live;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = live ? v[i] : 0.f;
   }
   const uint32_t sbase = smem_u32(stage);
   const uint32_t wr = sbase + (uint32_t)lane * 64u, wsw = (uint32_t)((lane >> 1) & 3);
@@ -488,6 +523,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       const long long colbase = (MODE == 2) ? (long long)tapN * g.c_tap_stride + n0 * cstr : n0;
       const bool vec_f32 = cstr == 1 && !g.c_bf16 && !atomic && al4 && (colbase % 4 == 0) && aux_al;
       const bool vec_bf16 = cstr == 1 && g.c_bf16 && al8 && (colbase % 8 == 0) && aux_al;
+      // coalesced (smem-transposed) store path: decided and set up once per tile
+      EpiT et;
+      bool t_path = p.epi_transpose &&
+                    ((vec_f32 && g.relu_aux == nullptr) || (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
+      if (t_path) {
+        epi_t_setup(er, row_ok, et);
+        t_path = !et.mirrors;
+      }
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, err)) { ok = false; break; }
       tc_fence_after();
 #pragma unroll 1
@@ -502,11 +545,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
           if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
         }
         const int nb0 = n0 + c * 32;
-        if (nb0 >= g.N) continue;                               // warp-uniform
-        const bool t_ok = p.epi_transpose && nb0 + 32 <= g.N &&
-                          ((vec_f32 && g.relu_aux == nullptr) || (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
-        if (t_ok && __ballot_sync(0xffffffffu, row_ok && (er.mirror != 0 || er.mirror2 != 0)) == 0u) {
-          epi_chunk_t<MODE>(g, er, row_ok, r, nb0, colbase + (long long)c * 32, vec_bf16, stage);
+        if (nb0 >= g.N || p.dbg_mode == 3) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
+        if (t_path && nb0 + 32 <= g.N) {
+          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4);
           continue;
         }
         if (!row_ok || er.skip) continue;
@@ -734,6 +775,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
       const long long colbase = (MODE == 2) ? (long long)tapN * g.c_tap_stride + n0 * cstr : n0;
       const bool vec_f32 = cstr == 1 && !g.c_bf16 && !atomic && al4 && (colbase % 4 == 0) && aux_al;
       const bool vec_bf16 = cstr == 1 && g.c_bf16 && al8 && (colbase % 8 == 0) && aux_al;
+      // coalesced (smem-transposed) store path: decided and set up once per tile
+      EpiT et;
+      bool t_path = p.epi_transpose &&
+                    ((vec_f32 && g.relu_aux == nullptr) || (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
+      if (t_path) {
+        epi_t_setup(er, row_ok, et);
+        t_path = !et.mirrors;
+      }
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, err)) { ok = false; break; }
       tc_fence_after();
 #pragma unroll 1
@@ -752,11 +801,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
           }
         }
         const int nb0 = n0 + c * 32;
-        if (nb0 >= g.N) continue;                               // warp-uniform
-        const bool t_ok = p.epi_transpose && nb0 + 32 <= g.N &&
-                          ((vec_f32 && g.relu_aux == nullptr) || (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
-        if (t_ok && __ballot_sync(0xffffffffu, row_ok && (er.mirror != 0 || er.mirror2 != 0)) == 0u) {
-          epi_chunk_t<MODE>(g, er, row_ok, r, nb0, colbase + (long long)c * 32, vec_bf16, stage);
+        if (nb0 >= g.N || p.dbg_mode == 3) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
+        if (t_path && nb0 + 32 <= g.N) {
+          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4);
           continue;
         }
         if (!row_ok || er.skip) continue;
@@ -1048,7 +1095,7 @@ int fs2_tc_error_ptr(int** out) {
 // tuning hook (tools/gemm_sweep.py): pair = 0 single-CTA, 1 CTA pair, 2 heuristic; cfg = -1 auto or 0|1|2
 extern "C" int fs2_gemm_tc_tune(int pair, int cfg) {
   g_use_pair = pair & 3;
-  g_dbg_mode = (pair >> 4) & 3;     // bits 4-5: pipeline-isolation experiments (tools/gemm_sweep.py), 0 in production
+  g_dbg_mode = (pair >> 4) & 7;     // bits 4-5: pipeline-isolation experiments (tools/gemm_sweep.py), 0 in production
   g_force_cfg = cfg;
   return FS2_OK;
 }

@@ -56,7 +56,10 @@ def run(name, N, K, c_bf16, bn, graph):
           flush=True)
 
 
-for graph in (False, True):
+if os.environ.get("GEMM_DBG"):
+    L.gemm_tc_tune(pair=2 | (int(os.environ["GEMM_DBG"]) << 4), cfg=-1)
+    print("dbg_mode", os.environ["GEMM_DBG"], "(results are garbage, timings only)")
+for graph in (True,):
     print("CUDA-graph replay of 20 launches" if graph else "eager launches from Python")
     run("out_proj 384->384 fp32 out", 384, 384, False, 192, graph)
     run("qkv 384->1152 bf16 out", 1152, 384, True, 192, graph)
