@@ -257,7 +257,8 @@ __device__ __forceinline__ void epi_t_setup(const EpiRow& er, bool row_ok, EpiT&
 
 template <int MODE>
 __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, bool row_ok, const EpiT& et, const uint32_t* r,
-                                            int nb0, long long col0, bool out_bf16, uint8_t* stage, bool no_stg = false) {
+                                            int nb0, long long col0, bool out_bf16, uint8_t* stage, bool no_stg = false,
+                                            bool atomic = false) {
   const int lane = threadIdx.x & 31;
   const unsigned okmask = no_stg ? 0u : et.okmask;
   const int tr = lane >> 2, tcq = lane & 3;                // transposed role: row tr (+8 per step), 16-byte quarter tcq
@@ -351,9 +352,14 @@ __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, 
       for (int jj = 0; jj < 4; ++jj) {
         const int row = jj * 8 + tr;
         const uint4 x = lds128(sbase + row * 64 + (((uint32_t)tcq ^ (uint32_t)((row >> 1) & 3)) << 4));
-        if ((okmask >> row) & 1u)
-          st4((float*)g.C + tb[jj] + col0 + half * 16 + tcq * 4,
-              make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w)));
+        if ((okmask >> row) & 1u) {
+          float* dst = (float*)g.C + tb[jj] + col0 + half * 16 + tcq * 4;
+          const float4 xv = make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w));
+          // split-K / accumulate: one 16-byte vector reduction per lane, 8 rows x 64 B per instruction -- 8x fewer L2
+          // atomic operations than the row-per-thread scalar atomics (the k = 1 weight gradients were bound by them)
+          if (atomic) atomicAdd(reinterpret_cast<float4*>(dst), xv);
+          else st4(dst, xv);
+        }
       }
       __syncwarp();
     }
@@ -525,8 +531,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       const bool vec_bf16 = cstr == 1 && g.c_bf16 && al8 && (colbase % 8 == 0) && aux_al;
       // coalesced (smem-transposed) store path: decided and set up once per tile
       EpiT et;
-      bool t_path = p.epi_transpose &&
-                    ((vec_f32 && g.relu_aux == nullptr) || (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
+      const bool vec_f32_at = cstr == 1 && !g.c_bf16 && atomic && al4 && (colbase % 4 == 0) && g.relu_aux == nullptr &&
+                              g.bias == nullptr && !g.relu;
+      bool t_path = p.epi_transpose && (vec_f32_at || (vec_f32 && g.relu_aux == nullptr) ||
+                                        (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
       if (t_path) {
         epi_t_setup(er, row_ok, et);
         t_path = !et.mirrors;
@@ -547,7 +555,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         const int nb0 = n0 + c * 32;
         if (nb0 >= g.N || p.dbg_mode == 3) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
         if (t_path && nb0 + 32 <= g.N) {
-          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4);
+          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4, atomic);
           continue;
         }
         if (!row_ok || er.skip) continue;
@@ -777,8 +785,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
       const bool vec_bf16 = cstr == 1 && g.c_bf16 && al8 && (colbase % 8 == 0) && aux_al;
       // coalesced (smem-transposed) store path: decided and set up once per tile
       EpiT et;
-      bool t_path = p.epi_transpose &&
-                    ((vec_f32 && g.relu_aux == nullptr) || (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
+      const bool vec_f32_at = cstr == 1 && !g.c_bf16 && atomic && al4 && (colbase % 4 == 0) && g.relu_aux == nullptr &&
+                              g.bias == nullptr && !g.relu;
+      bool t_path = p.epi_transpose && (vec_f32_at || (vec_f32 && g.relu_aux == nullptr) ||
+                                        (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
       if (t_path) {
         epi_t_setup(er, row_ok, et);
         t_path = !et.mirrors;
@@ -803,7 +813,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
         const int nb0 = n0 + c * 32;
         if (nb0 >= g.N || p.dbg_mode == 3) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
         if (t_path && nb0 + 32 <= g.N) {
-          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4);
+          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4, atomic);
           continue;
         }
         if (!row_ok || er.skip) continue;
