@@ -161,6 +161,47 @@ def cpu_reference_run(steps, warmup, sample_batch=8, quiet=False):
                        f"workload, fp32 eager PyTorch, dropout on, AdamW), {dt:.1f} s", ms_per_step=1e3 * dt / max(steps, 1))
 
 
+def eager_gpu_reference_run(steps=3, warmup=2, batch=BATCH):
+    """The north_star's "20x" denominator: the reference's eager-PyTorch step on the same B200 -- the oracle
+    restatement moved to cuda:0 as it is (fp32, no AMP, its per-sample Python loops and host syncs included), on the
+    same synthetic batches as the GPU workload.  CUDA-event timed; a reported baseline, not part of the product path."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fs2_oracle as O
+    data = importlib.import_module(PKG + ".data")
+    dev = torch.device("cuda")
+    model = O.build(seed=0).to(dev).train()
+    crit = O.Loss(**O.DEFAULT_LOSS_CONFIG).to(dev) if hasattr(O.Loss, "to") else O.Loss(**O.DEFAULT_LOSS_CONFIG)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    batches = [([t.to(dev) if torch.is_tensor(t) else t for t in b[:8]], i.to(dev))
+               for b, i in data.synthetic_batches(batch, N_DISTINCT, seed=1234, rank=0)]
+
+    def one(i):
+        (tokens, speakers, in_lens, mel, pitch, energy, dur, out_lens), intensity = batches[i % len(batches)]
+        preds = model(tokens, speakers, dur, pitch, energy, intensity=intensity)
+        loss = crit(preds, (mel, dur, pitch, energy, out_lens, in_lens), 0)
+        opt.zero_grad()
+        loss["total_loss"].backward()
+        opt.step()
+        return int(out_lens.sum())
+
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    frames = 0
+    for i in range(steps):
+        frames += one(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del model, opt, batches
+    torch.cuda.empty_cache()
+    return {"value": frames / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "kind": "port",
+            "sample": f"{steps} training steps of batch {batch} on cuda:0 (oracle restatement of the reference, eager PyTorch "
+                      "fp32, TF32 off, dropout on, AdamW); same batches as the GPU workload"}
+
+
 # ------------------------------------------------------------------------------------------- dominant kernel
 def dominant_kernel_roofline(pkg, model, peaks, B=BATCH, Tm=800, iters=12):
     """tcgen05 implicit-GEMM Conv1d k=9 (decoder FFN, 384 -> 1536 + bias + ReLU): the largest share of the step.
@@ -344,6 +385,10 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(8, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        try:
+            line["eager_gpu_baseline"] = eager_gpu_reference_run()
+        except Exception as e:                       # a baseline leg must never take the product number down with it
+            line["eager_gpu_baseline"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

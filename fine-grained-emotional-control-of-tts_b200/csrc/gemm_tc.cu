@@ -1075,7 +1075,10 @@ int g_epi_transpose = 1;   // FS2_TC_EPIT=0 switches the coalesced (smem-transpo
 bool prefer_pair(const Fs2Gemm& g) {
   // the pair kernel wins (1-8 %) where its 256-wide tiles divide N and the reduction is long; elsewhere the single-CTA
   // kernel's exact-fit 192 / 128 tiles are faster (gpurun_out/gemm_sweep4.log)
-  return g.N % 256 == 0 && (long long)g.K * g.taps >= 1024 && g.M >= 2048;
+  if (g.N % 256 == 0 && (long long)g.K * g.taps >= 1024 && g.M >= 2048) return true;
+  // the k = 9 FFN dgrad (N = 384, reduction 1536 x 9) on mel-length row counts: pair/384 151 us vs 164 us single-CTA/192 at
+  // T = 488; at phoneme-length row counts (4352 rows) the pair kernel has too few tiles and loses 1.7x
+  return g.mode == 1 && g.N == 384 && (long long)g.K * g.taps >= 8192 && g.M >= 8192;
 }
 
 }  // namespace

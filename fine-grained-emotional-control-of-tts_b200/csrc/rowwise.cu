@@ -222,19 +222,27 @@ __device__ __forceinline__ void block_reduce_cols(float4 (&a)[NV], float* out, i
 // NV = float4 per lane (ceil(C / 128)): 3 for the 384-wide model rows, 4 for the PostNet (512), 1 for n_mels (80);
 // HEAD = the variance predictors' 384 -> 1 output layer is folded in.  Both only size the register arrays.
 template <typename TA, int NV, bool HEAD>
-__global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
+__global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_kernel(Fs2LnBwd p) {
   pdl_wait();
   __shared__ float red[WARPS][128];
+  // dgamma / dbeta partial sums live in shared memory, one private slab per warp (a lane only ever touches its own
+  // columns, so no synchronisation is needed inside the row loop): 24 registers fewer than register accumulators,
+  // which is the difference between 2 and 3 resident CTAs per SM for the 384-wide rows.
+  __shared__ __align__(16) float acc_g[WARPS][NV * 128];
+  __shared__ __align__(16) float acc_b[WARPS][NV * 128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = p.T, C = p.C, TP = T + 2 * FS2_PAD;
   const long long rows = (long long)p.B * TP;
   const float invC = 1.0f / (float)C;
   TA* da_out = (TA*)p.dact;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    *reinterpret_cast<float4*>(&acc_g[warp][lane * 4 + i * 128]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(&acc_b[warp][lane * 4 + i * 128]) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const unsigned long long bump = p.seed_dev ? mix64(*p.seed_dev) : 0ull;
   const DropCfg db{p.drop_b_p, p.drop_b_seed ^ bump}, da{p.drop_a_p, p.drop_a_seed ^ bump};
-  float4 dg[NV], dbt[NV], dhw[HEAD ? NV : 1];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) dg[i] = dbt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dhw[HEAD ? NV : 1];
 #pragma unroll
   for (int i = 0; i < (HEAD ? NV : 1); ++i) dhw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float dhb = 0.f;
@@ -256,6 +264,7 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
     const long long m2 = (f > 0 && t >= T - 1 - f && t <= T - 2) ? 2LL * (T - 1 - t) * C : 0;
     float4 xh[NV], gx[NV];
     float s1 = 0.f, s2 = 0.f;
+    unsigned keep_b = 0u;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       int c = lane * 4 + i * 128;
@@ -266,6 +275,8 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
           float4 br = ld4(p.branch + ro + c);
           float4 k = drop_scale4(db, (uint64_t)(ro + c) >> 2);
           z.x += br.x * k.x; z.y += br.y * k.y; z.z += br.z * k.z; z.w += br.w * k.w;
+          // remember the keep bits: the gradient of the branch needs the same mask again (one RNG evaluation, not two)
+          keep_b |= ((k.x != 0.f ? 1u : 0u) | (k.y != 0.f ? 2u : 0u) | (k.z != 0.f ? 4u : 0u) | (k.w != 0.f ? 8u : 0u)) << (4 * i);
         }
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.dy) g = ld4(p.dy + ro + c);
@@ -293,8 +304,15 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
         if (p.tanh_act) {
           g.x *= (1.f - u.x * u.x); g.y *= (1.f - u.y * u.y); g.z *= (1.f - u.z * u.z); g.w *= (1.f - u.w * u.w);
         }
-        dg[i].x += g.x * h.x; dg[i].y += g.y * h.y; dg[i].z += g.z * h.z; dg[i].w += g.w * h.w;
-        dbt[i].x += g.x; dbt[i].y += g.y; dbt[i].z += g.z; dbt[i].w += g.w;
+        {
+          float4* ag = reinterpret_cast<float4*>(&acc_g[warp][c]);
+          float4* ab = reinterpret_cast<float4*>(&acc_b[warp][c]);
+          float4 sg = *ag, sb = *ab;
+          sg.x += g.x * h.x; sg.y += g.y * h.y; sg.z += g.z * h.z; sg.w += g.w * h.w;
+          sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
+          *ag = sg;
+          *ab = sb;
+        }
         g.x *= gam.x; g.y *= gam.y; g.z *= gam.z; g.w *= gam.w;
         s1 += g.x + g.y + g.z + g.w;
         s2 += g.x * h.x + g.y * h.y + g.z * h.z + g.w * h.w;
@@ -324,8 +342,9 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
         if (p.dx_f32) st4(p.dx_f32 + ro + c, dz);
         if (da_out) {
           if (p.branch) {
-            float4 k = drop_scale4(db, (uint64_t)(ro + c) >> 2);
-            dz.x *= k.x; dz.y *= k.y; dz.z *= k.z; dz.w *= k.w;
+            const float sk = db.p > 0.f ? 1.0f / (1.0f - db.p) : 1.0f;
+            const unsigned kb = keep_b >> (4 * i);
+            dz.x *= (kb & 1u) ? sk : 0.f; dz.y *= (kb & 2u) ? sk : 0.f; dz.z *= (kb & 4u) ? sk : 0.f; dz.w *= (kb & 8u) ? sk : 0.f;
           }
           st4(da_out + ro + c, dz);
         }
@@ -333,8 +352,14 @@ __global__ void __launch_bounds__(THREADS) ln_bwd_kernel(Fs2LnBwd p) {
     }
   }
   // block reduction of the parameter gradients, one atomicAdd per column per block
-  block_reduce_cols(dg, p.dgamma, C, red, warp, lane);
-  block_reduce_cols(dbt, p.dbeta, C, red, warp, lane);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += THREADS) {
+    float vg = 0.f, vb = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { vg += acc_g[w][c]; vb += acc_b[w][c]; }
+    if (p.dgamma) atomicAdd(p.dgamma + c, vg);
+    if (p.dbeta) atomicAdd(p.dbeta + c, vb);
+  }
   if (HEAD) block_reduce_cols(dhw, p.dhead_w, C, red, warp, lane);
   if (HEAD && p.dhead_b) {
     __syncthreads();
@@ -1095,7 +1120,7 @@ extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
   REQUIRE(p->C % 4 == 0 && p->C <= 128 * MAXV, "fs2_ln_bwd: C must be a multiple of 4 and <= 512");
   const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
   int grid = grid_for_rows(rows);
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148 * 6) grid = 148 * 6;      // two waves of three resident CTAs per SM
   const int nv = (p->C + 127) / 128;
   const bool head = p->head_w != nullptr || p->dhead_w != nullptr || p->dhead_b != nullptr;
 #define LN_BWD_LAUNCH(TA, NV, HEAD) FS2_LAUNCH((ln_bwd_kernel<TA, NV, HEAD>), grid, THREADS, 0, ST, *p)

@@ -1,0 +1,37 @@
+"""Per-phoneme emotion-intensity representation: the step immediately upstream of every training step
+(`/root/reference/emo_rank_tts/fastspeech2/train.py:16-51`).
+
+The reference runs the frozen extractor and then loops over the batch in Python -- `.item()` syncs,
+`repeat_interleave`, `index_add_`, divide by `clamp(dur, 1)`.  Here the segmented mean of the (B, Tm, D) frame
+intensities over the durations is ONE kernel (`fs2_intensity_segment_mean`): no host sync, no per-sample launch."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def intensity_segment_mean(I, duration_tgt, phon_len, T_phon_max=None):
+    """I: (B, Tm, D) float CUDA; duration_tgt: (B, Tp) int; phon_len: (B,) int  ->  (B, Tp, D) fp32.
+    out[b, p] = mean of I[b, f] over the frames of phoneme p (zero-duration phonemes and p >= phon_len[b] give 0;
+    frames beyond Tm are ignored, as the reference's slice I[b, :T_mel] does)."""
+    if not I.is_cuda:
+        raise RuntimeError("fs2_b200: intensity_segment_mean needs CUDA tensors (there is no CPU fallback)")
+    B, Tm, D = I.shape
+    Tp = int(T_phon_max) if T_phon_max is not None else int(duration_tgt.shape[1])
+    if duration_tgt.shape[1] != Tp:
+        raise ValueError("duration_tgt must be (B, T_phon_max)")
+    I = I.detach().contiguous().float()
+    dur = duration_tgt.to(I.device).contiguous().long()
+    pl = phon_len.to(I.device).contiguous().long()
+    out = torch.empty(B, Tp, D, device=I.device, dtype=torch.float32)
+    L.call("fs2_intensity_segment_mean", I, dur, pl, B, Tp, Tm, D, out)
+    return out
+
+
+def get_intensity_representation(intensity_extractor, batch, device):
+    """Drop-in for train.py:16-51: same arguments, same (B, T_phon_max, D) result."""
+    (phoneme, _, phon_len, _, _, _, duration_tgt, mel_len, _, _, rank_X, emo_ids) = batch
+    with torch.no_grad():
+        I = intensity_extractor(rank_X, mel_len, emo_ids)
+        return intensity_segment_mean(I.to(device), duration_tgt, phon_len, phoneme.shape[1])

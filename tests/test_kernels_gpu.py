@@ -426,3 +426,22 @@ def test_intensity_segment_mean_matches_train_py(lib):
     out = torch.empty(B, Tp, D, device="cuda")
     lib.call("fs2_intensity_segment_mean", inten.cuda(), dur.cuda(), phon_len.cuda(), B, Tp, Tm, D, out)
     assert (out.cpu() - ref).abs().max() <= 1e-5
+
+
+def test_get_intensity_representation_drop_in(pkg):
+    """Same call as train.py:69 with a stand-in extractor: the batch tuple layout of dataset.py:120-133 goes in, the
+    (B, T_phon_max, 5) representation comes out and equals the reference's per-sample loop (restated in the oracle)."""
+    data = importlib.import_module(pkg.__name__ + ".data")
+    (batch, _), = data.synthetic_batches(6, 1, seed=5, min_tp=6, max_tp=20, max_frames=120, pool_factor=2)
+    g = torch.Generator().manual_seed(9)
+    Tm = batch[3].shape[1]
+    frames = torch.randn(6, Tm, 5, generator=g)
+
+    def extractor(rank_X, mel_len, emo_ids):          # stands in for RankModel.intensity_extractor (frozen)
+        assert rank_X.shape == (6, 82, Tm)
+        return frames.cuda()
+
+    dev_batch = tuple(t.cuda() if torch.is_tensor(t) else t for t in batch)
+    out = pkg.get_intensity_representation(extractor, dev_batch, torch.device("cuda"))
+    ref = O.intensity_segment_mean(frames, batch[2], batch[6], batch[0].shape[1])
+    assert out.shape == ref.shape and (out.cpu() - ref).abs().max() <= 1e-5
