@@ -525,43 +525,72 @@ __global__ void __launch_bounds__(THREADS) cond_finish_kernel(const float* G, co
 }
 
 // dsum[b,c] = sum_t dy[b,t,c];  dWi[c,i] += sum_{b,t} dy[b,t,c] * int[b,t,i]     (dy already masked)
-__global__ void cond_bwd_rows_kernel(const float* dy, const float* intensity, int B, int Tp, int D, float* dsum,
-                                     float* dWcat) {
+constexpr int COND_ROWS = 16;     // phoneme rows per CTA of cond_bwd_rows_kernel
+__global__ void cond_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ intensity, int B, int Tp,
+                                     int D, float* dsum, float* dWcat) {
   pdl_wait();
-  const int b = blockIdx.x;
+  // grid (row chunks, B): every thread owns columns c, c+128, ... and COND_ROWS rows; dsum must be zero on entry
+  __shared__ float iv[COND_ROWS][5];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * COND_ROWS;
+  const int nt = min(COND_ROWS, Tp - t0);
   const int TP = Tp + 2 * FS2_PAD;
   const int ldw = 2 * D + 5;
+  for (int i = threadIdx.x; i < nt * 5; i += blockDim.x) iv[i / 5][i % 5] = intensity[((long long)b * Tp + t0) * 5 + i];
+  __syncthreads();
+  const float* src = dy + ((long long)b * TP + FS2_PAD + t0) * D;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float s = 0.f, wi[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int t = 0; t < Tp; ++t) {
-      float g = dy[((long long)b * TP + FS2_PAD + t) * D + c];
-      s += g;
-      const float* iv = intensity + ((long long)b * Tp + t) * 5;
+    float g[COND_ROWS];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) wi[i] += g * iv[i];
+    for (int t = 0; t < COND_ROWS; ++t) g[t] = (t < nt) ? src[(long long)t * D + c] : 0.f;     // independent loads
+    float s = 0.f, wi[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < COND_ROWS; ++t) {
+      s += g[t];
+      if (t < nt) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) wi[i] += g[t] * iv[t][i];
+      }
     }
-    dsum[(long long)b * D + c] = s;
+    atomicAdd(dsum + (long long)b * D + c, s);
 #pragma unroll
     for (int i = 0; i < 5; ++i) atomicAdd(dWcat + (long long)c * ldw + 2 * D + i, wi[i]);
   }
 }
 // dWs[c,e] += sum_b dsum[b,c]*emb[spk[b],e];   dspk_emb[spk[b],e] += sum_c Ws[c,e]*dsum[b,c]
-__global__ void cond_bwd_spk_kernel(const float* dsum, const float* Wcat, const float* spk_emb, const int64_t* speakers,
-                                    int B, int D, float* dWcat, float* dspk_emb) {
+__global__ void cond_bwd_spk_kernel(const float* __restrict__ dsum, const float* __restrict__ Wcat,
+                                    const float* __restrict__ spk_emb, const int64_t* __restrict__ speakers, int B, int D,
+                                    float* dWcat, float* dspk_emb) {
   pdl_wait();
   const int ldw = 2 * D + 5;
-  const long long n = (long long)D * D;
+  // dWcat[c, D + e] += sum_b dsum[b, c] * spk_emb[spk[b], e]: one item per (c, e, chunk of 8 utterances)
+  const int bch = (B + 7) / 8;
+  const long long n = (long long)D * D * bch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i / D), e = (int)(i - (long long)c * D);
+    const int e = (int)(i % D);
+    const long long q = i / D;
+    const int c = (int)(q % D), b0 = (int)(q / D) * 8;
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dsum[(long long)b * D + c] * spk_emb[speakers[b] * D + e];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j;
+      if (b < B) s += dsum[(long long)b * D + c] * spk_emb[speakers[b] * D + e];
+    }
     atomicAdd(dWcat + (long long)c * ldw + D + e, s);
   }
-  const long long m = (long long)B * D;
+  // dspk_emb[spk[b], e] += sum_c Wcat[c, D + e] * dsum[b, c]: one item per (b, e, chunk of 32 input channels)
+  const int cch = (D + 31) / 32;
+  const long long m = (long long)B * D * cch;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
-    int b = (int)(i / D), e = (int)(i - (long long)b * D);
+    const int e = (int)(i % D);
+    const long long q = i / D;
+    const int b = (int)(q % B), c0 = (int)(q / B) * 32;
     float s = 0.f;
-    for (int c = 0; c < D; ++c) s += Wcat[(long long)c * ldw + D + e] * dsum[(long long)b * D + c];
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const int c = c0 + j;
+      if (c < D) s += Wcat[(long long)c * ldw + D + e] * dsum[(long long)b * D + c];
+    }
     atomicAdd(dspk_emb + speakers[b] * D + e, s);
   }
 }
@@ -581,21 +610,51 @@ __global__ void avg_over_durations_kernel(const float* values, const int64_t* du
   for (int i = threadIdx.x; i < Tm; i += blockDim.x) vc[i + 1] = v[i];
   for (int i = threadIdx.x; i < Tp; i += blockDim.x) de[i] = (int)durs[(long long)b * Tp + i];
   __syncthreads();
-  if (threadIdx.x == 0) {
+  // prefix sums with a double accumulator (torch CPU cumsum semantics, fp32 prefixes): warp 0 scans the values, warp 1
+  // the durations.  Each lane sums a contiguous chunk, the lane totals are scanned with shuffles, then the chunk is
+  // replayed with its offset -- ~Tm/32 dependent adds instead of Tm.
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (wid == 0) {
+    const int per = (Tm + 31) / 32;
+    const int i0 = 1 + lane * per, i1 = min(Tm + 1, i0 + per);
     double acc = 0.0;
     int cnt = 0;
-    vc[0] = 0.f;
-    nc[0] = 0;
-    for (int i = 1; i <= Tm; ++i) {
-      float x = vc[i];
+    for (int i = i0; i < i1; ++i) {
+      const float x = vc[i];
       acc += (double)x;
       cnt += (x != 0.0f) ? 1 : 0;
-      vc[i] = (float)acc;
-      nc[i] = cnt;
     }
-  } else if (threadIdx.x == 32) {
+    double off = acc;
+    int coff = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double a = __shfl_up_sync(0xffffffffu, off, o);
+      const int c = __shfl_up_sync(0xffffffffu, coff, o);
+      if (lane >= o) { off += a; coff += c; }
+    }
+    off -= acc;                      // exclusive offsets of this lane's chunk
+    coff -= cnt;
+    if (lane == 0) { vc[0] = 0.f; nc[0] = 0; }
+    for (int i = i0; i < i1; ++i) {
+      const float x = vc[i];
+      off += (double)x;
+      coff += (x != 0.0f) ? 1 : 0;
+      vc[i] = (float)off;
+      nc[i] = coff;
+    }
+  } else if (wid == 1) {
+    const int per = (Tp + 31) / 32;
+    const int i0 = lane * per, i1 = min(Tp, i0 + per);
     int acc = 0;
-    for (int i = 0; i < Tp; ++i) { acc += de[i]; de[i] = acc; }
+    for (int i = i0; i < i1; ++i) acc += de[i];
+    int off = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, off, o);
+      if (lane >= o) off += a;
+    }
+    off -= acc;
+    for (int i = i0; i < i1; ++i) { off += de[i]; de[i] = off; }
   }
   __syncthreads();
   for (int p = threadIdx.x; p < Tp; p += blockDim.x) {
@@ -654,8 +713,8 @@ __global__ void __launch_bounds__(THREADS) embed_add_kernel(const float* x, cons
 }
 
 // dw[c,j] += sum_{b,t} dy[b,t,c]*contour_r[b,t+j-p]; dbias[c] += sum dy   (all rect rows, unmasked)
-__global__ void embed_add_bwd_kernel(const float* dy, const float* contour, int ksize, int B, int Tp, int D, float* dw,
-                                     float* dbias) {
+__global__ void embed_add_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ contour, int ksize, int B,
+                                     int Tp, int D, float* dw, float* dbias) {
   pdl_wait();
   const int TP = Tp + 2 * FS2_PAD;
   const int pad = (ksize - 1) / 2;
@@ -664,11 +723,26 @@ __global__ void embed_add_bwd_kernel(const float* dy, const float* contour, int 
   float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float sb = 0.f;
   const long long total = (long long)B * Tp;
-  for (long long i = blockIdx.y; i < total; i += gridDim.y) {
-    int b = (int)(i / Tp), t = (int)(i - (long long)b * Tp);
-    float g = dy[((long long)b * TP + FS2_PAD + t) * D + c];
-    sb += g;
-    for (int j = 0; j < ksize; ++j) acc[j] += g * contour[(long long)b * Tp + reflect_idx(t + j - pad, Tp)];
+  for (long long i0 = blockIdx.y; i0 < total; i0 += 4LL * gridDim.y) {
+    float g[4];
+    int bb[4], tt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                      // four independent row loads in flight
+      const long long i = i0 + (long long)u * gridDim.y;
+      g[u] = 0.f;
+      bb[u] = 0;
+      tt[u] = 0;
+      if (i < total) {
+        bb[u] = (int)(i / Tp);
+        tt[u] = (int)(i - (long long)bb[u] * Tp);
+        g[u] = dy[((long long)bb[u] * TP + FS2_PAD + tt[u]) * D + c];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sb += g[u];
+      for (int j = 0; j < ksize; ++j) acc[j] += g[u] * contour[(long long)bb[u] * Tp + reflect_idx(tt[u] + j - pad, Tp)];
+    }
   }
   for (int j = 0; j < ksize; ++j) atomicAdd(dw + (long long)c * ksize + j, acc[j]);
   atomicAdd(dbias + c, sb);
@@ -1174,10 +1248,12 @@ extern "C" int fs2_cond_bwd(const float* dy, const float* Wcat, const float* spk
                             const float* intensity, int B, int Tp, int D, float* dsum_ws, float* dWcat, float* dspk_emb,
                             void* stream) {
   REQUIRE(dy && Wcat && spk_emb && speakers && intensity && dsum_ws && dWcat && dspk_emb, "fs2_cond_bwd: null pointer");
-  FS2_LAUNCH((cond_bwd_rows_kernel), B, 128, 0, ST, dy, intensity, B, Tp, D, dsum_ws, dWcat);
+  REQUIRE(B > 0 && B <= 65535, "fs2_cond_bwd: B <= 65535");
+  CUDA_CHECK_RET(cudaMemsetAsync(dsum_ws, 0, (size_t)B * D * sizeof(float), ST));
+  FS2_LAUNCH((cond_bwd_rows_kernel), dim3((Tp + COND_ROWS - 1) / COND_ROWS, B), 128, 0, ST, dy, intensity, B, Tp, D, dsum_ws, dWcat);
   int rc = fs2_check_launch();
   if (rc) return rc;
-  FS2_LAUNCH((cond_bwd_spk_kernel), 148, 256, 0, ST, dsum_ws, Wcat, spk_emb, speakers, B, D, dWcat, dspk_emb);
+  FS2_LAUNCH((cond_bwd_spk_kernel), 148 * 4, 256, 0, ST, dsum_ws, Wcat, spk_emb, speakers, B, D, dWcat, dspk_emb);
   return fs2_check_launch();
 }
 
@@ -1204,7 +1280,7 @@ extern "C" int fs2_embed_add(const float* x, const float* contour, const float* 
 extern "C" int fs2_embed_add_bwd(const float* dy, const float* contour, int ksize, int B, int Tp, int D, float* dw,
                                  float* dbias, void* stream) {
   REQUIRE(dy && contour && dw && dbias && ksize <= 9, "fs2_embed_add_bwd: bad arguments");
-  dim3 grid((D + 127) / 128, 64);
+  dim3 grid((D + 127) / 128, 256);
   FS2_LAUNCH((embed_add_bwd_kernel), grid, 128, 0, ST, dy, contour, ksize, B, Tp, D, dw, dbias);
   return fs2_check_launch();
 }
