@@ -1175,7 +1175,36 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   }
   p.epi_transpose = g_epi_transpose;
   const bool pair_ok = g.batch1 * g.batch2 == 1 && g.M > BM;
-  if (pair_ok && (g_use_pair == 1 || g_use_pair == 3 || (g_use_pair == 2 && prefer_pair(g)))) {
+  const bool use_pair = pair_ok && (g_use_pair == 1 || g_use_pair == 3 || (g_use_pair == 2 && prefer_pair(g)));
+  // dgrad with a plain fp32 epilogue and fewer tiles than ~2 waves (phoneme-length row counts: 56 tiles of a k = 9
+  // reduction on 148 SMs): split the reduction like the weight gradients do; the partial sums meet in C through the
+  // 16-byte vector atomics of the transposed epilogue.  C is zeroed here.
+  if (!use_pair && g.mode == 1 && g.split_k == 0 && !g.c_bf16 && !g.accumulate && !g.bias && !g.relu && !g.relu_aux &&
+      g.rs_Tp == 0 && g.lens == nullptr && g.halo == 0 && g.batch1 * g.batch2 == 1 && g.ldc == g.N && g.c_col_off == 0 &&
+      g_epi_transpose) {
+    if (g_num_sms == 0) {
+      int dev = 0;
+      CUDA_CHECK_RET(cudaGetDevice(&dev));
+      CUDA_CHECK_RET(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long tiles = (long long)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+    const int epi_kb = 4;
+    long long best_cost = -1;
+    int best = 1;
+    for (int s = 1; s <= 16 && s <= p.total_kb; ++s) {
+      const long long waves = (tiles * s + g_num_sms - 1) / g_num_sms;
+      const long long cost = waves * ((p.total_kb + s - 1) / s + (s > 1 ? 2 * epi_kb : epi_kb));
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+    }
+    if (best > 1) {
+      p.nsplit = best;
+      p.kb_per_split = (p.total_kb + p.nsplit - 1) / p.nsplit;
+      p.nsplit = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
+      if (p.nsplit > 1)
+        CUDA_CHECK_RET(cudaMemsetAsync((float*)g.C + (long long)g.c_row_off * g.ldc, 0, (size_t)g.M * g.N * sizeof(float), st));
+    }
+  }
+  if (use_pair) {
     const int cfg = (g_force_cfg >= 0 && g_force_cfg <= 2) ? g_force_cfg : pick_cfg(g.N);
     const int ncta = g_use_pair == 3 ? 1 : 2;
     CUtensorMap ta, tb;

@@ -268,6 +268,9 @@ class FastSpeech2(nn.Module):
                a_row_off=p, a_tap_step=-1, B=self.store.packed_buf, B_off=w.off, ldb=w.k * w.cin, b_rows=w.cout,
                b_inner=w.k * w.cin, b_tap_step=w.cin, Cout=out, ldc=w.cin, c_bf16=c_bf16, ab_bf16=self._bf16,
                relu_aux=relu_aux, aux_bf16=int(self._bf16))
+        # (split_k=0 would let fs2_gemm_tc split short-grid dgrads; measured: no step-time gain once the weight gradients
+        #  fill the idle SMs from the second stream, and the atomics' summation order would leak into the bf16 roundings
+        #  of the activation gradients -- run-to-run differences of 5e-4 instead of 1e-6 -- so it stays off)
 
     def _side_begin(self, dev):
         if not self.overlap_wgrad:

@@ -54,6 +54,9 @@ CASES = [
     ("pair_wgrad_n1536", 2, 384, 1536, 1500, 1, 1500, 384, 1500, 1536, dict(split_k=0)),
     ("pair_wgrad_m1536", 2, 1536, 384, 1500, 3, 1500, 1536, 1500, 384, dict(b_row_off=-1, b_tap_step=1, split_k=0)),
     ("pair_wgrad_n80", 2, 512, 80, 1300, 5, 1300, 512, 1300, 80, dict(b_row_off=-2, b_tap_step=1, split_k=0)),
+    # dgrad with fewer tiles than SMs: split_k = 0 lets the library split the reduction (vector atomics into a C it zeroes)
+    ("dgrad_autosplit", 1, 600, 384, 512, 9, 608, 512, 512, 9 * 384, dict(a_row_off=4, a_tap_step=-1, b_tap_step=384, split_k=0)),
+    ("dgrad_autosplit_k1", 1, 1000, 384, 1152, 1, 1000, 1152, 1152, 384, dict(split_k=0)),
 ]
 
 
