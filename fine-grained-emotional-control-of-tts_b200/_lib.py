@@ -106,7 +106,7 @@ class Fs2LnBwd(C.Structure):
         ("relu_x", C.c_int),
         ("dx_f32", C.c_void_p), ("dact", C.c_void_p), ("act_bf16", C.c_int),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dhead_w", C.c_void_p), ("dhead_b", C.c_void_p),
-        ("seed_dev", C.c_void_p),
+        ("seed_dev", C.c_void_p), ("dact_colsum", C.c_void_p),
     ]
 
 

@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
   // which is the difference between 2 and 3 resident CTAs per SM for the 384-wide rows.
   __shared__ __align__(16) float acc_g[WARPS][NV * 128];
   __shared__ __align__(16) float acc_b[WARPS][NV * 128];
+  constexpr bool CS_OK = NV <= 3;                                    // third slab only where static smem allows it
+  __shared__ __align__(16) float acc_d[CS_OK ? WARPS : 1][CS_OK ? NV * 128 : 4];   // column sums of dact (bias gradient)
+  const bool want_cs = CS_OK && p.dact_colsum != nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int T = p.T, C = p.C, TP = T + 2 * FS2_PAD;
   const long long rows = (long long)p.B * TP;
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
   for (int i = 0; i < NV; ++i) {
     *reinterpret_cast<float4*>(&acc_g[warp][lane * 4 + i * 128]) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(&acc_b[warp][lane * 4 + i * 128]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (CS_OK) *reinterpret_cast<float4*>(&acc_d[CS_OK ? warp : 0][lane * 4 + i * 128]) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const unsigned long long bump = p.seed_dev ? mix64(*p.seed_dev) : 0ull;
   const DropCfg db{p.drop_b_p, p.drop_b_seed ^ bump}, da{p.drop_a_p, p.drop_a_seed ^ bump};
@@ -347,6 +351,12 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
             dz.x *= (kb & 1u) ? sk : 0.f; dz.y *= (kb & 2u) ? sk : 0.f; dz.z *= (kb & 4u) ? sk : 0.f; dz.w *= (kb & 8u) ? sk : 0.f;
           }
           st4(da_out + ro + c, dz);
+          if (want_cs) {
+            float4* ad = reinterpret_cast<float4*>(&acc_d[CS_OK ? warp : 0][CS_OK ? c : 0]);
+            float4 sd = *ad;
+            sd.x += dz.x; sd.y += dz.y; sd.z += dz.z; sd.w += dz.w;
+            *ad = sd;
+          }
         }
       }
     }
@@ -359,6 +369,12 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
     for (int w = 0; w < WARPS; ++w) { vg += acc_g[w][c]; vb += acc_b[w][c]; }
     if (p.dgamma) atomicAdd(p.dgamma + c, vg);
     if (p.dbeta) atomicAdd(p.dbeta + c, vb);
+    if (want_cs) {
+      float vd = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) vd += acc_d[CS_OK ? w : 0][CS_OK ? c : 0];
+      atomicAdd(p.dact_colsum + c, vd);
+    }
   }
   if (HEAD) block_reduce_cols(dhw, p.dhead_w, C, red, warp, lane);
   if (HEAD && p.dhead_b) {
@@ -1192,6 +1208,7 @@ extern "C" int fs2_ln_fwd(const Fs2LnFwd* p, void* stream) {
 extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
   REQUIRE(p && p->x && p->gamma && p->beta && p->mean && p->rstd, "fs2_ln_bwd: null pointer");
   REQUIRE(p->C % 4 == 0 && p->C <= 128 * MAXV, "fs2_ln_bwd: C must be a multiple of 4 and <= 512");
+  REQUIRE(p->dact_colsum == nullptr || (p->C <= 384 && p->dact != nullptr), "fs2_ln_bwd: dact_colsum needs dact and C <= 384");
   const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
   int grid = grid_for_rows(rows);
   if (grid > 148 * 6) grid = 148 * 6;      // two waves of three resident CTAs per SM

@@ -350,7 +350,7 @@ class FastSpeech2(nn.Module):
 
     def _ln_bwd(self, B, T, C, x, gamma, beta, eps, mean, rstd, *, dy=None, dy2=None, dy2_fold=0, dhead=None,
                 head_w=None, head_scale=1.0, branch=None, drop_b=(0.0, 0), tanh=0, drop_a=(0.0, 0), lens=None,
-                relu_x=0, dx_f32=None, dact=None, dgamma=None, dbeta=None, dhead_w=None, dhead_b=None):
+                relu_x=0, dx_f32=None, dact=None, dgamma=None, dbeta=None, dhead_w=None, dhead_b=None, dact_colsum=None):
         self._wait_side(dact)
         p = L.Fs2LnBwd()
         p.B, p.T, p.C = B, T, C
@@ -376,6 +376,7 @@ class FastSpeech2(nn.Module):
         p.dhead_w = dhead_w.data_ptr() if dhead_w is not None else None
         p.dhead_b = dhead_b.data_ptr() if dhead_b is not None else None
         p.seed_dev = self._ctr.data_ptr()
+        p.dact_colsum = dact_colsum.data_ptr() if dact_colsum is not None else None
         L.call("fs2_ln_bwd", L.C.addressof(p))
 
     # ------------------------------------------------------------------- FFT block stack
@@ -483,6 +484,7 @@ class FastSpeech2(nn.Module):
         dX1c, dz2, dz1, dXa = self._f32(rows, D), self._f32(rows, D), self._f32(rows, D), self._f32(rows, D)
         dProj_act, dO_act = self._act(rows, D), self._act(rows, D)
         dy_a, dy_b = self._f32(rows, D), None
+        fuse_bias = D <= 384           # bias gradients of the out-proj / FFN-2 convs come out of the LN backward kernels
         self._ln_bwd(B, T, D, fin.x_f32, self._P(f"{name}.norm.norm.weight"), self._P(f"{name}.norm.norm.bias"), 1e-6,
                      fin.mean, fin.rstd, dy=dout, dy2=dout2, lens=final_lens, dx_f32=dy_a,
                      dgamma=self._G(f"{name}.norm.norm.weight"), dbeta=self._G(f"{name}.norm.norm.bias"))
@@ -493,9 +495,10 @@ class FastSpeech2(nn.Module):
             self._ln_bwd(B, T, D, sv.x1_f32, self._P(f"{pre}.norm2.norm.weight"), self._P(f"{pre}.norm2.norm.bias"), 1e-6,
                          sv.mean2, sv.rstd2, dy=dy_a, dy2=dy_b, branch=sv.Fo, drop_b=(p, sv.seeds[2]),
                          dx_f32=dz2, dact=dF_act, dgamma=self._G(f"{pre}.norm2.norm.weight"),
-                         dbeta=self._G(f"{pre}.norm2.norm.bias"))
+                         dbeta=self._G(f"{pre}.norm2.norm.bias"),
+                         dact_colsum=self._G(f"{pre}.pos_ffn.2.conv.bias") if fuse_bias else None)
             self._conv_wgrad(dF_act, sv.Hh, B, T, f"{pre}.pos_ffn.2.conv.weight", f"{pre}.pos_ffn.2.conv.weight",
-                             f"{pre}.pos_ffn.2.conv.bias")
+                             None if fuse_bias else f"{pre}.pos_ffn.2.conv.bias")
             if h2 == 0:
                 self._conv_dgrad(dF_act, B, T, f"{pre}.pos_ffn.2.conv.weight", dH_act, c_bf16=bf, relu_aux=sv.Hh)
             else:
@@ -508,9 +511,10 @@ class FastSpeech2(nn.Module):
             self._ln_bwd(B, T, D, sv.x_f32, self._P(f"{pre}.norm1.norm.weight"), self._P(f"{pre}.norm1.norm.bias"), 1e-6,
                          sv.mean1, sv.rstd1, dy=dz2, dy2=dX1c, dy2_fold=h1, branch=sv.proj, drop_b=(p, sv.seeds[1]),
                          dx_f32=dz1, dact=dProj_act, dgamma=self._G(f"{pre}.norm1.norm.weight"),
-                         dbeta=self._G(f"{pre}.norm1.norm.bias"))
+                         dbeta=self._G(f"{pre}.norm1.norm.bias"),
+                         dact_colsum=self._G(f"{pre}.self_att.att.out_proj.bias") if fuse_bias else None)
             self._conv_wgrad(dProj_act, sv.O, B, T, f"{pre}.self_att.att.out_proj.weight",
-                             f"{pre}.self_att.att.out_proj.weight", f"{pre}.self_att.att.out_proj.bias")
+                             f"{pre}.self_att.att.out_proj.weight", None if fuse_bias else f"{pre}.self_att.att.out_proj.bias")
             self._conv_dgrad(dProj_act, B, T, f"{pre}.self_att.att.out_proj.weight", dO_act, c_bf16=bf)
             if not fused:
                 # dPd = dO V^T

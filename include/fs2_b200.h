@@ -120,6 +120,8 @@ typedef struct {
   float* dx_f32; void* dact; int act_bf16;
   float* dgamma; float* dbeta; float* dhead_w; float* dhead_b;   /* accumulated (+=) */
   const unsigned long long* seed_dev;
+  float* dact_colsum;   /* optional [C], accumulated (+=): column sums of `dact` over all rows = the bias gradient of the
+                           GEMM that produced `branch` (saves the separate fs2_colsum pass over dact); C <= 384 only */
 } Fs2LnBwd;
 int fs2_ln_bwd(const Fs2LnBwd* p, void* stream);
 
