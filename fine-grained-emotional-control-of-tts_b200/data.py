@@ -100,13 +100,18 @@ def synthetic_batches(batch_size, n_batches, seed=1234, rank=0, min_tp=24, max_t
         pool = [_one_utterance(g, min_tp, max_tp, max_frames) for _ in range(pool_factor * batch_size)]
         n_groups = len(pool) // batch_size + (1 if len(pool) % batch_size else 0)
         perm = torch.randperm(n_groups, generator=g).tolist()
+        fine = 1
         if world > 1:
+            # a 4x larger pool: the `world` neighbouring buckets of one step then span 1/(4*pool_factor) of the length
+            # distribution, which keeps the slowest rank of a step within ~1-2 % of the mean
+            fine = 4
             gw = torch.Generator().manual_seed(seed + step + 7919 * world)
-            pool = [_one_utterance(gw, min_tp, max_tp, max_frames) for _ in range(pool_factor * batch_size * world)]
+            pool = [_one_utterance(gw, min_tp, max_tp, max_frames) for _ in range(pool_factor * batch_size * world * fine)]
         pool.sort(key=lambda u: u["mel"].shape[0])
         groups = [pool[i:i + batch_size] for i in range(0, len(pool), batch_size)]
         for k in perm:
-            out.append(collate(groups[k * world + rank] if world > 1 else groups[k]))
+            # length class k of the single-GPU stream = super-groups k*fine .. k*fine+fine-1; take the middle one
+            out.append(collate(groups[(k * fine + fine // 2) * world + rank] if world > 1 else groups[k]))
             if len(out) == n_batches:
                 break
         step += 1

@@ -88,10 +88,14 @@ class DataParallelStep:
             if hook:
                 self.model.grad_ready_hook = None
         g = self.model.store.flat_grad
+        n = g.numel()
         if self.world > 1:
-            head = g if self._early_lo is None else g[: self._early_lo]
-            allreduce_flat_(head, self.world, self.group)
-            for w in self._pending:
-                w.wait()
-        self.optimizer.step(grad_scale=1.0 / self.world)
+            lo = n if self._early_lo is None else self._early_lo
+            early = list(self._pending)
+            head = dist.all_reduce(g[:lo], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            # tail (decoder / PostNet) is updated while the head (encoder, variance adaptor) is still on the wire
+            self.optimizer.step(grad_scale=1.0 / self.world,
+                                ranges=[(lo, n, lambda: [w.wait() for w in early]), (0, lo, head.wait)])
+        else:
+            self.optimizer.step(grad_scale=1.0)
         return losses, preds

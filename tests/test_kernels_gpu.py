@@ -445,3 +445,26 @@ def test_get_intensity_representation_drop_in(pkg):
     out = pkg.get_intensity_representation(extractor, dev_batch, torch.device("cuda"))
     ref = O.intensity_segment_mean(frames, batch[2], batch[6], batch[0].shape[1])
     assert out.shape == ref.shape and (out.cpu() - ref).abs().max() <= 1e-5
+
+
+def test_fused_adamw_ranges_equal_one_launch(pkg):
+    """FusedAdamW.step(ranges=...) -- used by the data-parallel step to update one all-reduced piece while the next
+    is still on the wire -- gives bit-identical parameters to the single-launch update."""
+    torch.manual_seed(0)
+    ma = pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4).cuda()
+    mb = pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4).cuda()
+    mb.store.flat.copy_(ma.store.flat)
+    for m in (ma, mb):
+        m.store.ensure_grads()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ma.store.flat_grad.copy_(torch.randn(ma.store.flat.numel(), device="cuda", generator=g) * 1e-2)
+    mb.store.flat_grad.copy_(ma.store.flat_grad)
+    oa, ob = pkg.FusedAdamW(ma, lr=1e-3), pkg.FusedAdamW(mb, lr=1e-3)
+    lo, n = ma.grad_split_lo, ma.store.flat.numel()
+    assert 0 < lo < n and lo % 4 == 0
+    called = []
+    for _ in range(3):
+        oa.step(grad_scale=0.5)
+        ob.step(grad_scale=0.5, ranges=[(lo, n, lambda: called.append("tail")), (0, lo, lambda: called.append("head"))])
+    assert called == ["tail", "head"] * 3
+    assert torch.equal(ma.store.flat, mb.store.flat) and torch.equal(oa.m, ob.m) and torch.equal(oa.v, ob.v)
