@@ -284,6 +284,8 @@ def main():
     par = importlib.import_module(PKG + ".parallel")
     data = importlib.import_module(PKG + ".data")
     L = importlib.import_module(PKG + "._lib")
+    # rank 0 prints ONE JSON line on stdout: NCCL's own messages (version banner, warnings) go to a per-process file
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fs2_bench_nccl_%h_%p.log")
     rank, world, local = par.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
