@@ -240,6 +240,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
 struct EpiT {
   long long tb[4];      // C offsets of rows tr, tr+8, tr+16, tr+24 of this warp's 32 rows (tr = lane / 4)
   unsigned okmask;      // rows that exist and are written
+  unsigned livemask;    // ... and are not masked (t < lens[b])
   bool any_dead;        // some written row is masked (t >= lens[b]): the value path has to select zeros
   bool mirrors;         // some row needs a halo mirror store -> the chunk takes the row-per-thread path
 };
@@ -248,11 +249,46 @@ __device__ __forceinline__ void epi_t_setup(const EpiRow& er, bool row_ok, EpiT&
   const int lane = threadIdx.x & 31;
   const bool mine = row_ok && !er.skip;
   et.okmask = __ballot_sync(0xffffffffu, mine);
-  et.any_dead = __ballot_sync(0xffffffffu, mine && !er.live) != 0u;
+  et.livemask = __ballot_sync(0xffffffffu, mine && er.live);
+  et.any_dead = et.livemask != et.okmask;
   et.mirrors = __ballot_sync(0xffffffffu, row_ok && (er.mirror != 0 || er.mirror2 != 0)) != 0u;
   const long long mybase = mine ? er.base : 0;
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) et.tb[jj] = __shfl_sync(0xffffffffu, mybase, jj * 8 + (lane >> 2));
+}
+
+// fp32 output straight from the 16x256b TMEM register layout (tmem_ld_16x256b_x4, two loads = 32 rows x 32 columns):
+// lane (tr = lane/4, tq = lane%4) holds rows tr, tr+8, tr+16, tr+24 and, per 8-column group n, columns 8n + 2tq + {0,1}.
+// One 8-byte store per (row, group): four lanes fill one 32-byte sector, one instruction covers 8 rows -- the same
+// sector efficiency as the smem-transposed path without its st.shared / ld.shared / __syncwarp chain.
+template <int MODE>
+__device__ __forceinline__ void epi_chunk_q(const Fs2Gemm& g, const EpiT& et, const uint32_t* rlo, const uint32_t* rhi,
+                                            int nb0, long long col0, bool atomic, bool no_stg) {
+  const int lane = threadIdx.x & 31;
+  const int tr = lane >> 2, tq = lane & 3;
+  const unsigned okmask = no_stg ? 0u : et.okmask;
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const int col = 8 * n + 2 * tq;
+    float2 b2 = make_float2(0.f, 0.f);
+    if (g.bias) b2 = __ldg(reinterpret_cast<const float2*>(g.bias + nb0 + col));
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const uint32_t* r = (jj & 2) ? rhi : rlo;
+      float x0 = __uint_as_float(r[4 * n + 2 * (jj & 1)]), x1 = __uint_as_float(r[4 * n + 2 * (jj & 1) + 1]);
+      if (g.alpha != 1.f) { x0 *= g.alpha; x1 *= g.alpha; }
+      x0 += b2.x;
+      x1 += b2.y;
+      if (g.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      const int row = jj * 8 + tr;
+      if (et.any_dead && !((et.livemask >> row) & 1u)) { x0 = 0.f; x1 = 0.f; }
+      if ((okmask >> row) & 1u) {
+        float2* dst = reinterpret_cast<float2*>((float*)g.C + et.tb[jj] + col0 + col);
+        if (atomic) atomicAdd(dst, make_float2(x0, x1));
+        else *dst = make_float2(x0, x1);
+      }
+    }
+  }
 }
 
 template <int MODE>
@@ -420,8 +456,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      uint32_t it = 0;
+      // The issue loops of this thread and of the MMA thread are single-thread instruction streams: every k-block must
+      // cost them fewer cycles than its MMAs take (4 x 48 cycles at BN = 192), so stage / phase / tap counters are
+      // incremental (no division, no modulo) and the tensor-map coordinate permutation is resolved once per kernel.
       bool ok = true;
+      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+      long long w_empty = 0, t_all = prof ? clock64() : 0;
+      const int ars = p.pa[1], ai1 = p.pa[2];        // slot (1..3) of the row coordinate / of i1 in A's tensor map
+      const int brs = p.pb[1], bi1 = p.pb[2];
+      const uint32_t smem0 = smem_u32(smem);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      uint32_t s = 0, ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x) {
         const int nt = t % p.n_tiles_total;
         const int rest = t / p.n_tiles_total;
@@ -433,72 +478,100 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         if (MODE == 2) { tapN = nt / p.ntiles_per_tap; n0 = (nt % p.ntiles_per_tap) * BN; }
         const int kb_begin = zs * p.kb_per_split;
         const int kb_end = min(p.total_kb, kb_begin + p.kb_per_split);
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          if (!mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, err)) { ok = false; break; }
-          const uint32_t fb = smem_u32(&full_bar[s]);
+        // coordinates of the batch dims in their slots; the row slot is patched per load with three selects
+        const int a1 = (ai1 == 1) ? i1 : i2, a2 = (ai1 == 2) ? i1 : i2, a3 = (ai1 == 3) ? i1 : i2;
+        const int b1 = (bi1 == 1) ? i1 : i2, b2 = (bi1 == 2) ? i1 : i2, b3 = (bi1 == 3) ? i1 : i2;
+        int j = (MODE == 2) ? 0 : kb_begin / p.kb_per_tap;            // tap of the current k-block (modes 0/1)
+        int kk = (MODE == 2) ? kb_begin * BK : (kb_begin - j * p.kb_per_tap) * BK;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const long long tq = prof ? clock64() : 0;
+          if (!mbar_wait(empty0 + 8 * s, ph ^ 1, err)) { ok = false; break; }
+          if (prof) w_empty += clock64() - tq;
+          const uint32_t fb = full0 + 8 * s;
           mbar_expect_tx(fb, STAGE_BYTES);
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sa = smem0 + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           if (MODE == 0 || MODE == 1) {
-            const int j = kb / p.kb_per_tap;
-            const int kk = (kb - j * p.kb_per_tap) * BK;
-            tma_issue(sa, &tmA, fb, p.pa, kk, g.a_row_off + m0 + j * g.a_tap_step, i1, i2);
+            const int arow = g.a_row_off + m0 + j * g.a_tap_step;
+            tma_load_4d(sa, &tmA, fb, kk, ars == 1 ? arow : a1, ars == 2 ? arow : a2, ars == 3 ? arow : a3);
             if (MODE == 0) {
-              tma_issue(sb, &tmB, fb, p.pb, j * g.b_tap_step + kk, n0, i1, i2);
+              tma_load_4d(sb, &tmB, fb, j * g.b_tap_step + kk, brs == 1 ? n0 : b1, brs == 2 ? n0 : b2, brs == 3 ? n0 : b3);
             } else {
+              const int brow = g.b_row_off + kk;
 #pragma unroll
               for (int i = 0; i < BN / 64; ++i)
-                tma_issue(sb + i * (BK * 128), &tmB, fb, p.pb, n0 + 64 * i + j * g.b_tap_step, g.b_row_off + kk, i1, i2);
+                tma_load_4d(sb + i * (BK * 128), &tmB, fb, n0 + 64 * i + j * g.b_tap_step, brs == 1 ? brow : b1,
+                            brs == 2 ? brow : b2, brs == 3 ? brow : b3);
             }
+            kk += BK;
+            if (kk >= p.kb_per_tap * BK) { kk = 0; ++j; }
           } else {
-            const int k0 = kb * BK;
+            const int arow = g.a_row_off + kk, brow = g.b_row_off + kk + tapN * g.b_tap_step;
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i)
-              tma_issue(sa + i * (BK * 128), &tmA, fb, p.pa, m0 + 64 * i, g.a_row_off + k0, i1, i2);
+              tma_load_4d(sa + i * (BK * 128), &tmA, fb, m0 + 64 * i, ars == 1 ? arow : a1, ars == 2 ? arow : a2,
+                          ars == 3 ? arow : a3);
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
-              tma_issue(sb + i * (BK * 128), &tmB, fb, p.pb, n0 + 64 * i, g.b_row_off + k0 + tapN * g.b_tap_step, i1, i2);
+              tma_load_4d(sb + i * (BK * 128), &tmB, fb, n0 + 64 * i, brs == 1 ? brow : b1, brs == 2 ? brow : b2,
+                          brs == 3 ? brow : b3);
+            kk += BK;
           }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
+      if (prof) { p.dbg[2] = clock64() - t_all; p.dbg[3] = w_empty; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      uint32_t it = 0, tc = 0;
+      uint32_t tc = 0;
       bool ok = true;
+      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+      long long w_acc = 0, w_full = 0, t_all = prof ? clock64() : 0;
+      // shared-memory descriptors: everything but the 14-bit start-address field is constant, and that field only ever
+      // moves by (bytes >> 4) -- one descriptor per operand for stage 0, then plain 64-bit adds
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t adesc0 = A_MN ? smem_desc(smem0, BK * 128, 1024) : smem_desc(smem0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? smem_desc(smem0 + A_BYTES, BK * 128, 1024) : smem_desc(smem0 + A_BYTES, 16, 1024);
+      constexpr uint64_t A_STEP = A_MN ? (2048 >> 4) : (32 >> 4);      // one K = 16 step inside the stage
+      constexpr uint64_t B_STEP = B_MN ? (2048 >> 4) : (32 >> 4);
+      constexpr uint64_t STAGE_STEP = STAGE_BYTES >> 4;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      uint32_t s = 0, ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x, ++tc) {
         const int z = (t / p.n_tiles_total) / p.m_tiles;
         const int zs = z % p.nsplit;
         const int kb_begin = zs * p.kb_per_split;
         const int nkb = min(p.total_kb, kb_begin + p.kb_per_split) - kb_begin;
         const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+        const long long tq0 = prof ? clock64() : 0;
         if (!mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1, err)) { ok = false; break; }
+        if (prof) w_acc += clock64() - tq0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int i = 0; i < nkb; ++i, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          if (!mbar_wait(smem_u32(&full_bar[s]), ph, err)) { ok = false; break; }
+        uint32_t acc = 0;
+        for (int i = 0; i < nkb; ++i) {
+          const long long tq1 = prof ? clock64() : 0;
+          if (!mbar_wait(full0 + 8 * s, ph, err)) { ok = false; break; }
+          if (prof) w_full += clock64() - tq1;
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const uint64_t ad = adesc0 + (uint64_t)s * STAGE_STEP, bd = bdesc0 + (uint64_t)s * STAGE_STEP;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // K-major: 16 elements = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
             // MN-major: 16 k-rows = 2 groups of 8 rows (1024 B each); 64-wide MN blocks 8192 B apart.
-            const uint64_t ad = A_MN ? smem_desc(sa + k * 2048, BK * 128, 1024) : smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t bd = B_MN ? smem_desc(sb + k * 2048, BK * 128, 1024) : smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(tmem_d, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, ad + k * A_STEP, bd + k * B_STEP, idesc, acc);
+            acc = 1;
           }
-          umma_commit(smem_u32(&empty_bar[s]));
+          umma_commit(empty0 + 8 * s);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         if (ok) umma_commit(smem_u32(&tfull_bar[as]));
       }
+      if (prof) { p.dbg[4] = clock64() - t_all; p.dbg[5] = w_acc; p.dbg[6] = w_full; p.dbg[7] = tc; }
     }
   } else {
     // ---------------- epilogue: 8 warps; TMEM lane quadrant = warp % 4, column half = (warp-2)/4 ----------------
@@ -512,6 +585,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     const bool aux_al = g.relu_aux == nullptr || (((uintptr_t)g.relu_aux) % 16 == 0);
     uint32_t tc = 0;
     bool ok = true;
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
+    long long w_tfull = 0, t_chunks = 0, t_ld = 0, t_all = prof ? clock64() : 0;
     for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x, ++tc) {
       const int nt = t % p.n_tiles_total;
       const int rest = t / p.n_tiles_total;
@@ -539,20 +614,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         epi_t_setup(er, row_ok, et);
         t_path = !et.mirrors;
       }
+      // experiment switch FS2_TC_EPIT=3: fp32 outputs skip the smem transpose (direct 8-byte stores from the 16x256b TMEM
+      // layout).  Measured equal-to-slower than the transpose (profiles/r01_summary.md section 3: in steady state these
+      // GEMMs are bound by the HBM traffic of their fp32 output, not by the store instruction pattern), so it is off.
+      const bool q_path = t_path && p.epi_transpose == 3 && (vec_f32_at || (vec_f32 && g.relu_aux == nullptr)) &&
+                          (g.bias == nullptr || (((uintptr_t)g.bias) % 8 == 0));
+      const long long tq2 = prof ? clock64() : 0;
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, err)) { ok = false; break; }
+      const long long tq3 = prof ? clock64() : 0;
+      if (prof) w_tfull += tq3 - tq2;
       tc_fence_after();
 #pragma unroll 1
       for (int ci = 0; ci < CHUNKS_PER_HALF; ++ci) {
         const int c = half * CHUNKS_PER_HALF + ci;
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+        const int nb0 = n0 + c * 32;
+        const bool q_use = q_path && nb0 + 32 <= g.N && p.dbg_mode != 3;
+        const long long tq4 = prof ? clock64() : 0;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32);
+        if (q_use) {
+          tmem_ld_16x256b_x4(taddr, r);
+          tmem_ld_16x256b_x4(taddr + (16u << 16), r + 16);
+          tmem_wait_ld();
+        } else {
+          tmem_ld32(taddr, r);
+        }
+        if (prof) t_ld += clock64() - tq4;
         if (ci == CHUNKS_PER_HALF - 1) {
           // all of this warp's TMEM reads are complete: hand the accumulator buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
         }
-        const int nb0 = n0 + c * 32;
+        if (q_use) {
+          epi_chunk_q<MODE>(g, et, r, r + 16, nb0, colbase + (long long)c * 32, atomic, p.dbg_mode == 4);
+          continue;
+        }
         if (nb0 >= g.N || p.dbg_mode == 3) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
         if (t_path && nb0 + 32 <= g.N) {
           epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4, atomic);
@@ -561,7 +658,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         if (!row_ok || er.skip) continue;
         epi_chunk<MODE>(g, er, r, nb0, colbase + (long long)c * 32 * cstr, cstr, atomic, vec_f32, vec_bf16);
       }
+      if (prof) t_chunks += clock64() - tq3;
     }
+    if (prof && lane == 0) { p.dbg[8] = clock64() - t_all; p.dbg[9] = w_tfull; p.dbg[10] = t_chunks; p.dbg[11] = t_ld; }
   }
 
   tc_fence_before();
@@ -793,13 +892,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
         epi_t_setup(er, row_ok, et);
         t_path = !et.mirrors;
       }
+      // experiment switch FS2_TC_EPIT=3: fp32 outputs skip the smem transpose (direct 8-byte stores from the 16x256b TMEM
+      // layout).  Measured equal-to-slower than the transpose (profiles/r01_summary.md section 3: in steady state these
+      // GEMMs are bound by the HBM traffic of their fp32 output, not by the store instruction pattern), so it is off.
+      const bool q_path = t_path && p.epi_transpose == 3 && (vec_f32_at || (vec_f32 && g.relu_aux == nullptr)) &&
+                          (g.bias == nullptr || (((uintptr_t)g.bias) % 8 == 0));
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, err)) { ok = false; break; }
       tc_fence_after();
 #pragma unroll 1
       for (int ci = 0; ci < CHUNKS_PER_HALF; ++ci) {
         const int c = half * CHUNKS_PER_HALF + ci;
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TILE_N + c * 32), r);
+        const int nb0 = n0 + c * 32;
+        const bool q_use = q_path && nb0 + 32 <= g.N && p.dbg_mode != 3;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TILE_N + c * 32);
+        if (q_use) {
+          tmem_ld_16x256b_x4(taddr, r);
+          tmem_ld_16x256b_x4(taddr + (16u << 16), r + 16);
+          tmem_wait_ld();
+        } else {
+          tmem_ld32(taddr, r);
+        }
         if (ci == CHUNKS_PER_HALF - 1) {
           // this warp's TMEM reads are done: hand the accumulator buffer back to the (leader's) MMA thread
           tc_fence_before();
@@ -810,7 +923,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
             else mbar_arrive(tb);
           }
         }
-        const int nb0 = n0 + c * 32;
+        if (q_use) {
+          epi_chunk_q<MODE>(g, et, r, r + 16, nb0, colbase + (long long)c * 32, atomic, p.dbg_mode == 4);
+          continue;
+        }
         if (nb0 >= g.N || p.dbg_mode == 3) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
         if (t_path && nb0 + 32 <= g.N) {
           epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4, atomic);
@@ -1171,7 +1287,7 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
     const char* c = getenv("FS2_TC_CFG");
     g_force_cfg = c ? atoi(c) : -1;
     const char* t = getenv("FS2_TC_EPIT");
-    if (t) g_epi_transpose = atoi(t) != 0;
+    if (t) g_epi_transpose = atoi(t);          // 0 off, 1 default (smem-transposed stores), 3 direct quad-layout stores for fp32 outputs (experiment)
   }
   p.epi_transpose = g_epi_transpose;
   const bool pair_ok = g.batch1 * g.batch2 == 1 && g.M > BM;

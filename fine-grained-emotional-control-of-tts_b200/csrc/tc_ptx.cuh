@@ -102,6 +102,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 
 
 
+// 16 TMEM lanes x 32 columns in the "16x256b" register layout (no wait): lane l of the warp receives, for column group
+// n = 0..3, r[4n + 0..1] = row l/4, columns 8n + 2(l%4) + {0,1} and r[4n + 2..3] = row l/4 + 8, same columns
+// (cute Copy_Traits<SM100_TMEM_LOAD_16dp256b4x>::DstLayout).  Four lanes hold 32 contiguous bytes of a row, so the
+// registers can go to global memory directly with full-sector stores -- no shared-memory transpose.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "

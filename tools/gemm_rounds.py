@@ -66,3 +66,25 @@ for graph in (True,):
     run("conv1 1536->384 fp32 out", 384, 1536, False, 192, graph)
     run("ffn-in 384->1536 bf16 out (k=1)", 1536, 384, True, 256, graph)
 print("flag", L.gemm_tc_error_flag())
+
+# ---- role probe of CTA 0 (single-CTA kernel): who waits on whom
+if os.environ.get("GEMM_PROBE"):
+    dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+    L.gemm_tc_set_debug(dbg)
+    bf = torch.bfloat16
+    for name, N, K, c_bf16, bn in (("out_proj 384->384 fp32", 384, 384, False, 192), ("qkv 384->1152 bf16", 1152, 384, True, 192),
+                                   ("conv1 1536->384 fp32", 384, 1536, False, 192)):
+        r = 8
+        M = 128 * (148 * r // ((N + bn - 1) // bn))
+        w = (torch.randn(N, K, device="cuda") * 0.05).to(bf)
+        x = torch.randn(M, K, device="cuda").to(bf)
+        o = torch.empty(M, N, device="cuda", dtype=bf if c_bf16 else torch.float32)
+        for _ in range(3):
+            L.gemm(mode=0, M=M, N=N, K=K, A=x, lda=K, a_rows=M, a_inner=K, B=w, ldb=K, b_rows=N, b_inner=K, Cout=o, ldc=N,
+                   c_bf16=c_bf16, ab_bf16=True)
+        torch.cuda.synchronize()
+        d = dbg.tolist()
+        print(f"{name}: tiles/CTA {d[7]} | TMA thread total {d[2]} cyc, waiting for a free stage {d[3]} | MMA thread total {d[4]}, "
+              f"waiting for accumulator {d[5]}, for operands {d[6]} | epilogue warp total {d[8]}, waiting for MMA {d[9]}, "
+              f"in chunk loop {d[10]} (of which tcgen05.ld + wait {d[11]})")
+    L.gemm_tc_set_debug(None)
