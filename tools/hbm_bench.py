@@ -64,6 +64,16 @@ def main():
         out.append(r)
         print(json.dumps(r), flush=True)
 
+    # ------------------------------------------------- reference point: a plain device copy of the same byte count
+    # (the measured HBM peak comes from a 2 GiB copy; a 91 MB launch pays its ramp and tail inside the timed window)
+    n_ref = 45_629_440 // 4
+    src_c = [torch.randn(n_ref, device=dev) for _ in range(6)]
+    dst_c = [torch.empty(n_ref, device=dev) for _ in range(6)]
+    us = timeit(lambda i: dst_c[i].copy_(src_c[i]), 6)
+    report("torch copy_ of 45.6 MB (91.3 MB read+write): same bytes as lr_expand", 2 * n_ref * 4, us,
+           "what a small launch can reach at all; compare the LengthRegulator rows against this, not only against the 2 GiB peak")
+    del src_c, dst_c
+
     # ------------------------------------------------------------- cfg-2: LengthRegulator, B=64, Tp=128, D=384
     B, Tp, D = 64, 128, 384
     dur = torch.exp(torch.randn(B, Tp, generator=g) * 0.6 + 1.6).round().clamp(0, 40).long()
