@@ -36,6 +36,9 @@ SIGNATURES = {
     "fs2_embed_add": "ppppipiiippiip",
     "fs2_embed_add_bwd": "ppiiiippp",
     "fs2_attn_fwd": "ppiiiiiffQppppp",
+    "fs2_attn_fwd_ex": "ppiiiiiffQppppip",
+    "fs2_frames_to_rows": "piiiiipip",
+    "fs2_intensity_head": "ppppppiiiipp",
     "fs2_attn_bwd": "pppppiiiiiffQpppp",
     "fs2_dur_decode": "pqpp",
     "fs2_lr_prepare": "ppfiippp",

@@ -53,11 +53,13 @@ struct AttnParams {
   const bf16* dO;              // bwd
   int* err;
   long long* dbg;              // optional cycle breakdown of CTA 0 (measurements only)
+  int plain_mask;              // 0: FastSpeech2's attn_mask quirk, 1: plain key-padding mask
 };
 
-__device__ __forceinline__ int attn_kv(const int* lens, int B, int H, int bh) {
-  // quirk Q1: keys valid for (b,h) are [0, min(len[b], len[(b*H+h) % B]))
-  return min(lens[bh / H], lens[bh % B]);
+__device__ __forceinline__ int attn_kv(const int* lens, int B, int H, int bh, int plain) {
+  // FastSpeech2 (quirk Q1): keys valid for (b,h) are [0, min(len[b], len[(b*H+h) % B]));
+  // plain = 1: ordinary key-padding mask, keys [0, len[b])  (rank_model/model.py:34, 103)
+  return plain ? lens[bh / H] : min(lens[bh / H], lens[bh % B]);
 }
 
 __device__ __forceinline__ float ex2f_(float x) {
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(att_threads(NCH), 1) attn_kernel(const __grid_
   const int qb = blockIdx.x % nqb;
   const int bh = blockIdx.x / nqb;
   const int b = bh / p.H, h = bh % p.H;
-  const int kv = attn_kv(p.lens, p.B, p.H, bh);
+  const int kv = attn_kv(p.lens, p.B, p.H, bh, p.plain_mask);
   const int nkb = (kv + AK - 1) / AK;
   const int njobs = BWD ? nkb : 2 * nkb;          // fwd: a statistics pass, then the P / PV pass
   const int first_main = BWD ? 0 : nkb;
@@ -523,6 +525,12 @@ extern "C" int fs2_attn_set_debug(long long* dev_buf) {
 extern "C" int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int T, int D, int ldk, float scale, float drop_p,
                             unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd, void* O,
                             void* stream) {
+  return fs2_attn_fwd_ex(qkv, lens, B, H, T, D, ldk, scale, drop_p, seed, seed_dev, P, Pd, O, 0, stream);
+}
+
+extern "C" int fs2_attn_fwd_ex(const void* qkv, const int* lens, int B, int H, int T, int D, int ldk, float scale,
+                               float drop_p, unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd,
+                               void* O, int plain_mask, void* stream) {
   AttnParams p;
   CUtensorMap tq, tkv;
   int rc = attn_common(qkv, lens, B, H, T, D, ldk, p, &tkv);
@@ -539,6 +547,7 @@ extern "C" int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int 
   p.Pd = drop_p > 0.f ? (bf16*)Pd : nullptr;
   p.out = (bf16*)O;
   p.out_ld = D;
+  p.plain_mask = plain_mask;
   return launch_attn<false, 2>(tq, tkv, p, (cudaStream_t)stream);
 }
 

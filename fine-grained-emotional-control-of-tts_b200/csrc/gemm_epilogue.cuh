@@ -3,6 +3,13 @@
 #include "common.cuh"
 #include "../../include/fs2_b200.h"
 
+// Fs2Gemm.relu: 0 = none, 1 = ReLU, 2 = GELU (exact erf form, torch nn.GELU() default -- rank_model/model.py:31)
+__device__ __forceinline__ float epi_act(float v, int kind) {
+  if (kind == 1) return fmaxf(v, 0.f);
+  if (kind == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  return v;
+}
+
 struct EpiRow {
   long long base;      // element offset of (row, c_col_off) in C
   long long mirror;    // element offset delta of the reflect-halo mirror row at the item's start (0 = none)
@@ -38,7 +45,7 @@ __device__ __forceinline__ void epi_row_setup(const Fs2Gemm& g, int i1, int i2, 
 __device__ __forceinline__ float epi_value(const Fs2Gemm& g, const EpiRow& er, long long col, int nb, float acc) {
   float v = acc * g.alpha;
   if (g.bias) v += g.bias[nb];
-  if (g.relu) v = fmaxf(v, 0.f);
+  if (g.relu) v = epi_act(v, g.relu);
   if (g.relu_aux) {
     float a = g.aux_bf16 ? __bfloat162float(((const bf16*)g.relu_aux)[er.base + col])
                          : ((const float*)g.relu_aux)[er.base + col];

@@ -141,7 +141,7 @@ __device__ __forceinline__ void epi_chunk(const Fs2Gemm& g, const EpiRow& er, co
     for (int i = 0; i < 32; ++i) {
       float x = __uint_as_float(r[i]) * g.alpha;
       if (g.bias) x += g.bias[nb0 + i];
-      if (g.relu) x = fmaxf(x, 0.f);
+      if (g.relu) x = epi_act(x, g.relu);
       v[i] = er.live ? x : 0.f;
     }
     if (g.relu_aux) {
@@ -279,7 +279,7 @@ __device__ __forceinline__ void epi_chunk_q(const Fs2Gemm& g, const EpiT& et, co
       if (g.alpha != 1.f) { x0 *= g.alpha; x1 *= g.alpha; }
       x0 += b2.x;
       x1 += b2.y;
-      if (g.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      if (g.relu) { x0 = epi_act(x0, g.relu); x1 = epi_act(x1, g.relu); }
       const int row = jj * 8 + tr;
       if (et.any_dead && !((et.livemask >> row) & 1u)) { x0 = 0.f; x1 = 0.f; }
       if ((okmask >> row) & 1u) {
@@ -319,9 +319,12 @@ __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, 
       for (int i = 0; i < 32; ++i) v[i] += g.bias[nb0 + i];
     }
   }
-  if (g.relu) {
+  if (g.relu == 1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (g.relu == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = epi_act(v[i], 2);
   }
   if (et.any_dead) {
     const bool live = row_ok && !er.skip && er.live;

@@ -1173,6 +1173,58 @@ __global__ void intensity_segment_mean_kernel(const float* I, const int64_t* dur
 
 }  // namespace
 
+// ------------------------------------------------------------ intensity extractor glue --
+template <typename TA>
+__global__ void __launch_bounds__(THREADS) frames_to_rows_kernel(const float* __restrict__ x, int channels_first, int B,
+                                                                 int C, int T, int Cpad, TA* __restrict__ out) {
+  pdl_wait();
+  const int TP = T + 2 * FS2_PAD;
+  const long long n = (long long)B * TP * Cpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const long long r = i / Cpad;
+    const int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
+    float v = 0.f;
+    if (t >= 0 && t < T && c < C)
+      v = channels_first ? x[((long long)b * C + c) * T + t] : x[((long long)b * T + t) * C + c];
+    ActT<TA>::st(out + i, v);
+  }
+}
+
+// one warp per (b, t): n_out (<= 8) dot products over D of the masked, emotion-shifted hidden row
+__global__ void __launch_bounds__(THREADS) intensity_head_kernel(const float* __restrict__ h, const float* __restrict__ emb,
+                                                                 const int64_t* __restrict__ emotions,
+                                                                 const int* __restrict__ lens, const float* __restrict__ Wc,
+                                                                 const float* __restrict__ bc, int B, int T, int D,
+                                                                 int n_out, float* __restrict__ out) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int TP = T + 2 * FS2_PAD;
+  const long long rows = (long long)B * T;
+  for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
+    const int b = (int)(r / T), t = (int)(r - (long long)b * T);
+    const bool live = t < lens[b];
+    const float* hr = h + ((long long)b * TP + FS2_PAD + t) * D;
+    const float* er = emb + emotions[b] * D;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      for (int c = lane; c < D; c += 32) {
+        const float v = hr[c] + er[c];
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          if (o < n_out) acc[o] += v * Wc[(long long)o * D + c];
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      if (o < n_out) {
+        const float s = warp_sum(acc[o]);
+        if (lane == 0) out[r * n_out + o] = s + bc[o];
+      }
+    }
+  }
+}
+
 #define ST ((cudaStream_t)stream)
 #define REQUIRE(cond, msg) do { if (!(cond)) { fs2_set_error(msg); return FS2_ERR_ARG; } } while (0)
 
@@ -1439,5 +1491,24 @@ extern "C" int fs2_intensity_segment_mean(const float* I, const int64_t* dur, co
                                           int Tm, int D, float* out, void* stream) {
   REQUIRE(I && dur && phon_len && out, "fs2_intensity_segment_mean: null pointer");
   FS2_LAUNCH((intensity_segment_mean_kernel), B, 256, (size_t)Tp * 4, ST, I, dur, phon_len, B, Tp, Tm, D, out);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_frames_to_rows(const float* x, int channels_first, int B, int C, int T, int Cpad, void* out_act,
+                                  int act_bf16, void* stream) {
+  REQUIRE(x && out_act && B > 0 && C > 0 && T > 0 && Cpad >= C, "fs2_frames_to_rows: bad arguments");
+  const long long n = (long long)B * (T + 2 * FS2_PAD) * Cpad;
+  const int grid = (int)((n + THREADS - 1) / THREADS < 148 * 16 ? (n + THREADS - 1) / THREADS : 148 * 16);
+  if (act_bf16) FS2_LAUNCH((frames_to_rows_kernel<bf16>), grid, THREADS, 0, ST, x, channels_first, B, C, T, Cpad, (bf16*)out_act);
+  else FS2_LAUNCH((frames_to_rows_kernel<float>), grid, THREADS, 0, ST, x, channels_first, B, C, T, Cpad, (float*)out_act);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_intensity_head(const float* h, const float* emb, const int64_t* emotions, const int* lens,
+                                  const float* Wc, const float* bc, int B, int T, int D, int n_out, float* out,
+                                  void* stream) {
+  REQUIRE(h && emb && emotions && lens && Wc && bc && out && n_out >= 1 && n_out <= 8, "fs2_intensity_head: bad arguments");
+  FS2_LAUNCH((intensity_head_kernel), grid_for_rows((long long)B * T), THREADS, 0, ST, h, emb, emotions, lens, Wc, bc, B, T, D,
+             n_out, out);
   return fs2_check_launch();
 }

@@ -144,6 +144,11 @@ int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int T, int D, i
                  unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd, void* O, void* stream);
 /* Backward companion: dPd = dO.V^T (TMEM) -> dS = scale*P*(dPd*keep - rowsum(dO*O)) -> dS (B*H, T, ldk) bf16 and
  * dQ = dS.K written into columns [0, D) of dqkv (B*(T+8), 3D).  dK = dS^T Q and dV = Pd^T dO stay batched GEMMs. */
+/* same, with the mask selectable: plain_mask = 1 is an ordinary key-padding mask (keys [0, lens[b]) for every head),
+ * as nn.MultiheadAttention(key_padding_mask=...) in the intensity extractor (rank_model/model.py:34, 103) */
+int fs2_attn_fwd_ex(const void* qkv, const int* lens, int B, int H, int T, int D, int ldk, float scale, float drop_p,
+                    unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd, void* O,
+                    int plain_mask, void* stream);
 int fs2_attn_bwd(const void* dO, const void* O, const void* qkv, const void* P, const int* lens, int B, int H, int T,
                  int D, int ldk, float scale, float drop_p, unsigned long long seed,
                  const unsigned long long* seed_dev, void* dS, void* dqkv, void* stream);
@@ -237,6 +242,16 @@ int fs2_ssim_loss(const float* mel_out, const float* mel_tgt, const int64_t* mel
 /* train.py:81 AdamW (torch defaults: decoupled weight decay, bias correction) over one flat buffer */
 int fs2_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
               float beta2, float eps, float wd, int step, float grad_scale, void* stream);
+
+/* Intensity extractor glue (rank_model/model.py:56-109).
+ * fs2_frames_to_rows: frame features -> padded row space [B*(T+8), Cpad] in operand storage, columns >= C and the
+ *   halo rows zero.  channels_first = 1: x is (B, C, T) (the collate's rank_X, dataset.py:106-110); 0: (B, T, C).
+ * fs2_intensity_head: I[b,t,:] = Wc . mask(h[b,t,:] + emb[emotions[b],:]) + bc with mask = (t < lens[b])
+ *   (model.py:104-107); h is the fp32 padded-row output of the last FFT block. */
+int fs2_frames_to_rows(const float* x, int channels_first, int B, int C, int T, int Cpad, void* out_act, int act_bf16,
+                       void* stream);
+int fs2_intensity_head(const float* h, const float* emb, const int64_t* emotions, const int* lens, const float* Wc,
+                       const float* bc, int B, int T, int D, int n_out, float* out /*(B,T,n_out)*/, void* stream);
 
 /* train.py:16-51 duration-segment mean of frame intensities ("next" row f-1) */
 int fs2_intensity_segment_mean(const float* I /*(B,Tm,D)*/, const int64_t* dur, const int64_t* phon_len,
