@@ -5,6 +5,7 @@ from .loss import Loss  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 from .intensity import get_intensity_representation, intensity_segment_mean  # noqa: F401
 from .rank_model import IntensityExtractor  # noqa: F401
+from .collate import DeviceCollate  # noqa: F401
 
 DEFAULT_MODEL_CONFIG = dict(
     enc_num_layers=6, enc_num_head=2, enc_d_model=384, enc_ffn_dim=1536, enc_k_dim=384, enc_v_dim=384,

@@ -1,0 +1,80 @@
+"""Device-side collate: drop-in for `TextMelCollateWithAlignment` (`/root/reference/emo_rank_tts/fastspeech2/dataset.py:60-133`,
+SURVEY 8f row 3).  Same call (`collate(list_of_samples)`), same 12-tuple, but the tensors come back ON THE DEVICE.
+
+The reference pads on the host with 5 slice copies per utterance and then ships the padded rectangle (plus `rank_X`, a
+second copy of mel / pitch / energy) over PCIe.  Here the ragged arrays are concatenated into one pinned staging buffer,
+cross PCIe once (no padding, no duplicate), and ONE kernel (`fs2_collate`) writes every padded tensor -- including the
+(B, Tm, 80) transposed mel and the channels-first `rank_X` -- with zero padding.  The host only sorts B lengths."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+class DeviceCollate:
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+        self._pin = None
+
+    def _staging(self, nbytes):
+        if self._pin is None or self._pin.numel() < nbytes:
+            self._pin = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        return self._pin
+
+    def __call__(self, batch):
+        if self.device.type != "cuda":
+            raise RuntimeError("fs2_b200: DeviceCollate needs a CUDA device (there is no CPU fallback)")
+        B = len(batch)
+        # dataset.py:65-67: sort by descending phoneme count (torch.sort on a LongTensor, as the reference)
+        input_lengths, order = torch.sort(torch.LongTensor([len(x["phoneme"]) for x in batch]), dim=0, descending=True)
+        order = order.tolist()
+        Tp = int(input_lengths[0])
+        n_mels = int(batch[0]["mel"].size(0))
+        fr_len = [int(batch[j]["mel"].size(1)) for j in order]
+        ph_len = [int(len(batch[j]["phoneme"])) for j in order]
+        Tm = max(fr_len)
+        n_ph, n_fr = sum(ph_len), sum(fr_len)
+        # one pinned staging buffer: [phoneme i64 | duration i64 | mel f32 | pitch f32 | energy f32 | 4 x descriptors i32]
+        o_ph, o_du = 0, 8 * n_ph
+        o_mel = 16 * n_ph
+        o_pi = o_mel + 4 * n_fr * n_mels
+        o_en = o_pi + 4 * n_fr
+        o_desc = o_en + 4 * n_fr
+        total = o_desc + 16 * B
+        pin = self._staging(total)
+        ph_v = pin[o_ph:o_du].view(torch.int64)
+        du_v = pin[o_du:o_mel].view(torch.int64)
+        mel_v = pin[o_mel:o_pi].view(torch.float32)
+        pi_v = pin[o_pi:o_en].view(torch.float32)
+        en_v = pin[o_en:o_desc].view(torch.float32)
+        desc = pin[o_desc:total].view(torch.int32).view(4, B)
+        p0 = f0 = 0
+        for i, j in enumerate(order):
+            x = batch[j]
+            np_, nf = ph_len[i], fr_len[i]
+            ph_v[p0:p0 + np_] = x["phoneme"]
+            du_v[p0:p0 + np_] = x["duration"]
+            mel_v[f0 * n_mels:(f0 + nf) * n_mels] = x["mel"].reshape(-1)          # (n_mels, nf) row-major
+            pi_v[f0:f0 + nf] = x["pitch"]
+            en_v[f0:f0 + nf] = x["energy"]
+            desc[0, i], desc[1, i], desc[2, i], desc[3, i] = p0, np_, f0, nf
+            p0 += np_
+            f0 += nf
+        dev = self.device
+        stage = pin[:total].to(dev, non_blocking=True)                             # the batch's ONLY host->device copy
+        base = stage.data_ptr()
+        mk = lambda *s, dt=torch.float32: torch.empty(*s, device=dev, dtype=dt)
+        phoneme, duration = mk(B, Tp, dt=torch.int64), mk(B, Tp, dt=torch.int64)
+        mel, pitch, energy, rank_X = mk(B, Tm, n_mels), mk(B, Tm), mk(B, Tm), mk(B, n_mels + 2, Tm)
+        lib = L.load()
+        rc = lib.fs2_collate(base + o_ph, base + o_du, base + o_mel, base + o_pi, base + o_en, base + o_desc,
+                             base + o_desc + 4 * B, base + o_desc + 8 * B, base + o_desc + 12 * B, B, Tp, Tm, n_mels,
+                             phoneme.data_ptr(), duration.data_ptr(), mel.data_ptr(), pitch.data_ptr(), energy.data_ptr(),
+                             rank_X.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        L.check(rc, "fs2_collate")
+        stage.record_stream(torch.cuda.current_stream())
+        to_dev = lambda v: torch.tensor(v, dtype=torch.long).to(dev, non_blocking=True)
+        return (phoneme, to_dev([int(batch[j]["speaker"]) for j in order]), input_lengths.to(dev, non_blocking=True), mel,
+                pitch, energy, duration, to_dev(fr_len), [batch[j]["text"] for j in order],
+                [batch[j]["audio_path"] for j in order], rank_X, to_dev([int(batch[j]["emotion"]) for j in order]))

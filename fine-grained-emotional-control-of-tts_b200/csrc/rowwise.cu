@@ -1225,6 +1225,60 @@ __global__ void __launch_bounds__(THREADS) intensity_head_kernel(const float* __
   }
 }
 
+// ---------------------------------------------------------------------- device collate --
+constexpr int COL_T = 32;      // frames per CTA
+// grid (ceil(Tm / 32) + 1, B): x < ceil(Tm/32) handles a 32-frame slab of utterance row i (all n_mels + 2 channels go
+// through shared memory so that the channels-first reads, the channels-first rank_X writes and the frames-first mel
+// writes are all coalesced); the last x handles the phoneme / duration row.
+__global__ void __launch_bounds__(256) collate_kernel(const int64_t* __restrict__ phon_cat, const int64_t* __restrict__ dur_cat,
+                                                      const float* __restrict__ mel_cat, const float* __restrict__ pitch_cat,
+                                                      const float* __restrict__ energy_cat, const int* __restrict__ ph_start,
+                                                      const int* __restrict__ ph_len, const int* __restrict__ fr_start,
+                                                      const int* __restrict__ fr_len, int B, int Tp, int Tm, int n_mels,
+                                                      int64_t* __restrict__ phoneme, int64_t* __restrict__ duration,
+                                                      float* __restrict__ mel, float* __restrict__ pitch,
+                                                      float* __restrict__ energy, float* __restrict__ rank_X) {
+  pdl_wait();
+  extern __shared__ float tile[];                 // [(n_mels + 2)][COL_T + 1]
+  const int i = blockIdx.y;
+  const int nslab = (Tm + COL_T - 1) / COL_T;
+  if ((int)blockIdx.x == nslab) {
+    const int n = ph_len[i];
+    const long long s0 = ph_start[i];
+    for (int p = threadIdx.x; p < Tp; p += blockDim.x) {
+      phoneme[(long long)i * Tp + p] = p < n ? phon_cat[s0 + p] : 0;
+      duration[(long long)i * Tp + p] = p < n ? dur_cat[s0 + p] : 0;
+    }
+    return;
+  }
+  const int C = n_mels + 2;
+  const int t0 = blockIdx.x * COL_T;
+  const int L = fr_len[i];
+  const long long f0 = fr_start[i];
+  for (int e = threadIdx.x; e < C * COL_T; e += blockDim.x) {
+    const int c = e / COL_T, tt = e - c * COL_T;
+    const int t = t0 + tt;
+    float v = 0.f;
+    if (t < L) {
+      if (c < n_mels) v = mel_cat[f0 * n_mels + (long long)c * L + t];
+      else if (c == n_mels) v = pitch_cat[f0 + t];
+      else v = energy_cat[f0 + t];
+    }
+    tile[c * (COL_T + 1) + tt] = v;
+    if (t < Tm) {
+      rank_X[((long long)i * C + c) * Tm + t] = v;
+      if (c == n_mels) pitch[(long long)i * Tm + t] = v;
+      if (c == n_mels + 1) energy[(long long)i * Tm + t] = v;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < COL_T * n_mels; e += blockDim.x) {
+    const int tt = e / n_mels, c = e - tt * n_mels;
+    const int t = t0 + tt;
+    if (t < Tm) mel[((long long)i * Tm + t) * n_mels + c] = tile[c * (COL_T + 1) + tt];
+  }
+}
+
 #define ST ((cudaStream_t)stream)
 #define REQUIRE(cond, msg) do { if (!(cond)) { fs2_set_error(msg); return FS2_ERR_ARG; } } while (0)
 
@@ -1510,5 +1564,20 @@ extern "C" int fs2_intensity_head(const float* h, const float* emb, const int64_
   REQUIRE(h && emb && emotions && lens && Wc && bc && out && n_out >= 1 && n_out <= 8, "fs2_intensity_head: bad arguments");
   FS2_LAUNCH((intensity_head_kernel), grid_for_rows((long long)B * T), THREADS, 0, ST, h, emb, emotions, lens, Wc, bc, B, T, D,
              n_out, out);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_collate(const int64_t* phon_cat, const int64_t* dur_cat, const float* mel_cat, const float* pitch_cat,
+                           const float* energy_cat, const int* ph_start, const int* ph_len, const int* fr_start,
+                           const int* fr_len, int B, int Tp, int Tm, int n_mels, int64_t* phoneme, int64_t* duration,
+                           float* mel, float* pitch, float* energy, float* rank_X, void* stream) {
+  REQUIRE(phon_cat && dur_cat && mel_cat && pitch_cat && energy_cat && ph_start && ph_len && fr_start && fr_len && phoneme &&
+              duration && mel && pitch && energy && rank_X,
+          "fs2_collate: null pointer");
+  REQUIRE(B > 0 && B <= 65535 && Tp > 0 && Tm > 0 && n_mels > 0 && n_mels <= 254, "fs2_collate: bad sizes");
+  const dim3 grid((Tm + COL_T - 1) / COL_T + 1, B);
+  const size_t sm = (size_t)(n_mels + 2) * (COL_T + 1) * sizeof(float);
+  FS2_LAUNCH((collate_kernel), grid, 256, sm, ST, phon_cat, dur_cat, mel_cat, pitch_cat, energy_cat, ph_start, ph_len, fr_start,
+             fr_len, B, Tp, Tm, n_mels, phoneme, duration, mel, pitch, energy, rank_X);
   return fs2_check_launch();
 }

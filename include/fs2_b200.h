@@ -253,6 +253,17 @@ int fs2_frames_to_rows(const float* x, int channels_first, int B, int C, int T, 
 int fs2_intensity_head(const float* h, const float* emb, const int64_t* emotions, const int* lens, const float* Wc,
                        const float* bc, int B, int T, int D, int n_out, float* out /*(B,T,n_out)*/, void* stream);
 
+/* Device-side collate (fastspeech2/dataset.py:60-133): the ragged per-utterance arrays arrive in ONE
+ * staging buffer (one host->device copy); this call writes every padded batch tensor, zero padding included.
+ * Output row i takes utterance i of the (already sorted) descriptor arrays: ph_start/ph_len index phon_cat / dur_cat,
+ * fr_start/fr_len index pitch_cat / energy_cat and, times n_mels, mel_cat whose utterance block is (n_mels, fr_len)
+ * row-major (the dataset's mel layout).  Outputs: phoneme, duration (B,Tp) i64; mel (B,Tm,n_mels); pitch, energy
+ * (B,Tm); rank_X (B,n_mels+2,Tm) = [mel; pitch; energy] channels-first (dataset.py:116-117). */
+int fs2_collate(const int64_t* phon_cat, const int64_t* dur_cat, const float* mel_cat, const float* pitch_cat,
+                const float* energy_cat, const int* ph_start, const int* ph_len, const int* fr_start, const int* fr_len,
+                int B, int Tp, int Tm, int n_mels, int64_t* phoneme, int64_t* duration, float* mel, float* pitch,
+                float* energy, float* rank_X, void* stream);
+
 /* train.py:16-51 duration-segment mean of frame intensities ("next" row f-1) */
 int fs2_intensity_segment_mean(const float* I /*(B,Tm,D)*/, const int64_t* dur, const int64_t* phon_len,
                                int B, int Tp, int Tm, int D, float* out /*(B,Tp,D)*/, void* stream);
