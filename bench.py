@@ -312,13 +312,23 @@ def main():
     copy_stream = torch.cuda.Stream(device=dev)
     loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()     # two slots: the read-back lags the launch by one step
 
+    # device landing buffers, one set per distinct batch, allocated once: the per-step host -> device copies write into
+    # them (no allocator traffic across streams inside the timed loop)
+    landing = [to_dev(b, i, dev) for b, i in host]
+    last_use = [None] * N_DISTINCT
+
     def prefetch(j):
         """Host -> device copy of batch j from pinned memory on the copy stream (overlaps the running step)."""
         with torch.cuda.stream(copy_stream):
-            b, it = to_dev(host[j][0], host[j][1], dev, pinned=True)
+            if last_use[j] is not None:
+                copy_stream.wait_event(last_use[j])            # the step that last read this landing set has finished
+            b, it = landing[j]
+            for d, h in zip(b, host[j][0][:8]):
+                d.copy_(h, non_blocking=True)
+            it.copy_(host[j][1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return b, it, ev
+        return j, b, it, ev
 
     def run(n, first, e2e):
         """e2e: every step's inputs come from pinned host memory (copied while the previous step computes) and every
@@ -337,16 +347,14 @@ def main():
         pending = None
         seen = 0.0
         for i in range(n):
-            j = (first + i) % N_DISTINCT
-            b, it, ev = nxt
+            j, b, it, ev = nxt
             main.wait_event(ev)
-            for t in list(b) + [it]:
-                t.record_stream(main)
             losses, _ = trainer(b, it)
             slot = i & 1
             loss_pin[slot:slot + 1].copy_(losses["total_loss"].detach().reshape(1), non_blocking=True)   # device -> host
             done = torch.cuda.Event()
             done.record(main)
+            last_use[j] = done
             if i + 1 < n:
                 nxt = prefetch((first + i + 1) % N_DISTINCT)
             if pending is not None:                      # the previous step's loss, now on the host

@@ -3,12 +3,10 @@
 #include "common.cuh"
 #include "../../include/fs2_b200.h"
 
-// Fs2Gemm.relu: 0 = none, 1 = ReLU, 2 = GELU (exact erf form, torch nn.GELU() default -- rank_model/model.py:31)
-__device__ __forceinline__ float epi_act(float v, int kind) {
-  if (kind == 1) return fmaxf(v, 0.f);
-  if (kind == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-  return v;
-}
+// Fs2Gemm.relu: 0 = none, 1 = ReLU.  (A GELU variant lived here for the intensity extractor; its erff code alone made
+// every GEMM kernel ~2 % slower on the FastSpeech2 step -- instruction footprint -- so GELU is a separate elementwise
+// kernel, fs2_gelu.)
+__device__ __forceinline__ float epi_act(float v, int kind) { return kind ? fmaxf(v, 0.f) : v; }
 
 struct EpiRow {
   long long base;      // element offset of (row, c_col_off) in C

@@ -319,12 +319,9 @@ __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, 
       for (int i = 0; i < 32; ++i) v[i] += g.bias[nb0 + i];
     }
   }
-  if (g.relu == 1) {
+  if (g.relu) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-  } else if (g.relu == 2) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = epi_act(v[i], 2);
   }
   if (et.any_dead) {
     const bool live = row_ok && !er.skip && er.live;

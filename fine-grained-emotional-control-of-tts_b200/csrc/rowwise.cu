@@ -1225,6 +1225,22 @@ __global__ void __launch_bounds__(THREADS) intensity_head_kernel(const float* __
   }
 }
 
+// exact (erf) GELU in place over an operand buffer: nn.GELU() of rank_model/model.py:31, 42
+template <typename TA>
+__global__ void __launch_bounds__(256) gelu_kernel(TA* x, long long n) {
+  pdl_wait();
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = ld4(x + i);
+    v.x = 0.5f * v.x * (1.0f + erff(v.x * 0.70710678118654752f));
+    v.y = 0.5f * v.y * (1.0f + erff(v.y * 0.70710678118654752f));
+    v.z = 0.5f * v.z * (1.0f + erff(v.z * 0.70710678118654752f));
+    v.w = 0.5f * v.w * (1.0f + erff(v.w * 0.70710678118654752f));
+    st4(x + i, v);
+  }
+}
+
 // ---------------------------------------------------------------------- device collate --
 constexpr int COL_T = 32;      // frames per CTA
 // grid (ceil(Tm / 32) + 1, B): x < ceil(Tm/32) handles a 32-frame slab of utterance row i (all n_mels + 2 channels go
@@ -1579,5 +1595,15 @@ extern "C" int fs2_collate(const int64_t* phon_cat, const int64_t* dur_cat, cons
   const size_t sm = (size_t)(n_mels + 2) * (COL_T + 1) * sizeof(float);
   FS2_LAUNCH((collate_kernel), grid, 256, sm, ST, phon_cat, dur_cat, mel_cat, pitch_cat, energy_cat, ph_start, ph_len, fr_start,
              fr_len, B, Tp, Tm, n_mels, phoneme, duration, mel, pitch, energy, rank_X);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_gelu(void* x, long long n, int act_bf16, void* stream) {
+  REQUIRE(x && n >= 0 && n % 4 == 0, "fs2_gelu: n must be a multiple of 4");
+  if (n == 0) return FS2_OK;
+  const long long blocks = (n / 4 + 255) / 256;
+  const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+  if (act_bf16) FS2_LAUNCH((gelu_kernel<bf16>), grid, 256, 0, ST, (bf16*)x, n);
+  else FS2_LAUNCH((gelu_kernel<float>), grid, 256, 0, ST, (float*)x, n);
   return fs2_check_launch();
 }

@@ -5,7 +5,7 @@ shapes as the reference class (parameters are held by ordinary torch modules -- 
 called), same `forward(x, length, emotions) -> (B, T, n_emotions)`.
 
 Everything numeric runs in the C-ABI library: the 82 -> 384 input projection, six post-norm FFT blocks (fused tcgen05
-attention with a plain key-padding mask; Conv1d k=9 384 -> 1536 + GELU and Conv1d k=9 1536 -> 384 as zero-padded
+attention with a plain key-padding mask; Conv1d k=9 384 -> 1536, GELU, Conv1d k=9 1536 -> 384 as zero-padded
 implicit GEMMs; residual + LayerNorm), the emotion-embedding shift, mask and 384 -> 5 classifier.  Inference only
 (`torch.no_grad()`, dropout inactive), bf16 operands with fp32 accumulation; no CPU fallback.
 
@@ -161,7 +161,8 @@ class IntensityExtractor(nn.Module):
             self._ln(B, T, D, cur_f32, ws["proj"], ly["g1"], ly["be1"], ly["eps1"], nxt_f32, nxt_act)
             cur_f32, cur_act, nxt_f32, nxt_act = nxt_f32, nxt_act, cur_f32, cur_act
             # convolutional feed-forward (model.py:39-46): conv k -> GELU -> conv k, zero padding
-            self._gemm(cur_act, ly["w1"], ws["hid"], rows=rows, cin=D, cout=4 * D, k=k, T=T, bias=ly["b1"], c_bf16=True, act=2)
+            self._gemm(cur_act, ly["w1"], ws["hid"], rows=rows, cin=D, cout=4 * D, k=k, T=T, bias=ly["b1"], c_bf16=True)
+            L.call("fs2_gelu", ws["hid"], rows * 4 * D, 1)          # halo rows hold zeros: GELU(0) = 0 keeps the zero padding
             self._gemm(ws["hid"], ly["w2"], ws["ffn"], rows=rows, cin=4 * D, cout=D, k=k, T=T, bias=ly["b2"], c_bf16=False)
             self._ln(B, T, D, cur_f32, ws["ffn"], ly["g2"], ly["be2"], ly["eps2"], nxt_f32, nxt_act)
             cur_f32, cur_act, nxt_f32, nxt_act = nxt_f32, nxt_act, cur_f32, cur_act

@@ -248,6 +248,8 @@ int fs2_adamw(float* p, const float* g, float* m, float* v, long long n, float l
  *   halo rows zero.  channels_first = 1: x is (B, C, T) (the collate's rank_X, dataset.py:106-110); 0: (B, T, C).
  * fs2_intensity_head: I[b,t,:] = Wc . mask(h[b,t,:] + emb[emotions[b],:]) + bc with mask = (t < lens[b])
  *   (model.py:104-107); h is the fp32 padded-row output of the last FFT block. */
+/* x = GELU(x) in place, exact erf form (nn.GELU(), rank_model/model.py:31), n elements of operand storage, n % 4 == 0 */
+int fs2_gelu(void* x, long long n, int act_bf16, void* stream);
 int fs2_frames_to_rows(const float* x, int channels_first, int B, int C, int T, int Cpad, void* out_act, int act_bf16,
                        void* stream);
 int fs2_intensity_head(const float* h, const float* emb, const int64_t* emotions, const int* lens, const float* Wc,
