@@ -393,7 +393,7 @@ def main():
     if rank == 0:
         sampler.start()
     ms, tot, launches = timed(args.steps, 0, False)
-    run(2, 0, True)
+    run(N_DISTINCT + 2, 0, True)                   # every landing set and pinned buffer touched once before timing
     ms_e, tot_e, _ = timed(args.steps, 0, True)      # back to back with the resident run: no idle gap, same clocks
     clocks = sampler.stop() if rank == 0 else None
 

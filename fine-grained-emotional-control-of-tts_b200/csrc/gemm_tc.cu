@@ -31,6 +31,15 @@ constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NTHREADS = 32 * (2 + NUM_EPI_WARPS);
 
+// Measurement-only code (role-level cycle probes of tools/gemm_rounds.py, the FS2_TC_EPIT=3 direct-store epilogue) is
+// compiled in with `make EXTRA=-DFS2_TC_PROBE`; in the product build it is dead code and is removed by the compiler --
+// the GEMM kernels are sensitive to their instruction footprint (1-3 % of the training step).
+#ifdef FS2_TC_PROBE
+constexpr bool kTcProbe = true;
+#else
+constexpr bool kTcProbe = false;
+#endif
+
 struct TcParams {
   Fs2Gemm g;
   int kb_per_tap;     // ceil(K / 64)
@@ -131,90 +140,19 @@ __device__ __forceinline__ void umma_commit_x(uint32_t bar) {
 
 // One 32-column accumulator chunk of one output row: scale/bias/ReLU/masks, then vector or scalar stores
 // (halo mirror rows included).  r[] holds the fp32 accumulators of columns [nb0, nb0+32).
+// Row-per-thread scalar stores: the complete epilogue semantics (bias, ReLU, ReLU-mask, row mask, halo mirrors, bf16 /
+// fp32 / atomics, strided columns).  Used for partial chunks, strided wgrad outputs (k > 1) and the few warp tiles that
+// contain halo-mirror rows; everything else goes through epi_chunk_t.  (A row-per-thread VECTOR path used to live here
+// as well; it is gone because its code, inlined next to the other two paths, cost more in instruction footprint than it
+// saved on the rare tiles that still took it.)
 template <int MODE>
 __device__ __forceinline__ void epi_chunk(const Fs2Gemm& g, const EpiRow& er, const uint32_t* r, int nb0, long long col0,
                                           long long cstr, bool atomic, bool vec_f32, bool vec_bf16) {
-  const bool full = (nb0 + 32 <= g.N);
-  if (full && (vec_f32 || vec_bf16)) {
-    float v[32];
+  (void)vec_f32;
+  (void)vec_bf16;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float x = __uint_as_float(r[i]) * g.alpha;
-      if (g.bias) x += g.bias[nb0 + i];
-      if (g.relu) x = epi_act(x, g.relu);
-      v[i] = er.live ? x : 0.f;
-    }
-    if (g.relu_aux) {
-      if (g.aux_bf16) {
-        const uint4* ap = reinterpret_cast<const uint4*>((const bf16*)g.relu_aux + er.base + col0);
-        uint4 a[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = ap[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t w[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-            if (!((w[j] & 0x8000u) == 0 && (w[j] & 0x7FFFu) != 0)) v[i * 8 + j * 2] = 0.f;
-            if (!((w[j] & 0x80000000u) == 0 && (w[j] & 0x7FFF0000u) != 0)) v[i * 8 + j * 2 + 1] = 0.f;
-          }
-        }
-      } else {
-        const float4* ap = reinterpret_cast<const float4*>((const float*)g.relu_aux + er.base + col0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 a = ap[i];
-          if (!(a.x > 0.f)) v[4 * i] = 0.f;
-          if (!(a.y > 0.f)) v[4 * i + 1] = 0.f;
-          if (!(a.z > 0.f)) v[4 * i + 2] = 0.f;
-          if (!(a.w > 0.f)) v[4 * i + 3] = 0.f;
-        }
-      }
-    }
-    if (vec_f32) {
-      float* dst = (float*)g.C + er.base + col0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        const long long mo = mi ? er.mirror2 : er.mirror;
-        if (mo) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            st4(dst + mo + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-        }
-      }
-    } else {
-      bf16* dst = (bf16*)g.C + er.base + col0;
-      uint4 pk[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-        pk[i].x = *reinterpret_cast<uint32_t*>(&h0);
-        pk[i].y = *reinterpret_cast<uint32_t*>(&h1);
-        pk[i].z = *reinterpret_cast<uint32_t*>(&h2);
-        pk[i].w = *reinterpret_cast<uint32_t*>(&h3);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = pk[i];
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        const long long mo = mi ? er.mirror2 : er.mirror;
-        if (mo) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst + mo)[i] = pk[i];
-        }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
-  }
+  for (int i = 0; i < 32; ++i)
+    if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
 }
 
 // Coalesced variant of the vector store path.  tcgen05.ld hands every lane one accumulator ROW, so a direct st.v4 per
@@ -460,7 +398,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       // cost them fewer cycles than its MMAs take (4 x 48 cycles at BN = 192), so stage / phase / tap counters are
       // incremental (no division, no modulo) and the tensor-map coordinate permutation is resolved once per kernel.
       bool ok = true;
-      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+      const bool prof = kTcProbe && p.dbg != nullptr && blockIdx.x == 0;
       long long w_empty = 0, t_all = prof ? clock64() : 0;
       const int ars = p.pa[1], ai1 = p.pa[2];        // slot (1..3) of the row coordinate / of i1 in A's tensor map
       const int brs = p.pb[1], bi1 = p.pb[2];
@@ -529,7 +467,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t tc = 0;
       bool ok = true;
-      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+      const bool prof = kTcProbe && p.dbg != nullptr && blockIdx.x == 0;
       long long w_acc = 0, w_full = 0, t_all = prof ? clock64() : 0;
       // shared-memory descriptors: everything but the 14-bit start-address field is constant, and that field only ever
       // moves by (bytes >> 4) -- one descriptor per operand for stage 0, then plain 64-bit adds
@@ -585,7 +523,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     const bool aux_al = g.relu_aux == nullptr || (((uintptr_t)g.relu_aux) % 16 == 0);
     uint32_t tc = 0;
     bool ok = true;
-    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
+    const bool prof = kTcProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 2;
     long long w_tfull = 0, t_chunks = 0, t_ld = 0, t_all = prof ? clock64() : 0;
     for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x, ++tc) {
       const int nt = t % p.n_tiles_total;
@@ -617,7 +555,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       // experiment switch FS2_TC_EPIT=3: fp32 outputs skip the smem transpose (direct 8-byte stores from the 16x256b TMEM
       // layout).  Measured equal-to-slower than the transpose (profiles/r01_summary.md section 3: in steady state these
       // GEMMs are bound by the HBM traffic of their fp32 output, not by the store instruction pattern), so it is off.
-      const bool q_path = t_path && p.epi_transpose == 3 && (vec_f32_at || (vec_f32 && g.relu_aux == nullptr)) &&
+      const bool q_path = kTcProbe && t_path && p.epi_transpose == 3 && (vec_f32_at || (vec_f32 && g.relu_aux == nullptr)) &&
                           (g.bias == nullptr || (((uintptr_t)g.bias) % 8 == 0));
       const long long tq2 = prof ? clock64() : 0;
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, err)) { ok = false; break; }
@@ -629,7 +567,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         const int c = half * CHUNKS_PER_HALF + ci;
         uint32_t r[32];
         const int nb0 = n0 + c * 32;
-        const bool q_use = q_path && nb0 + 32 <= g.N && p.dbg_mode != 3;
+        const bool q_use = q_path && nb0 + 32 <= g.N && !(kTcProbe && p.dbg_mode == 3);
         const long long tq4 = prof ? clock64() : 0;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32);
         if (q_use) {
@@ -647,12 +585,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
           if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[as]));
         }
         if (q_use) {
-          epi_chunk_q<MODE>(g, et, r, r + 16, nb0, colbase + (long long)c * 32, atomic, p.dbg_mode == 4);
+          epi_chunk_q<MODE>(g, et, r, r + 16, nb0, colbase + (long long)c * 32, atomic, kTcProbe && p.dbg_mode == 4);
           continue;
         }
-        if (nb0 >= g.N || p.dbg_mode == 3) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
+        if (nb0 >= g.N || (kTcProbe && p.dbg_mode == 3)) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
         if (t_path && nb0 + 32 <= g.N) {
-          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4, atomic);
+          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, kTcProbe && p.dbg_mode == 4, atomic);
           continue;
         }
         if (!row_ok || er.skip) continue;
@@ -714,7 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
   const int nunits = (NCTA == 2) ? (int)cluster_count_x() : (int)gridDim.x;
   long long dbg_c0 = 0;
   uint64_t dbg_t0 = 0;
-  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { dbg_c0 = clock64(); dbg_t0 = globaltimer_ns(); }
+  if (kTcProbe && p.dbg && blockIdx.x == 0 && threadIdx.x == 0) { dbg_c0 = clock64(); dbg_t0 = globaltimer_ns(); }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -754,7 +692,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       int s = 0;
       uint32_t ph = 0;
-      bool ok = p.dbg_mode != 1;
+      bool ok = !(kTcProbe && p.dbg_mode == 1);
       const int p1a = p.pa[1], p2a = p.pa[2], p1b = p.pb[1], p2b = p.pb[2];
       const int pa_[4] = {0, p1a, p2a, 0}, pb_[4] = {0, p1b, p2b, 0};
       for (int t = unit; t < p.total_tiles && ok; t += nunits) {
@@ -832,13 +770,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * TILE_N;
         for (int i = 0; i < nkb; ++i) {
-          if (p.dbg_mode != 1 && !mbar_wait(smem_u32(&full_bar[s]), ph, err)) { ok = false; break; }
+          if (!(kTcProbe && p.dbg_mode == 1) && !mbar_wait(smem_u32(&full_bar[s]), ph, err)) { ok = false; break; }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            if (p.dbg_mode == 2) break;
+            if (kTcProbe && p.dbg_mode == 2) break;
             const uint64_t ad = A_MN ? smem_desc(sa + k * 2048, BK * 128, 1024) : smem_desc(sa + k * 32, 16, 1024);
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
@@ -895,7 +833,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
       // experiment switch FS2_TC_EPIT=3: fp32 outputs skip the smem transpose (direct 8-byte stores from the 16x256b TMEM
       // layout).  Measured equal-to-slower than the transpose (profiles/r01_summary.md section 3: in steady state these
       // GEMMs are bound by the HBM traffic of their fp32 output, not by the store instruction pattern), so it is off.
-      const bool q_path = t_path && p.epi_transpose == 3 && (vec_f32_at || (vec_f32 && g.relu_aux == nullptr)) &&
+      const bool q_path = kTcProbe && t_path && p.epi_transpose == 3 && (vec_f32_at || (vec_f32 && g.relu_aux == nullptr)) &&
                           (g.bias == nullptr || (((uintptr_t)g.bias) % 8 == 0));
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, err)) { ok = false; break; }
       tc_fence_after();
@@ -904,7 +842,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
         const int c = half * CHUNKS_PER_HALF + ci;
         uint32_t r[32];
         const int nb0 = n0 + c * 32;
-        const bool q_use = q_path && nb0 + 32 <= g.N && p.dbg_mode != 3;
+        const bool q_use = q_path && nb0 + 32 <= g.N && !(kTcProbe && p.dbg_mode == 3);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TILE_N + c * 32);
         if (q_use) {
           tmem_ld_16x256b_x4(taddr, r);
@@ -924,12 +862,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
           }
         }
         if (q_use) {
-          epi_chunk_q<MODE>(g, et, r, r + 16, nb0, colbase + (long long)c * 32, atomic, p.dbg_mode == 4);
+          epi_chunk_q<MODE>(g, et, r, r + 16, nb0, colbase + (long long)c * 32, atomic, kTcProbe && p.dbg_mode == 4);
           continue;
         }
-        if (nb0 >= g.N || p.dbg_mode == 3) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
+        if (nb0 >= g.N || (kTcProbe && p.dbg_mode == 3)) continue;            // warp-uniform (dbg_mode 3: measurement without stores)
         if (t_path && nb0 + 32 <= g.N) {
-          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, p.dbg_mode == 4, atomic);
+          epi_chunk_t<MODE>(g, er, row_ok, et, r, nb0, colbase + (long long)c * 32, vec_bf16, stage, kTcProbe && p.dbg_mode == 4, atomic);
           continue;
         }
         if (!row_ok || er.skip) continue;
@@ -941,7 +879,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
   __syncwarp();
   tc_fence_before();
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();     // nobody leaves while the peer can still signal its barriers
-  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (kTcProbe && p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
     p.dbg[0] = clock64() - dbg_c0;
     p.dbg[1] = (long long)(globaltimer_ns() - dbg_t0);
   }

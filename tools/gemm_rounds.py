@@ -67,7 +67,7 @@ for graph in (True,):
     run("ffn-in 384->1536 bf16 out (k=1)", 1536, 384, True, 256, graph)
 print("flag", L.gemm_tc_error_flag())
 
-# ---- role probe of CTA 0 (single-CTA kernel): who waits on whom
+# ---- role probe of CTA 0 (single-CTA kernel): who waits on whom (needs a library built with `make EXTRA=-DFS2_TC_PROBE`)
 if os.environ.get("GEMM_PROBE"):
     dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
     L.gemm_tc_set_debug(dbg)
