@@ -21,6 +21,12 @@
 namespace {
 
 long long* g_attn_dbg = nullptr;
+// the cycle probe of tools/attn_bench.py (ATTN_DBG=1) is compiled in with `make EXTRA=-DFS2_TC_PROBE` only
+#ifdef FS2_TC_PROBE
+constexpr bool kAttnProbe = true;
+#else
+constexpr bool kAttnProbe = false;
+#endif
 
 constexpr int AQ = 128;        // query rows per CTA
 constexpr int AK = 64;         // keys per block (one 128-byte swizzle row of P)
@@ -28,7 +34,7 @@ constexpr int HD = 192;        // head dimension: three 64-wide swizzle atoms
 constexpr int KSTAGES = 3;
 constexpr int VSTAGES = 2;
 // NCH = threads per query row (column slices of a key block): 2 in the forward (8 softmax warps), 4 in the backward
-// (16 warps: the dS math has more loads in flight per column) -- measured on B200, see profiles/r01_attention.md
+// (16 warps: the dS math has more loads in flight per column) -- measured on B200, see profiles/r01_summary.md section 4
 constexpr int att_threads(int nch) { return 32 * (2 + 4 * nch); }    // TMA, MMA, 4*NCH softmax warps
 constexpr int Q_BYTES = 3 * AQ * 128;          // 49152
 constexpr int KV_BYTES = 3 * AK * 128;         // 24576
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(att_threads(NCH), 1) attn_kernel(const __grid_
       bool ok = mbar_wait(smem_u32(qfull), 0, err);
       int s = 0, sv = 0;
       uint32_t ph = 0, phv = 0;
-      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+      const bool prof = kAttnProbe && p.dbg != nullptr && blockIdx.x == 0;
       long long w_k = 0, w_se = 0, w_pf = 0, w_v = 0, t_all = clock64(), tt = 0;
       for (int job = 0; job <= njobs && ok; ++job) {
         if (job < njobs) {
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(att_threads(NCH), 1) attn_kernel(const __grid_
 #pragma unroll
       for (int c = 0; c < NCH; ++c) dsum += xch[c * AQ + row].x;
     }
-    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
+    const bool prof = kAttnProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
     long long w_sf = 0, w_ld = 0, w_cmp = 0, w_pe = 0, w_st = 0, t_all = clock64(), tt = 0;
     uint4 pk[CW / 8];                                             // bwd: this job's P chunk (packed bf16), prefetched
     auto load_p = [&](int j) {

@@ -147,12 +147,32 @@ __device__ __forceinline__ void umma_commit_x(uint32_t bar) {
 // saved on the rare tiles that still took it.)
 template <int MODE>
 __device__ __forceinline__ void epi_chunk(const Fs2Gemm& g, const EpiRow& er, const uint32_t* r, int nb0, long long col0,
-                                          long long cstr, bool atomic, bool vec_f32, bool vec_bf16) {
-  (void)vec_f32;
-  (void)vec_bf16;
+                                          long long cstr, bool atomic, uint8_t* stage) {
+  // Forward / dgrad kernels reach this path only for partial chunks and halo-mirror tiles: the 32 values of the row go
+  // through the warp's staging tile (word i of lane l at (i*32 + l)*4: conflict-free) so that ONE epi_store body in a
+  // rolled loop serves them all -- 32 inlined copies of it were the largest single piece of code in those kernels.
+  if constexpr (MODE == 2) {
+    // weight gradients with k > 1 live on this path (strided columns, scalar atomics): keep it unrolled in registers
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
+    for (int i = 0; i < 32; ++i)
+      if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
+    return;
+  }
+  const uint32_t sb = smem_u32(stage) + (uint32_t)(threadIdx.x & 31) * 4u;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sb + (uint32_t)i * 128u), "r"(half ? r[16 + i] : r[i]) : "memory");
+#pragma unroll 1
+    for (int i = 0; i < 16; ++i) {
+      const int n = nb0 + half * 16 + i;
+      if (n >= g.N) break;
+      uint32_t v;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sb + (uint32_t)i * 128u) : "memory");
+      epi_store(g, er, col0 + (long long)(half * 16 + i) * cstr, n, __uint_as_float(v), atomic);
+    }
+  }
 }
 
 // Coalesced variant of the vector store path.  tcgen05.ld hands every lane one accumulator ROW, so a direct st.v4 per
@@ -594,7 +614,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
           continue;
         }
         if (!row_ok || er.skip) continue;
-        epi_chunk<MODE>(g, er, r, nb0, colbase + (long long)c * 32 * cstr, cstr, atomic, vec_f32, vec_bf16);
+        epi_chunk<MODE>(g, er, r, nb0, colbase + (long long)c * 32 * cstr, cstr, atomic, stage);
       }
       if (prof) t_chunks += clock64() - tq3;
     }
@@ -871,7 +891,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
           continue;
         }
         if (!row_ok || er.skip) continue;
-        epi_chunk<MODE>(g, er, r, nb0, colbase + (long long)c * 32 * cstr, cstr, atomic, vec_f32, vec_bf16);
+        epi_chunk<MODE>(g, er, r, nb0, colbase + (long long)c * 32 * cstr, cstr, atomic, stage);
       }
     }
   }
