@@ -780,6 +780,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
       uint32_t tc = 0, ph = 0;
       int s = 0;
       bool ok = true;
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t adesc0 = A_MN ? smem_desc(smem0, BK * 128, 1024) : smem_desc(smem0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? smem_desc(smem0 + A_BYTES, BK * 128, 1024) : smem_desc(smem0 + A_BYTES, 16, 1024);
+      constexpr uint64_t A_STEP = A_MN ? (2048 >> 4) : (32 >> 4);
+      constexpr uint64_t B_STEP = B_MN ? (2048 >> 4) : (32 >> 4);
+      constexpr uint64_t STAGE_STEP = STAGE_BYTES >> 4;
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       for (int t = unit; t < p.total_tiles && ok; t += nunits, ++tc) {
         const int z = (t / p.n_tiles_total) / p.m_tiles;
         const int zs = z % p.nsplit;
@@ -789,23 +796,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
         if (!mbar_wait(smem_u32(&tempty_bar[as]), aph ^ 1, err)) { ok = false; break; }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * TILE_N;
+        uint32_t acc = 0;
         for (int i = 0; i < nkb; ++i) {
-          if (!(kTcProbe && p.dbg_mode == 1) && !mbar_wait(smem_u32(&full_bar[s]), ph, err)) { ok = false; break; }
+          if (!(kTcProbe && p.dbg_mode == 1) && !mbar_wait(full0 + 8 * s, ph, err)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          // descriptors: stage-0 descriptor + (byte offset >> 4), see tc_gemm_kernel
+          const uint64_t ad0 = adesc0 + (uint64_t)s * STAGE_STEP, bd0 = bdesc0 + (uint64_t)s * STAGE_STEP;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             if (kTcProbe && p.dbg_mode == 2) break;
-            const uint64_t ad = A_MN ? smem_desc(sa + k * 2048, BK * 128, 1024) : smem_desc(sa + k * 32, 16, 1024);
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub) {
-              const uint32_t sbs = sb + sub * BSUB_BYTES;
-              const uint64_t bd = B_MN ? smem_desc(sbs + k * 2048, BK * 128, 1024) : smem_desc(sbs + k * 32, 16, 1024);
-              umma_bf16_x<NCTA>(tmem_d + sub * BNS, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int sub = 0; sub < NSUB; ++sub)
+              umma_bf16_x<NCTA>(tmem_d + sub * BNS, ad0 + k * A_STEP, bd0 + sub * (uint64_t)(BSUB_BYTES >> 4) + k * B_STEP, idesc,
+                                acc);
+            acc = 1;
           }
-          umma_commit_x<NCTA>(smem_u32(&empty_bar[s]));
+          umma_commit_x<NCTA>(empty0 + 8 * s);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         if (ok) umma_commit_x<NCTA>(smem_u32(&tfull_bar[as]));
