@@ -152,11 +152,21 @@ __device__ __forceinline__ void epi_chunk(const Fs2Gemm& g, const EpiRow& er, co
   // through the warp's staging tile (word i of lane l at (i*32 + l)*4: conflict-free) so that ONE epi_store body in a
   // rolled loop serves them all -- 32 inlined copies of it were the largest single piece of code in those kernels.
   if constexpr (MODE == 2) {
-    // weight gradients with k > 1 live on this path (strided columns, scalar atomics): keep it unrolled in registers
+    // weight gradients with k > 1 live on this path: fp32 atomics into strided columns and nothing else (no bias, ReLU,
+    // mask, mirror) -- 32 bare atomics from registers instead of 32 copies of the general store
+    if (atomic && !g.c_bf16 && !g.bias && !g.relu && !g.relu_aux && g.rs_Tp == 0) {
+      float* dst = (float*)g.C + er.base + col0;
+      const float alpha = g.alpha;
+      if (nb0 + 32 <= g.N) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (nb0 + i < g.N) epi_store(g, er, col0 + i * cstr, nb0 + i, __uint_as_float(r[i]), atomic);
-    return;
+        for (int i = 0; i < 32; ++i) atomicAdd(dst + i * cstr, __uint_as_float(r[i]) * alpha);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (nb0 + i < g.N) atomicAdd(dst + i * cstr, __uint_as_float(r[i]) * alpha);
+      }
+      return;
+    }
   }
   const uint32_t sb = smem_u32(stage) + (uint32_t)(threadIdx.x & 31) * 4u;
 #pragma unroll 1
