@@ -221,6 +221,9 @@ __device__ __forceinline__ void block_reduce_cols(float4 (&a)[NV], float* out, i
 // mask, drop_a, tanh, affine, normalisation, (ReLU of x), and the branch dropout.
 // NV = float4 per lane (ceil(C / 128)): 3 for the 384-wide model rows, 4 for the PostNet (512), 1 for n_mels (80);
 // HEAD = the variance predictors' 384 -> 1 output layer is folded in.  Both only size the register arrays.
+// HEAD doubles as the "rare features" switch: only the variance-predictor / PostNet calls use the 384 -> 1 head, tanh,
+// ReLU-of-x or the dropout AFTER the norm; the FFT-block LayerNorms (24 of the ~30 calls per step) run the HEAD = false
+// instantiation in which all of that is compiled out (3.2 k -> ~1.6 k instructions per kernel).
 template <typename TA, int NV, bool HEAD>
 __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_kernel(Fs2LnBwd p) {
   pdl_wait();
@@ -294,8 +297,8 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
         float4 h;
         h.x = (z.x - mean) * rstd; h.y = (z.y - mean) * rstd; h.z = (z.z - mean) * rstd; h.w = (z.w - mean) * rstd;
         float4 u = make_float4(h.x * gam.x + bet.x, h.y * gam.y + bet.y, h.z * gam.z + bet.z, h.w * gam.w + bet.w);
-        if (p.tanh_act) { u.x = tanhf(u.x); u.y = tanhf(u.y); u.z = tanhf(u.z); u.w = tanhf(u.w); }
-        float4 k = drop_scale4(da, (uint64_t)(ro + c) >> 2);
+        if (HEAD && p.tanh_act) { u.x = tanhf(u.x); u.y = tanhf(u.y); u.z = tanhf(u.z); u.w = tanhf(u.w); }
+        float4 k = HEAD ? drop_scale4(da, (uint64_t)(ro + c) >> 2) : make_float4(1.f, 1.f, 1.f, 1.f);
         if (HEAD && p.head_w) {
           float4 hw = ld4(p.head_w + c);
           g.x += dh * hw.x; g.y += dh * hw.y; g.z += dh * hw.z; g.w += dh * hw.w;
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
         }
         if (!live) g = make_float4(0.f, 0.f, 0.f, 0.f);
         g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
-        if (p.tanh_act) {
+        if (HEAD && p.tanh_act) {
           g.x *= (1.f - u.x * u.x); g.y *= (1.f - u.y * u.y); g.z *= (1.f - u.z * u.z); g.w *= (1.f - u.w * u.w);
         }
         {
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
         dz.y = rstd * (gx[i].y - s1 - xh[i].y * s2);
         dz.z = rstd * (gx[i].z - s1 - xh[i].z * s2);
         dz.w = rstd * (gx[i].w - s1 - xh[i].w * s2);
-        if (p.relu_x) {
+        if (HEAD && p.relu_x) {
           float4 x = ld4(p.x + ro + c);
           if (!(x.x > 0.f)) dz.x = 0.f;
           if (!(x.y > 0.f)) dz.y = 0.f;
@@ -1335,7 +1338,9 @@ extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
   int grid = grid_for_rows(rows);
   if (grid > 148 * 6) grid = 148 * 6;      // two waves of three resident CTAs per SM
   const int nv = (p->C + 127) / 128;
-  const bool head = p->head_w != nullptr || p->dhead_w != nullptr || p->dhead_b != nullptr;
+  // "head" selects the general instantiation: the 384 -> 1 head, tanh, ReLU-of-x or dropout after the norm
+  const bool head = p->head_w != nullptr || p->dhead_w != nullptr || p->dhead_b != nullptr || p->tanh_act || p->relu_x ||
+                    p->drop_a_p > 0.f;
 #define LN_BWD_LAUNCH(TA, NV, HEAD) FS2_LAUNCH((ln_bwd_kernel<TA, NV, HEAD>), grid, THREADS, 0, ST, *p)
 #define LN_BWD_NV(TA, NV) do { if (head) LN_BWD_LAUNCH(TA, NV, true); else LN_BWD_LAUNCH(TA, NV, false); } while (0)
 #define LN_BWD_TA(TA) do { if (nv == 1) LN_BWD_NV(TA, 1); else if (nv == 2) LN_BWD_NV(TA, 2); else if (nv == 3) LN_BWD_NV(TA, 3); else LN_BWD_NV(TA, 4); } while (0)
