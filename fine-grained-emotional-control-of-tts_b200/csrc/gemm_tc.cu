@@ -210,7 +210,8 @@ struct EpiT {
   unsigned okmask;      // rows that exist and are written
   unsigned livemask;    // ... and are not masked (t < lens[b])
   bool any_dead;        // some written row is masked (t >= lens[b]): the value path has to select zeros
-  bool mirrors;         // some row needs a halo mirror store -> the chunk takes the row-per-thread path
+  bool mirrors;         // some row of this warp also writes a reflect-halo mirror copy (m1 / m2 != 0)
+  long long m1[4], m2[4];   // mirror offsets of rows tr, tr+8, tr+16, tr+24 (valid when `mirrors`)
 };
 
 __device__ __forceinline__ void epi_t_setup(const EpiRow& er, bool row_ok, EpiT& et) {
@@ -223,6 +224,14 @@ __device__ __forceinline__ void epi_t_setup(const EpiRow& er, bool row_ok, EpiT&
   const long long mybase = mine ? er.base : 0;
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) et.tb[jj] = __shfl_sync(0xffffffffu, mybase, jj * 8 + (lane >> 2));
+  if (et.mirrors) {                       // warp-uniform; only GEMMs whose output feeds a k > 1 conv (halo > 0)
+    const long long a = mine ? er.mirror : 0, b = mine ? er.mirror2 : 0;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      et.m1[jj] = __shfl_sync(0xffffffffu, a, jj * 8 + (lane >> 2));
+      et.m2[jj] = __shfl_sync(0xffffffffu, b, jj * 8 + (lane >> 2));
+    }
+  }
 }
 
 // fp32 output straight from the 16x256b TMEM register layout (tmem_ld_16x256b_x4, two loads = 32 rows x 32 columns):
@@ -340,7 +349,12 @@ __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, 
           }
           x = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        *reinterpret_cast<uint4*>((bf16*)g.C + tb[jj] + col0 + tcq * 8) = x;
+        bf16* dst = (bf16*)g.C + tb[jj] + col0 + tcq * 8;
+        *reinterpret_cast<uint4*>(dst) = x;
+        if (et.mirrors) {
+          if (et.m1[jj]) *reinterpret_cast<uint4*>(dst + et.m1[jj]) = x;
+          if (et.m2[jj]) *reinterpret_cast<uint4*>(dst + et.m2[jj]) = x;
+        }
       }
     }
     __syncwarp();
@@ -362,7 +376,13 @@ __device__ __forceinline__ void epi_chunk_t(const Fs2Gemm& g, const EpiRow& er, 
           // split-K / accumulate: one 16-byte vector reduction per lane, 8 rows x 64 B per instruction -- 8x fewer L2
           // atomic operations than the row-per-thread scalar atomics (the k = 1 weight gradients were bound by them)
           if (atomic) atomicAdd(reinterpret_cast<float4*>(dst), xv);
-          else st4(dst, xv);
+          else {
+            st4(dst, xv);
+            if (et.mirrors) {
+              if (et.m1[jj]) st4(dst + et.m1[jj], xv);
+              if (et.m2[jj]) st4(dst + et.m2[jj], xv);
+            }
+          }
         }
       }
       __syncwarp();
@@ -580,7 +600,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                                         (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
       if (t_path) {
         epi_t_setup(er, row_ok, et);
-        t_path = !et.mirrors;
+        t_path = !(et.mirrors && atomic);
       }
       // experiment switch FS2_TC_EPIT=3: fp32 outputs skip the smem transpose (direct 8-byte stores from the 16x256b TMEM
       // layout).  Measured equal-to-slower than the transpose (profiles/r01_summary.md section 3: in steady state these
@@ -864,7 +884,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
                                         (vec_bf16 && (g.relu_aux == nullptr || g.aux_bf16)));
       if (t_path) {
         epi_t_setup(er, row_ok, et);
-        t_path = !et.mirrors;
+        t_path = !(et.mirrors && atomic);
       }
       // experiment switch FS2_TC_EPIT=3: fp32 outputs skip the smem transpose (direct 8-byte stores from the 16x256b TMEM
       // layout).  Measured equal-to-slower than the transpose (profiles/r01_summary.md section 3: in steady state these
