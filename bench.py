@@ -162,7 +162,7 @@ def cpu_reference_run(steps, warmup, sample_batch=8, quiet=False):
                        f"workload, fp32 eager PyTorch, dropout on, AdamW), {dt:.1f} s", ms_per_step=1e3 * dt / max(steps, 1))
 
 
-def eager_gpu_reference_run(steps=3, warmup=2, batch=BATCH):
+def eager_gpu_reference_run(steps=4, warmup=4, batch=BATCH):
     """The north_star's "20x" denominator: the reference's eager-PyTorch step on the same B200 -- the oracle
     restatement moved to cuda:0 as it is (fp32, no AMP, its per-sample Python loops and host syncs included), on the
     same synthetic batches as the GPU workload.  CUDA-event timed; a reported baseline, not part of the product path."""
@@ -287,6 +287,8 @@ def main():
     L = importlib.import_module(PKG + "._lib")
     # rank 0 prints ONE JSON line on stdout: NCCL's own messages (version banner, warnings) go to a per-process file
     os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fs2_bench_nccl_%h_%p.log")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "NONE"          # the version banner of the VERSION / WARN levels would land on stdout
     rank, world, local = par.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
