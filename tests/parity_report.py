@@ -1,5 +1,5 @@
 """Stage-by-stage parity report of the CUDA path against the oracle (run on the GPU box).
-Usage: python tools/parity_report.py [--B 4] [--tp 24] [--frames 150] [--precision fp32 bf16]"""
+Usage: python tests/parity_report.py [--B 4] [--tp 24] [--frames 150] [--precision fp32 bf16]"""
 import argparse
 import importlib
 import os
