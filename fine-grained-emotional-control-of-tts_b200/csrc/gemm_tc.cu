@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     uint8_t* stage = smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
-    const bool atomic = p.nsplit > 1 || g.accumulate;
+    const bool atomic = (p.nsplit > 1 && g.c_split_stride == 0) || g.accumulate;
     const long long cstr = (MODE == 2 && g.c_col_stride > 1) ? g.c_col_stride : 1;
     const bool al4 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 4 == 0) && (((uintptr_t)g.C) % 16 == 0);
     const bool al8 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 8 == 0) && (((uintptr_t)g.C) % 16 == 0);
@@ -588,7 +588,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       const int m = m0 + q * 32 + lane;
       EpiRow er;
       const bool row_ok = (m < g.M);
-      if (row_ok) epi_row_setup(g, i1, i2, m, er);
+      if (row_ok) {
+        epi_row_setup(g, i1, i2, m, er);
+        er.base += (long long)(z % p.nsplit) * g.c_split_stride;       // 0 unless deterministic split-K
+      }
       const long long colbase = (MODE == 2) ? (long long)tapN * g.c_tap_stride + n0 * cstr : n0;
       const bool vec_f32 = cstr == 1 && !g.c_bf16 && !atomic && al4 && (colbase % 4 == 0) && aux_al;
       const bool vec_bf16 = cstr == 1 && g.c_bf16 && al8 && (colbase % 8 == 0) && aux_al;
@@ -852,7 +855,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     uint8_t* stage = smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
-    const bool atomic = p.nsplit > 1 || g.accumulate;
+    const bool atomic = (p.nsplit > 1 && g.c_split_stride == 0) || g.accumulate;
     const long long cstr = (MODE == 2 && g.c_col_stride > 1) ? g.c_col_stride : 1;
     const bool al4 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 4 == 0) && (((uintptr_t)g.C) % 16 == 0);
     const bool al8 = ((g.ldc | g.c_col_off | g.c_s1 | g.c_s2) % 8 == 0) && (((uintptr_t)g.C) % 16 == 0);
@@ -872,7 +875,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
       const int m = m0 + q * 32 + lane;
       EpiRow er;
       const bool row_ok = (m < g.M);
-      if (row_ok) epi_row_setup(g, i1, i2, m, er);
+      if (row_ok) {
+        epi_row_setup(g, i1, i2, m, er);
+        er.base += (long long)(z % p.nsplit) * g.c_split_stride;       // 0 unless deterministic split-K
+      }
       const long long colbase = (MODE == 2) ? (long long)tapN * g.c_tap_stride + n0 * cstr : n0;
       const bool vec_f32 = cstr == 1 && !g.c_bf16 && !atomic && al4 && (colbase % 4 == 0) && aux_al;
       const bool vec_bf16 = cstr == 1 && g.c_bf16 && al8 && (colbase % 8 == 0) && aux_al;
@@ -1246,6 +1252,14 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   p.kb_per_tap = (g.K + BK - 1) / BK;
   p.total_kb = (g.mode == 2) ? p.kb_per_tap : p.kb_per_tap * g.taps;
   p.nsplit = (g.mode == 2 && g.split_k > 1) ? g.split_k : 1;
+  if (g.mode != 2 && g.split_k > 1 && g.c_split_stride != 0) {
+    // deterministic split-K: every split stores its partial result to its own copy of C
+    if (g.c_bf16 || g.accumulate || g.bias || g.relu || g.relu_aux) {
+      fs2_set_error("fs2_gemm_tc: c_split_stride needs fp32 C and a plain epilogue");
+      return FS2_ERR_ARG;
+    }
+    p.nsplit = g.split_k;
+  }
   if (g.mode == 2 && g.split_k <= 0) {
     // auto split-K: the persistent grid walks tiles*split work items in waves of one item per SM; pick the split
     // that minimises waves * (k-blocks per item + the atomic epilogue's cost in k-block units)

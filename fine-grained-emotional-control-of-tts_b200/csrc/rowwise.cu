@@ -292,6 +292,12 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
           g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
           if (m1) { a = ld4(p.dy2 + ro + m1 + c); g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
           if (m2) { a = ld4(p.dy2 + ro + m2 + c); g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
+          if (p.dy3) {                    // second partial result of a split-K dgrad: same rows, same halo fold
+            a = ld4(p.dy3 + ro + c);
+            g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w;
+            if (m1) { a = ld4(p.dy3 + ro + m1 + c); g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
+            if (m2) { a = ld4(p.dy3 + ro + m2 + c); g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; }
+          }
         }
         float4 gam = ld4(p.gamma + c), bet = ld4(p.beta + c);
         float4 h;

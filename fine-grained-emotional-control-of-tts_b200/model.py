@@ -12,6 +12,7 @@ its dgrad / wgrad are the same GEMM kernel in its other two operand modes.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -258,8 +259,10 @@ class FastSpeech2(nn.Module):
                b_inner=w.k * w.cin, b_tap_step=w.cin, Cout=out, ldc=w.cout, c_bf16=c_bf16, ab_bf16=self._bf16,
                bias=bias, relu=relu, rs_T=T, rs_Tp=T + 2 * PAD, lens=lens, halo=halo)
 
-    def _conv_dgrad(self, dy, B, T, wname, out, *, c_bf16=False, relu_aux=None):
-        """dx[r] = sum_j dy[r + p - j] . W_j  (gradient wrt the padded input, halo rows included)."""
+    def _conv_dgrad(self, dy, B, T, wname, out, *, c_bf16=False, relu_aux=None, split=1):
+        """dx[r] = sum_j dy[r + p - j] . W_j  (gradient wrt the padded input, halo rows included).
+        split = 2: `out` is (2, rows, Cin); each half of the reduction is STORED to its own slice (deterministic split-K,
+        the consumer adds the two) -- used where one wave of tiles leaves SMs idle, see _dgrad_split."""
         w = self.store.pw(wname)
         rows = B * (T + 2 * PAD)
         p = (w.k - 1) // 2
@@ -267,10 +270,24 @@ class FastSpeech2(nn.Module):
         L.gemm(mode=1, M=rows, N=w.cin, K=w.cout, taps=w.k, A=dy, lda=w.cout, a_rows=rows, a_inner=w.cout,
                a_row_off=p, a_tap_step=-1, B=self.store.packed_buf, B_off=w.off, ldb=w.k * w.cin, b_rows=w.cout,
                b_inner=w.k * w.cin, b_tap_step=w.cin, Cout=out, ldc=w.cin, c_bf16=c_bf16, ab_bf16=self._bf16,
-               relu_aux=relu_aux, aux_bf16=int(self._bf16))
-        # (split_k=0 would let fs2_gemm_tc split short-grid dgrads; measured: no step-time gain once the weight gradients
+               relu_aux=relu_aux, aux_bf16=int(self._bf16), split_k=split,
+               c_split_stride=rows * w.cin if split > 1 else 0)
+        # (split_k=0 would let fs2_gemm_tc split short-grid dgrads WITH ATOMICS; measured: no step-time gain once the weight gradients
         #  fill the idle SMs from the second stream, and the atomics' summation order would leak into the bf16 roundings
         #  of the activation gradients -- run-to-run differences of 5e-4 instead of 1e-6 -- so it stays off)
+
+    def _dgrad_split(self, rows, cin):
+        """2 when splitting the k = 9 FFN dgrad's reduction in two shortens its critical path: tiles * 2 work items fill
+        the persistent grid in fewer (half-length) rounds than the tiles alone (the kernel choice of fs2_gemm_tc is mirrored
+        here: CTA-pair 256 x 384 tiles from 8192 rows, else 128 x 192 tiles)."""
+        if not self._bf16 or cin != 384 or os.environ.get("FS2_DGRAD_SPLIT", "1") == "0":
+            return 1
+        if rows >= 8192:
+            tiles, units = -(-rows // 256), 74
+        else:
+            tiles, units = -(-rows // 128) * 2, 148
+        one, two = -(-tiles // units), -(-2 * tiles // units) / 2.0
+        return 2 if two <= 0.85 * one else 1
 
     def _side_begin(self, dev):
         if not self.overlap_wgrad:
@@ -348,7 +365,7 @@ class FastSpeech2(nn.Module):
         p.seed_dev = self._ctr.data_ptr()
         L.call("fs2_ln_fwd", L.C.addressof(p))
 
-    def _ln_bwd(self, B, T, C, x, gamma, beta, eps, mean, rstd, *, dy=None, dy2=None, dy2_fold=0, dhead=None,
+    def _ln_bwd(self, B, T, C, x, gamma, beta, eps, mean, rstd, *, dy=None, dy2=None, dy3=None, dy2_fold=0, dhead=None,
                 head_w=None, head_scale=1.0, branch=None, drop_b=(0.0, 0), tanh=0, drop_a=(0.0, 0), lens=None,
                 relu_x=0, dx_f32=None, dact=None, dgamma=None, dbeta=None, dhead_w=None, dhead_b=None, dact_colsum=None):
         self._wait_side(dact)
@@ -356,6 +373,7 @@ class FastSpeech2(nn.Module):
         p.B, p.T, p.C = B, T, C
         p.dy = dy.data_ptr() if dy is not None else None
         p.dy2 = dy2.data_ptr() if dy2 is not None else None
+        p.dy3 = dy3.data_ptr() if dy3 is not None else None
         p.dy2_fold = dy2_fold
         p.dhead = dhead.data_ptr() if dhead is not None else None
         p.head_w = head_w.data_ptr() if head_w is not None else None
@@ -481,7 +499,9 @@ class FastSpeech2(nn.Module):
         dqkv = self._act(rows, ld)
         dF_act, dH_act = self._act(rows, D), self._act(rows, F)
         dHc = self._f32(rows, F) if h2 > 0 else None
-        dX1c, dz2, dz1, dXa = self._f32(rows, D), self._f32(rows, D), self._f32(rows, D), self._f32(rows, D)
+        dz2, dz1, dXa = self._f32(rows, D), self._f32(rows, D), self._f32(rows, D)
+        ksplit = self._dgrad_split(rows, D) if h1 > 0 else 1
+        dX1c = self._f32(ksplit, rows, D)
         dProj_act, dO_act = self._act(rows, D), self._act(rows, D)
         dy_a, dy_b = self._f32(rows, D), None
         fuse_bias = D <= 384           # bias gradients of the out-proj / FFN-2 convs come out of the LN backward kernels
@@ -506,10 +526,11 @@ class FastSpeech2(nn.Module):
                 raise NotImplementedError("fs2_b200: second FFN conv with kernel > 1 is not supported in backward")
             self._conv_wgrad(dH_act, sv.x1_act, B, T, f"{pre}.pos_ffn.0.conv.weight", f"{pre}.pos_ffn.0.conv.weight",
                              f"{pre}.pos_ffn.0.conv.bias")
-            self._conv_dgrad(dH_act, B, T, f"{pre}.pos_ffn.0.conv.weight", dX1c)
+            self._conv_dgrad(dH_act, B, T, f"{pre}.pos_ffn.0.conv.weight", dX1c, split=ksplit)
             # ---- LN1 + attention
             self._ln_bwd(B, T, D, sv.x_f32, self._P(f"{pre}.norm1.norm.weight"), self._P(f"{pre}.norm1.norm.bias"), 1e-6,
-                         sv.mean1, sv.rstd1, dy=dz2, dy2=dX1c, dy2_fold=h1, branch=sv.proj, drop_b=(p, sv.seeds[1]),
+                         sv.mean1, sv.rstd1, dy=dz2, dy2=dX1c[0], dy3=dX1c[1] if ksplit > 1 else None, dy2_fold=h1,
+                         branch=sv.proj, drop_b=(p, sv.seeds[1]),
                          dx_f32=dz1, dact=dProj_act, dgamma=self._G(f"{pre}.norm1.norm.weight"),
                          dbeta=self._G(f"{pre}.norm1.norm.bias"),
                          dact_colsum=self._G(f"{pre}.self_att.att.out_proj.bias") if fuse_bias else None)

@@ -58,6 +58,9 @@ typedef struct {
   const int* lens;         /* optional per-item valid length: rows t >= lens[b] -> 0 */
   int halo;                /* >0: mirror-write the reflect halo of this width */
   int ab_bf16;             /* operand storage: 1 = bf16, 0 = fp32 (SIMT only) */
+  long long c_split_stride; /* modes 0/1, fs2_gemm_tc: with split_k = s > 1, split i of the reduction is STORED (no atomics) to
+                              C + i * c_split_stride -- s partial results the consumer adds up (deterministic split-K for
+                              short grids; fp32 C, plain epilogue).  0: not used. */
 } Fs2Gemm;
 
 int fs2_gemm_simt(const Fs2Gemm* g, void* stream);
@@ -122,6 +125,7 @@ typedef struct {
   const unsigned long long* seed_dev;
   float* dact_colsum;   /* optional [C], accumulated (+=): column sums of `dact` over all rows = the bias gradient of the
                            GEMM that produced `branch` (saves the separate fs2_colsum pass over dact); C <= 384 only */
+  const float* dy3;     /* optional second half of dy2 (same layout, same fold): the other partial result of a split-K dgrad */
 } Fs2LnBwd;
 int fs2_ln_bwd(const Fs2LnBwd* p, void* stream);
 

@@ -162,3 +162,26 @@ def test_gemm_attention_batched(lib, path):
     assert err <= 1e-2 * dVref.abs().max().item(), f"dV {path}: {err}"
     if use_tc:
         assert lib.gemm_tc_error_flag() == 0
+
+
+@pytest.mark.parametrize("M,rows", [(600, 608), (9000, 9008)])      # single-CTA tiles / CTA-pair 256 x 384 tiles
+def test_dgrad_deterministic_split_k(lib, M, rows):
+    """c_split_stride: every split of the reduction is stored (no atomics) to its own copy of C; the copies add up to
+    the full product and two runs are bit-identical."""
+    N, K, taps = 384, 512, 9
+    A = _rand((rows, K), 1, torch.bfloat16)
+    B = _rand((K, taps * N), 2, torch.bfloat16)
+    ref = ref_gemm(1, M, N, K, taps, A.float(), B.float(), a_row_off=4, a_tap_step=-1, b_tap_step=N)
+    outs = []
+    for _ in range(2):
+        C = torch.full((2, M, N), float("nan"), device="cuda")
+        lib.gemm(mode=1, M=M, N=N, K=K, taps=taps, A=A, lda=K, a_rows=rows, a_inner=K, a_row_off=4, a_tap_step=-1,
+                 B=B, ldb=taps * N, b_rows=K, b_inner=taps * N, b_tap_step=N, Cout=C, ldc=N, c_bf16=False, ab_bf16=True,
+                 split_k=2, c_split_stride=M * N, use_tc=True)
+        torch.cuda.synchronize()
+        assert lib.gemm_tc_error_flag() == 0
+        outs.append(C)
+    assert torch.equal(outs[0], outs[1])                                      # no atomics: run-to-run identical
+    got = outs[0].double().sum(0)
+    assert (got - ref).abs().max().item() <= 2e-4 * max(ref.abs().max().item(), 1.0)
+    assert outs[0][0].abs().max() > 0 and outs[0][1].abs().max() > 0           # both halves carry a partial sum
