@@ -1169,15 +1169,22 @@ int dispatch_x1(int cfg, const CUtensorMap& ta, const CUtensorMap& tb, TcParams&
 int cfg_tile_n(int cfg) { return cfg == 0 ? 256 : cfg == 1 ? 384 : 128; }
 int cfg_bsub_rows(int mode, int cfg) { return cfg == 0 ? 128 : cfg == 1 ? (mode == 0 ? 96 : 64) : 64; }
 
-// least padded columns, ties -> wider tile
-int pick_cfg(int N) {
+// least padded columns, ties -> 256-wide (double-buffered accumulator, full-rate N = 256 MMAs); between the two widths
+// that divide N equally well (N = 1536: 256 or 384) the one with fewer persistent rounds x tile width wins -- at
+// phoneme-length row counts 17 x 4 tiles of 384 fit one round of the 74 CTA pairs where 17 x 6 tiles of 256 need two
+int pick_cfg(int N, long long m_tiles, int units) {
   int best = 2;
   long long best_pad = ((N + 127) / 128) * 128LL;
-  const int cands[2] = {1, 0};      // ties -> 256-wide (double-buffered accumulator, full-rate N = 256 MMAs)
+  const int cands[2] = {1, 0};
   for (int i = 0; i < 2; ++i) {
     const int tn = cfg_tile_n(cands[i]);
     long long pad = ((N + tn - 1) / tn) * (long long)tn;
     if (pad <= best_pad) { best_pad = pad; best = cands[i]; }
+  }
+  if (best == 0 && N % 384 == 0 && units > 0 && m_tiles > 0) {
+    const long long c256 = ((m_tiles * (N / 256) + units - 1) / units) * 256;
+    const long long c384 = ((m_tiles * (N / 384) + units - 1) / units) * 384;
+    if (c384 * 100 < c256 * 85) best = 1;      // the 384-wide tile is slower per FLOP (single accumulator buffer, N = 128 MMAs)
   }
   return best;
 }
@@ -1329,8 +1336,15 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
     }
   }
   if (use_pair) {
-    const int cfg = (g_force_cfg >= 0 && g_force_cfg <= 2) ? g_force_cfg : pick_cfg(g.N);
     const int ncta = g_use_pair == 3 ? 1 : 2;
+    if (g_num_sms == 0) {
+      int dev = 0;
+      CUDA_CHECK_RET(cudaGetDevice(&dev));
+      CUDA_CHECK_RET(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int cfg = (g_force_cfg >= 0 && g_force_cfg <= 2)
+                        ? g_force_cfg
+                        : pick_cfg(g.N, g.mode == 2 ? 0 : (g.M + BM * ncta - 1) / (BM * ncta), g_num_sms / ncta);
     CUtensorMap ta, tb;
     if (g.mode == 2) rc = make_map(g.A, g.a_inner, g.a_rows, g.batch1, g.batch2, g.lda, g.a_s1, g.a_s2, 64, BK, &ta, p.pa);
     else rc = make_map(g.A, g.a_inner, g.a_rows, g.batch1, g.batch2, g.lda, g.a_s1, g.a_s2, BK, BM, &ta, p.pa);
