@@ -126,3 +126,18 @@ def test_dp_allreduce_and_sharding_gloo_world2():
     assert res[0][1] == 3.0 and res[1][1] == 3.0                       # SUM over ranks of the flat buffer
     assert res[0][2] == res[1][2] == [float(i) for i in range(10)]      # replicas identical after broadcast
     assert res[0][3] == [0, 2, 4, 6, 8] and res[1][3] == [1, 3, 5, 7, 9]
+
+
+def test_dgrad_split_rule_follows_the_persistent_grid():
+    """FastSpeech2._dgrad_split mirrors fs2_gemm_tc's kernel choice for the k = 9 FFN dgrad: split the reduction in two
+    where two half-length rounds of the persistent grid beat one (148 CTAs / 74 CTA pairs)."""
+    pkg = importlib.import_module(PKG)
+    m = pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4, precision="bf16")
+    rows = lambda B, T: B * (T + 8)
+    assert m._dgrad_split(rows(32, 128), 384) == 2       # 68 single-CTA tiles on 148 SMs: one half-length round
+    assert m._dgrad_split(rows(32, 376), 384) == 1       # 48 pair tiles fit one round of 74 pairs: nothing to gain
+    assert m._dgrad_split(rows(32, 632), 384) == 2       # 80 pair tiles = 2 rounds -> 160 items = 3 half rounds
+    assert m._dgrad_split(rows(32, 800), 384) == 2
+    assert m._dgrad_split(rows(256, 895), 384) == 1      # long grids: quantisation is already below 15 %
+    assert m._dgrad_split(rows(32, 800), 512) == 1       # only the 384-wide FFN dgrad has the two-buffer consumer
+    assert pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4, precision="fp32")._dgrad_split(rows(32, 128), 384) == 1
