@@ -610,6 +610,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       // GEMMs are bound by the HBM traffic of their fp32 output, not by the store instruction pattern), so it is off.
       const bool q_path = kTcProbe && t_path && p.epi_transpose == 3 && (vec_f32_at || (vec_f32 && g.relu_aux == nullptr)) &&
                           (g.bias == nullptr || (((uintptr_t)g.bias) % 8 == 0));
+      if constexpr (MODE == 1) {
+        // ReLU-mask operand of this tile (the forward activation, written long ago): the epilogue warps get here while the
+        // tile's MMAs are still running, so pull this lane's row segment into L2 now instead of paying the HBM latency
+        // inside the chunk loop
+        if (g.relu_aux && g.aux_bf16 && row_ok && !er.skip) {
+          const char* ap = reinterpret_cast<const char*>((const bf16*)g.relu_aux + er.base + colbase + half * (CHUNKS_PER_HALF * 32));
+#pragma unroll
+          for (int i = 0; i < CHUNKS_PER_HALF * 64; i += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + i));
+        }
+      }
       const long long tq2 = prof ? clock64() : 0;
       if (!mbar_wait(smem_u32(&tfull_bar[as]), aph, err)) { ok = false; break; }
       const long long tq3 = prof ? clock64() : 0;
