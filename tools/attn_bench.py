@@ -1,4 +1,5 @@
-"""Fused attention kernels vs the unfused GEMM + softmax + GEMM sequence, B=32, H=2, head_dim 192 (GPU time via CUDA graph)."""
+"""Fused attention kernels vs the unfused GEMM + softmax + GEMM sequence, B=32, H=2, head_dim 192 (GPU time via CUDA graph).
+ATTN_DBG=1 prints the cycle breakdown of CTA 0; it needs a library built with `make EXTRA=-DFS2_TC_PROBE`."""
 import importlib
 import math
 import os

@@ -1,6 +1,9 @@
 """Where does a short-K GEMM launch spend its time?  Times the same (N, K) GEMM at M = r * 148 tiles-worth of rows
 for r = 1..8 rounds of the persistent tile loop: the slope is the per-tile-round cost, the intercept the per-launch
-cost (launch, TMEM alloc, pipeline fill, tail).  Also runs a null kernel chain for the bare launch gap."""
+cost (launch, TMEM alloc, pipeline fill, tail).
+GEMM_DBG=3|4 (no epilogue stores / staging without global stores) and GEMM_PROBE=1 (cycle probe of CTA 0's TMA thread, MMA
+thread and first epilogue warp) need a library built with the measurement code: `make -C .../csrc clean all EXTRA=-DFS2_TC_PROBE`
+(the product build compiles it out -- the GEMM kernels are sensitive to their instruction footprint)."""
 import importlib
 import os
 import sys
