@@ -141,3 +141,17 @@ def test_dgrad_split_rule_follows_the_persistent_grid():
     assert m._dgrad_split(rows(256, 895), 384) == 1      # long grids: quantisation is already below 15 %
     assert m._dgrad_split(rows(32, 800), 512) == 1       # only the 384-wide FFN dgrad has the two-buffer consumer
     assert pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4, precision="fp32")._dgrad_split(rows(32, 128), 384) == 1
+
+
+def test_upstream_drop_ins_refuse_cpu_inputs():
+    """8f rows: the extractor, the segment mean and the device collate have no CPU path either."""
+    pkg = importlib.import_module(PKG)
+    ext = pkg.IntensityExtractor(**dict(pkg.DEFAULT_RANK_MODEL_CONFIG, n_encoder_layers=1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ext(torch.zeros(2, 30, 82), torch.tensor([30, 10]), torch.tensor([0, 1]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.intensity_segment_mean(torch.zeros(2, 30, 5), torch.ones(2, 6, dtype=torch.long), torch.tensor([6, 6]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.DeviceCollate("cpu")([])
+    with pytest.raises(NotImplementedError):
+        pkg.IntensityExtractor(n_mels=80, n_heads=4, n_emotions=5, n_encoder_layers=1, hidden_dim=384, kernel_size=9, dropout=0.1)
