@@ -3,7 +3,7 @@ from . import _lib  # noqa: F401
 from .model import FastSpeech2  # noqa: F401
 from .loss import Loss  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
-from .intensity import get_intensity_representation, intensity_segment_mean  # noqa: F401
+from .intensity import get_intensity_representation, intensity_prototypes, intensity_segment_mean  # noqa: F401
 from .rank_model import IntensityExtractor  # noqa: F401
 from .collate import DeviceCollate  # noqa: F401
 

@@ -39,6 +39,7 @@ SIGNATURES = {
     "fs2_attn_fwd_ex": "ppiiiiiffQppppip",
     "fs2_frames_to_rows": "piiiiipip",
     "fs2_gelu": "pqip",
+    "fs2_prototype_buckets": "pppppiiiiipp",
     "fs2_collate": "pppppppppiiiipppppp" + "p",
     "fs2_intensity_head": "ppppppiiiipp",
     "fs2_attn_bwd": "pppppiiiiiffQpppp",

@@ -1304,6 +1304,41 @@ __global__ void __launch_bounds__(256) collate_kernel(const int64_t* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ prototype buckets --
+__device__ __forceinline__ long long bucket_of(long long g, long long n, int k) {
+  const long long q = n / k, rem = n % k;          // np.array_split: the first `rem` buckets hold q + 1 elements
+  const long long edge = rem * (q + 1);
+  return g < edge ? g / (q + 1) : rem + (g - edge) / q;
+}
+__global__ void __launch_bounds__(256) prototype_accum_kernel(const float* __restrict__ I, const int* __restrict__ lens,
+                                                              const int* __restrict__ group,
+                                                              const long long* __restrict__ frame_off,
+                                                              const long long* __restrict__ group_total, int Tmax, int D,
+                                                              int n_buckets, float* __restrict__ sums) {
+  pdl_wait();
+  const int i = blockIdx.x;
+  const int L = lens[i], grp = group[i];
+  const long long n = group_total[grp], f0 = frame_off[i];
+  for (int e = threadIdx.x; e < L * D; e += blockDim.x) {
+    const int t = e / D, d = e - t * D;
+    const long long b = bucket_of(f0 + t, n, n_buckets);
+    atomicAdd(sums + ((long long)grp * n_buckets + b) * D + d, I[((long long)i * Tmax + t) * D + d]);
+  }
+}
+__global__ void prototype_finalize_kernel(const long long* __restrict__ group_total, int D, int n_groups, int n_buckets,
+                                          float* __restrict__ sums) {
+  pdl_wait();
+  const long long total = (long long)n_groups * n_buckets * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long gb = e / D;
+    const int grp = (int)(gb / n_buckets), b = (int)(gb - (long long)grp * n_buckets);
+    const long long n = group_total[grp];
+    if (n == 0) continue;                                   // the reference leaves such groups at zero
+    const long long size = n / n_buckets + (b < n % n_buckets ? 1 : 0);
+    sums[e] = sums[e] / (float)size;                        // size 0 -> 0/0 = NaN, numpy's mean of an empty slice
+  }
+}
+
 #define ST ((cudaStream_t)stream)
 #define REQUIRE(cond, msg) do { if (!(cond)) { fs2_set_error(msg); return FS2_ERR_ARG; } } while (0)
 
@@ -1616,5 +1651,17 @@ extern "C" int fs2_gelu(void* x, long long n, int act_bf16, void* stream) {
   const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
   if (act_bf16) FS2_LAUNCH((gelu_kernel<bf16>), grid, 256, 0, ST, (bf16*)x, n);
   else FS2_LAUNCH((gelu_kernel<float>), grid, 256, 0, ST, (float*)x, n);
+  return fs2_check_launch();
+}
+
+extern "C" int fs2_prototype_buckets(const float* I, const int* lens, const int* group, const long long* frame_off,
+                                     const long long* group_total, int N, int Tmax, int D, int n_groups, int n_buckets,
+                                     float* sums, void* stream) {
+  REQUIRE(I && lens && group && frame_off && group_total && sums && N > 0 && D > 0 && n_groups > 0 && n_buckets > 0,
+          "fs2_prototype_buckets: bad arguments");
+  FS2_LAUNCH((prototype_accum_kernel), N, 256, 0, ST, I, lens, group, frame_off, group_total, Tmax, D, n_buckets, sums);
+  int rc = fs2_check_launch();
+  if (rc) return rc;
+  FS2_LAUNCH((prototype_finalize_kernel), 64, 256, 0, ST, group_total, D, n_groups, n_buckets, sums);
   return fs2_check_launch();
 }

@@ -35,3 +35,33 @@ def get_intensity_representation(intensity_extractor, batch, device):
     with torch.no_grad():
         I = intensity_extractor(rank_X, mel_len, emo_ids)
         return intensity_segment_mean(I.to(device), duration_tgt, phon_len, phoneme.shape[1])
+
+
+def intensity_prototypes(I, length, scores, speakers, emotions, n_spk, n_emo, bucket_size):
+    """Intensity prototype bank of `rank_model/inference.py:88-114`, on the device.
+
+    I (N, Tmax, D) frame intensities of N utterances (the extractor's output), length (N,) valid frames, scores (N,) the
+    rank model's relevance score r, speakers / emotions (N,) ids  ->  (n_spk, n_emo, bucket_size, D) fp32: per
+    (speaker, emotion) the utterances are ordered by ascending score, their valid frames concatenated, cut into
+    `bucket_size` contiguous runs (numpy.array_split) and averaged.  The reference appends to Python lists, sorts them
+    and averages numpy slices; here the host only sorts N keys and one kernel pair does the rest."""
+    if not I.is_cuda:
+        raise RuntimeError("fs2_b200: intensity_prototypes needs CUDA tensors (there is no CPU fallback)")
+    N, Tmax, D = I.shape
+    dev = I.device
+    grp = (speakers.long() * n_emo + emotions.long()).to(dev)
+    scores = scores.to(dev).double()
+    # stable sort by (group, score): python's list.sort in the reference is stable in the score as well
+    order = torch.argsort(scores, stable=True)
+    order = order[torch.argsort(grp[order], stable=True)]
+    lens = length.to(dev).long()[order]
+    g_sorted = grp[order]
+    n_groups = n_spk * n_emo
+    totals = torch.zeros(n_groups, dtype=torch.long, device=dev).index_add_(0, g_sorted, lens)
+    start = torch.cumsum(lens, 0) - lens                                   # exclusive prefix over the sorted list
+    group_start = torch.cumsum(totals, 0) - totals
+    frame_off = start - group_start[g_sorted]                              # position inside the group's frame list
+    out = torch.zeros(n_spk, n_emo, bucket_size, D, device=dev, dtype=torch.float32)
+    L.call("fs2_prototype_buckets", I.detach().float()[order].contiguous(), lens.int().contiguous(), g_sorted.int().contiguous(),
+           frame_off.contiguous(), totals.contiguous(), N, Tmax, D, n_groups, bucket_size, out)
+    return out

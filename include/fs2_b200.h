@@ -270,6 +270,16 @@ int fs2_collate(const int64_t* phon_cat, const int64_t* dur_cat, const float* me
                 int B, int Tp, int Tm, int n_mels, int64_t* phoneme, int64_t* duration, float* mel, float* pitch,
                 float* energy, float* rank_X, void* stream);
 
+/* Intensity prototype buckets (rank_model/inference.py:88-114): utterances arrive sorted by
+ * (group = speaker * n_emo + emotion, relevance score); frame t of utterance i is element frame_off[i] + t of its group's
+ * concatenated frame list, which np.array_split cuts into `n_buckets` contiguous runs (the first n % k runs one longer).
+ * sums (n_groups, n_buckets, D) must be zero on entry; the call accumulates the per-bucket sums and then divides by the
+ * bucket sizes (empty bucket -> NaN, as numpy's mean of an empty slice; groups without frames stay 0 like the reference's
+ * zero-initialised array). */
+int fs2_prototype_buckets(const float* I /*(N,Tmax,D)*/, const int* lens, const int* group, const long long* frame_off,
+                          const long long* group_total /*(n_groups)*/, int N, int Tmax, int D, int n_groups, int n_buckets,
+                          float* sums /*(n_groups,n_buckets,D)*/, void* stream);
+
 /* train.py:16-51 duration-segment mean of frame intensities ("next" row f-1) */
 int fs2_intensity_segment_mean(const float* I /*(B,Tm,D)*/, const int64_t* dur, const int64_t* phon_len,
                                int B, int Tp, int Tm, int D, float* out /*(B,Tp,D)*/, void* stream);
