@@ -8,6 +8,7 @@
 // halo rows get the reflect mirror (when `halo` > 0, width `halo`) and zeros otherwise, so GEMMs that sweep
 // whole row ranges never meet stale data.
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/fs2_b200.h"
 
@@ -105,8 +106,16 @@ __global__ void embedding_bwd_kernel(const float* dx, const int64_t* tokens, int
 }
 
 // ----------------------------------------------------------------------- LayerNorm fwd --
+// L2 prefetch of one row (C floats) of a row-major operand, one 128-byte line per lane.  The LayerNorm kernels run one
+// row per warp per iteration with two warp reductions between the loads and the stores, so a warp has nothing in flight
+// for most of an iteration; asking L2 for the warp's NEXT row while the current one is being reduced turns that
+// row's DRAM latency into an L2 hit without spending registers (fs2_ln_tune switches it off for A/B timing).
+__device__ __forceinline__ void prefetch_row_l2(const float* base, long long off, int C, int lane) {
+  if (base != nullptr && lane * 32 < C) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off + lane * 32));
+}
+
 template <typename TA>
-__global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p) {
+__global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p, int pf) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int T = p.T, C = p.C, TP = T + 2 * FS2_PAD;
@@ -141,6 +150,14 @@ __global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p) {
           z[i].x += br.x * k.x; z[i].y += br.y * k.y; z[i].z += br.z * k.z; z[i].w += br.w * k.w;
         }
         s += z[i].x + z[i].y + z[i].z + z[i].w;
+      }
+    }
+    if (pf) {
+      const long long rn = r + (long long)gridDim.x * WARPS;
+      if (rn < rows) {
+        prefetch_row_l2(p.x, rn * C, C, lane);
+        prefetch_row_l2(p.branch, rn * C, C, lane);
+        prefetch_row_l2(p.post_add, rn * C, C, lane);
       }
     }
     const float mean = warp_sum(s) * invC;
@@ -225,7 +242,7 @@ __device__ __forceinline__ void block_reduce_cols(float4 (&a)[NV], float* out, i
 // ReLU-of-x or the dropout AFTER the norm; the FFT-block LayerNorms (24 of the ~30 calls per step) run the HEAD = false
 // instantiation in which all of that is compiled out (3.2 k -> ~1.6 k instructions per kernel).
 template <typename TA, int NV, bool HEAD>
-__global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_kernel(Fs2LnBwd p) {
+__global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_kernel(Fs2LnBwd p, int pf) {
   pdl_wait();
   __shared__ float red[WARPS][128];
   // dgamma / dbeta partial sums live in shared memory, one private slab per warp (a lane only ever touches its own
@@ -331,6 +348,16 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
         s2 += g.x * h.x + g.y * h.y + g.z * h.z + g.w * h.w;
         xh[i] = h;
         gx[i] = g;
+      }
+    }
+    if (pf) {
+      const long long rn = r + (long long)gridDim.x * WARPS;
+      if (rn < rows) {
+        prefetch_row_l2(p.x, rn * C, C, lane);
+        prefetch_row_l2(p.branch, rn * C, C, lane);
+        prefetch_row_l2(p.dy, rn * C, C, lane);
+        prefetch_row_l2(p.dy2, rn * C, C, lane);
+        prefetch_row_l2(p.dy3, rn * C, C, lane);
       }
     }
     if (HEAD && p.head_w && lane == 0) dhb += dh;
@@ -891,6 +918,79 @@ __global__ void __launch_bounds__(THREADS) lr_expand_kernel(const float* __restr
   }
 }
 
+// Plain fp32 expansion (no pos-enc, no bf16 copy: BASELINE configs[1], the standalone LengthRegulator) on the bulk-copy
+// engine.  One thread per output row, ROWS rows of one item per CTA.  The first row of every phoneme run inside the CTA
+// ("leader") pulls the phoneme's D floats into its shared-memory slot with one cp.async.bulk (global -> shared,
+// completion on an mbarrier), then every row pushes its run's slot -- or a zeroed slot for rows past the item's length
+// -- to global memory with one cp.async.bulk (shared -> global).  Source rows are read once per CTA instead of once per
+// frame, no data passes through registers, and a CTA keeps ROWS * D * 4 bytes of stores in flight from ~10 instructions
+// per row.  Same bytes out as lr_expand_kernel (bit-exact copy), same frame2ph map.
+__device__ __forceinline__ uint32_t lrb_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int ROWS>
+__global__ void __launch_bounds__(ROWS) lr_expand_bulk_kernel(const float* __restrict__ in, int in_pitch, int in_off,
+                                                              const int* __restrict__ ends, const int* __restrict__ mel_lens,
+                                                              int B, int Tp, int Tm, int D, float* __restrict__ of,
+                                                              int out_pitch, int out_off, int* __restrict__ frame2ph) {
+  pdl_wait();
+  extern __shared__ __align__(128) unsigned char lrb_raw[];
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(lrb_raw);                 // 16 bytes reserved
+  float* zero_row = reinterpret_cast<float*>(lrb_raw + 16);
+  unsigned char* slots = lrb_raw + 16 + row_bytes;
+  int* s_ends = reinterpret_cast<int*>(slots + (size_t)ROWS * row_bytes);
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const uint32_t bar_a = lrb_smem(bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(ROWS) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < Tp; i += ROWS) s_ends[i] = ends[(long long)b * Tp + i];
+  for (int i = tid; i < D; i += ROWS) zero_row[i] = 0.f;
+  const int mel_len = mel_lens[b];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // zero_row (generic stores) -> bulk-copy engine
+  __syncthreads();
+  const int total = min(min(mel_len, Tm), s_ends[Tp - 1]);
+  const int r_cta = blockIdx.x * ROWS;
+  const int r = r_cta + tid;
+  const int f = r - out_off;
+  const bool exists = r < out_pitch;
+  const int idx = exists ? lr_search(s_ends, Tp, f, total) : -1;
+  if (frame2ph && exists && f >= 0 && f < Tm) frame2ph[(long long)b * Tm + f] = idx;
+  int slot = -1;
+  if (idx >= 0) {
+    const int start = idx > 0 ? s_ends[idx - 1] : 0;                    // first frame of phoneme idx
+    slot = max(start + out_off, r_cta) - r_cta;                         // its first row inside this CTA
+  }
+  if (slot == tid) {                                                    // leader: fetch the phoneme row
+    const float* src = in + ((long long)b * in_pitch + in_off + idx) * D;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(row_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(lrb_smem(slots + (size_t)tid * row_bytes)), "l"(src), "r"(row_bytes), "r"(bar_a)
+                 : "memory");
+  } else {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
+  }
+  if (!exists) return;                                                  // (arrived above; issues no store)
+  {
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(bar_a), "r"(0u) : "memory");
+      if (ok) break;
+      if (++spins > (1u << 22)) __trap();                               // a protocol bug must not hang the GPU
+    }
+  }
+  const uint32_t src_s = idx >= 0 ? lrb_smem(slots + (size_t)slot * row_bytes) : lrb_smem(zero_row);
+  float* dst = of + ((long long)b * out_pitch + r) * D;
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_s), "r"(row_bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // shared memory must outlive the engine's reads
+}
+
 // backward of the expansion = per-phoneme sums over its frames.  Frame-parallel (a phoneme-parallel kernel waits on
 // its longest segment): every warp reads LR_RPW consecutive frame rows, merges neighbours that belong to the same
 // phoneme in registers and flushes each run with one 16-byte vector atomic.  dphon must be zero on entry.
@@ -946,6 +1046,7 @@ __global__ void __launch_bounds__(THREADS) lr_bwd_kernel(const float* __restrict
 }
 
 int g_lr_rb = 4;      // rows in flight per warp in lr_expand / lr_bwd: 2, 4 or 8 (fs2_lr_tune)
+int g_lr_bulk = 8;    // rows per CTA of lr_expand_bulk_kernel: 8 ... 128 (8 measured best on B200: 82 % of the HBM peak); 0 = SIMT kernel (fs2_lr_bulk_rows)
 
 // -------------------------------------------------------------------- row-space utilities --
 template <typename TA>
@@ -1361,13 +1462,28 @@ extern "C" int fs2_embedding_bwd(const float* dx, const int64_t* tokens, int B, 
   return fs2_check_launch();
 }
 
+// L2 prefetch of a warp's next row in ln_fwd / ln_bwd: on unless FS2_LN_PREFETCH=0 (whole-step A/B) or fs2_ln_tune(0)
+int g_ln_prefetch = [] { const char* e = getenv("FS2_LN_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
+
+// resident waves of CTAs the LayerNorm grids are capped at (FS2_LN_WAVES = 1 or 2; fewer, longer-lived CTAs prefetch a
+// larger share of their rows and flush fewer partial parameter gradients)
+int g_ln_waves = [] { const char* e = getenv("FS2_LN_WAVES"); return (e && e[0] == '1') ? 1 : 2; }();
+
+/* measurement hook: next-row L2 prefetch in the LayerNorm kernels on (1, default) / off (0) */
+extern "C" int fs2_ln_tune(int prefetch) {
+  g_ln_prefetch = prefetch ? 1 : 0;
+  return FS2_OK;
+}
+
 extern "C" int fs2_ln_fwd(const Fs2LnFwd* p, void* stream) {
   REQUIRE(p && p->x && p->gamma && p->beta, "fs2_ln_fwd: null pointer");
   REQUIRE(p->C % 4 == 0 && p->C <= 128 * MAXV, "fs2_ln_fwd: C must be a multiple of 4 and <= 512");
   REQUIRE(p->halo <= FS2_PAD && (p->halo == 0 || p->T > p->halo), "fs2_ln_fwd: halo too wide for T");
   const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
-  if (p->act_bf16) FS2_LAUNCH((ln_fwd_kernel<bf16>), grid_for_rows(rows), THREADS, 0, ST, *p);
-  else FS2_LAUNCH((ln_fwd_kernel<float>), grid_for_rows(rows), THREADS, 0, ST, *p);
+  int grid = grid_for_rows(rows);
+  if (grid > 148 * 4 * g_ln_waves) grid = 148 * 4 * g_ln_waves;   // four resident CTAs per SM (<= 64 registers)
+  if (p->act_bf16) FS2_LAUNCH((ln_fwd_kernel<bf16>), grid, THREADS, 0, ST, *p, g_ln_prefetch);
+  else FS2_LAUNCH((ln_fwd_kernel<float>), grid, THREADS, 0, ST, *p, g_ln_prefetch);
   return fs2_check_launch();
 }
 
@@ -1377,12 +1493,12 @@ extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
   REQUIRE(p->dact_colsum == nullptr || (p->C <= 384 && p->dact != nullptr), "fs2_ln_bwd: dact_colsum needs dact and C <= 384");
   const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
   int grid = grid_for_rows(rows);
-  if (grid > 148 * 6) grid = 148 * 6;      // two waves of three resident CTAs per SM
+  if (grid > 148 * 3 * g_ln_waves) grid = 148 * 3 * g_ln_waves;      // waves of three resident CTAs per SM
   const int nv = (p->C + 127) / 128;
   // "head" selects the general instantiation: the 384 -> 1 head, tanh, ReLU-of-x or dropout after the norm
   const bool head = p->head_w != nullptr || p->dhead_w != nullptr || p->dhead_b != nullptr || p->tanh_act || p->relu_x ||
                     p->drop_a_p > 0.f;
-#define LN_BWD_LAUNCH(TA, NV, HEAD) FS2_LAUNCH((ln_bwd_kernel<TA, NV, HEAD>), grid, THREADS, 0, ST, *p)
+#define LN_BWD_LAUNCH(TA, NV, HEAD) FS2_LAUNCH((ln_bwd_kernel<TA, NV, HEAD>), grid, THREADS, 0, ST, *p, g_ln_prefetch)
 #define LN_BWD_NV(TA, NV) do { if (head) LN_BWD_LAUNCH(TA, NV, true); else LN_BWD_LAUNCH(TA, NV, false); } while (0)
 #define LN_BWD_TA(TA) do { if (nv == 1) LN_BWD_NV(TA, 1); else if (nv == 2) LN_BWD_NV(TA, 2); else if (nv == 3) LN_BWD_NV(TA, 3); else LN_BWD_NV(TA, 4); } while (0)
   if (p->act_bf16) LN_BWD_TA(bf16);
@@ -1494,6 +1610,26 @@ extern "C" int fs2_lr_expand(const float* in, int in_pitch, int in_off, const in
                              int out_pitch, int out_off, int* frame2ph, void* stream) {
   REQUIRE(in && ends && mel_lens && D % 4 == 0, "fs2_lr_expand: bad arguments");
   REQUIRE(B > 0 && B <= 65535 && Tp > 0 && Tp <= 12000 && out_pitch > 0, "fs2_lr_expand: B <= 65535 and 0 < Tp <= 12000 (prefix sums are staged in shared memory)");
+  // plain fp32 copy form -> bulk-copy engine kernel (rows and bases must be 16-byte aligned, slots must fit in smem)
+  if (g_lr_bulk && !pe && !out_act && out_f32 && (((uintptr_t)in | (uintptr_t)out_f32) & 15) == 0) {
+    const size_t smb = 16 + (size_t)(g_lr_bulk + 1) * D * 4 + (size_t)Tp * sizeof(int);
+    if (smb <= 200 * 1024) {
+      const dim3 gridb((out_pitch + g_lr_bulk - 1) / g_lr_bulk, B);
+#define LR_BULK(R)                                                                                                       \
+  do {                                                                                                                   \
+    static bool smem_opt_in = false;                                                                                     \
+    if (!smem_opt_in) {                                                                                                  \
+      CUDA_CHECK_RET(cudaFuncSetAttribute(lr_expand_bulk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      smem_opt_in = true;                                                                                                \
+    }                                                                                                                    \
+    FS2_LAUNCH((lr_expand_bulk_kernel<R>), gridb, R, smb, ST, in, in_pitch, in_off, ends, mel_lens, B, Tp, Tm, D, out_f32, \
+               out_pitch, out_off, frame2ph);                                                                            \
+  } while (0)
+      if (g_lr_bulk == 8) LR_BULK(8); else if (g_lr_bulk == 16) LR_BULK(16); else if (g_lr_bulk == 32) LR_BULK(32); else if (g_lr_bulk == 128) LR_BULK(128); else if (g_lr_bulk == 64) LR_BULK(64); else LR_BULK(8);
+#undef LR_BULK
+      return fs2_check_launch();
+    }
+  }
   const dim3 grid((out_pitch + LR_ROWS - 1) / LR_ROWS, B);
   const size_t sm = (size_t)Tp * sizeof(int);
 #define LR_EXP(TA, RB) FS2_LAUNCH((lr_expand_kernel<TA, RB>), grid, THREADS, sm, ST, in, in_pitch, in_off, ends, mel_lens, pe, B, Tp, Tm, D, out_f32, (TA*)out_act, out_pitch, out_off, frame2ph)
@@ -1521,6 +1657,13 @@ extern "C" int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pit
 extern "C" int fs2_lr_tune(int rows_in_flight) {
   REQUIRE(rows_in_flight == 2 || rows_in_flight == 4 || rows_in_flight == 8, "fs2_lr_tune: 2, 4 or 8");
   g_lr_rb = rows_in_flight;
+  return FS2_OK;
+}
+
+/* measurement hook: rows per CTA (8 ... 128, default 8) of the bulk-copy-engine form of fs2_lr_expand, 0 = always the SIMT kernel */
+extern "C" int fs2_lr_bulk_rows(int rows) {
+  REQUIRE(rows == 0 || rows == 8 || rows == 16 || rows == 32 || rows == 64 || rows == 128, "fs2_lr_bulk_rows: 0, 8, 16, 32, 64 or 128");
+  g_lr_bulk = rows;
   return FS2_OK;
 }
 

@@ -128,6 +128,8 @@ typedef struct {
   const float* dy3;     /* optional second half of dy2 (same layout, same fold): the other partial result of a split-K dgrad */
 } Fs2LnBwd;
 int fs2_ln_bwd(const Fs2LnBwd* p, void* stream);
+/* measurement hook: the LayerNorm kernels ask L2 for a warp's next row while the current one is reduced (1, default) */
+int fs2_ln_tune(int prefetch);
 
 /* softmax over keys with the reference's attn_mask quirk (model.py:338-343, 414-419):
  * keys valid for (b,h) are [0, min(len[b], len[(b*H+h) % B])).  S (B*H, T, ldk) fp32 -> P (and Pd = dropout(P)
@@ -208,6 +210,10 @@ int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pitch, int f_o
                const int* mel_lens, int B, int Tp, int Tm, int D, float* dphon, int p_pitch, int p_off, void* stream);
 /* measurement hook: rows in flight per warp (2, 4 or 8) in fs2_lr_expand / fs2_lr_bwd (default 4, chosen on B200) */
 int fs2_lr_tune(int rows_in_flight);
+/* With pe == NULL and out_act == NULL (plain fp32 expansion = speechbrain upsample itself, BASELINE configs[1])
+ * fs2_lr_expand runs on the bulk-copy engine: cp.async.bulk global -> shared once per phoneme run, shared -> global
+ * once per frame, no register staging.  Measurement hook: rows per CTA of that form (8 ... 128, default 8; 0 = never use it). */
+int fs2_lr_bulk_rows(int rows);
 
 /* misc row-space utilities */
 /* out = (src + reflect-fold_p(src) + add + add2) * rowmask, zero halo */

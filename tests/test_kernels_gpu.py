@@ -40,8 +40,18 @@ def randn(*shape, seed=0):
 
 
 # ------------------------------------------------------------------------------------------ LengthRegulator
+@pytest.fixture(params=[8, 0, 16, 32, 64, 128], ids=lambda r: f"bulk{r}")
+def lr_bulk_rows(request, lib):
+    """plain fp32 expansion: bulk-copy-engine kernel at each CTA size, and the SIMT kernel (0)"""
+    raw = lib.load()
+    raw.fs2_lr_bulk_rows.argtypes = [lib.C.c_int]
+    assert raw.fs2_lr_bulk_rows(request.param) == 0
+    yield request.param
+    raw.fs2_lr_bulk_rows(8)
+
+
 @pytest.mark.parametrize("B,Tp,pace", [(2, 5, 1.0), (64, 128, 1.0), (64, 128, 0.8), (32, 128, 1.2), (3, 7, 1.0)])
-def test_length_regulator_bit_exact(lib, B, Tp, pace):
+def test_length_regulator_bit_exact(lib, lr_bulk_rows, B, Tp, pace):
     g = torch.Generator().manual_seed(B * 131 + Tp)
     dur = torch.exp(torch.randn(B, Tp, generator=g) * 0.6 + 1.6).round().clamp(0, 40).long()
     dur[torch.rand(B, Tp, generator=g) < 0.05] = 0
@@ -107,6 +117,36 @@ def test_length_regulator_with_posenc_and_padded_rows(lib):
     assert torch.equal(oa.float().cpu(), of.to(torch.bfloat16).float().cpu())
     full = of.view(B, Tm + 8, D)
     assert full[:, :PAD].abs().sum() == 0 and full[:, PAD + Tm:].abs().sum() == 0   # zero halo rows
+
+
+def test_length_regulator_plain_copy_in_padded_rows(lib, lr_bulk_rows):
+    """Plain fp32 expansion (bulk-copy-engine form) with row pitch / offset on both sides and long zero-duration runs:
+    halo rows and rows past an item's length must come out as zeros, phoneme runs straddle CTA boundaries."""
+    B, Tp, D = 5, 40, 384
+    g = torch.Generator().manual_seed(11)
+    dur = torch.randint(0, 30, (B, Tp), generator=g)
+    dur[0, 3:30] = 0
+    dur[1, 1:] = 0
+    dur[1, 0] = 200                                               # one phoneme across several CTAs
+    dur[2] = 0
+    dur[2, -1] = 7                                                # everything before the last phoneme is empty
+    feats = torch.randn(B, Tp, D, generator=g)
+    ref, lens = O.upsample(feats, dur)
+    Tm = ref.shape[1]
+    ends = torch.zeros(B, Tp, dtype=torch.int32, device="cuda")
+    ml = torch.zeros(B, dtype=torch.int32, device="cuda")
+    lib.call("fs2_lr_prepare", dur.cuda(), None, 1.0, B, Tp, ends, ml)
+    inp = pad_rows(feats.cuda())
+    of = torch.full((B * (Tm + 8), D), float("nan"), device="cuda")
+    f2p = torch.full((B, Tm), -7, dtype=torch.int32, device="cuda")
+    lib.call("fs2_lr_expand", inp, Tp + 8, PAD, ends, ml, None, B, Tp, Tm, D, of, None, 0, Tm + 8, PAD, f2p)
+    torch.cuda.synchronize()
+    assert torch.equal(unpad(of, B, Tm).cpu(), ref)
+    full = of.view(B, Tm + 8, D)
+    assert full[:, :PAD].abs().sum() == 0 and full[:, PAD + Tm:].abs().sum() == 0
+    for b in range(B):
+        m = torch.repeat_interleave(torch.arange(Tp), dur[b]).int()
+        assert torch.equal(f2p[b, : m.numel()].cpu(), m) and (f2p[b, m.numel():] == -1).all()
 
 
 def test_dur_decode_inference(lib):

@@ -100,6 +100,8 @@ def main():
     dph = [torch.zeros(B * (Tp + 8), D, device=dev) for _ in range(R)]
     lib = L.load()
     lib.fs2_lr_tune.argtypes = [L.C.c_int]
+    lib.fs2_lr_bulk_rows.argtypes = [L.C.c_int]
+    lib.fs2_lr_bulk_rows(0)                          # SIMT kernels in this loop; the bulk-copy form is swept below
     for rb in [int(x) for x in os.environ.get("LR_RB", "4").split(",")]:
         lib.fs2_lr_tune(rb)
         tag = f" [rows in flight {rb}]"
@@ -117,6 +119,15 @@ def main():
         report("lr_bwd (segment sums, B=64)" + tag, B * Tm * D * 4 + B * Tp * D * 4, us,
                "read B*Tm*D*4, write B*Tp*D*4 (+ the 13 MB memset of dphon inside the call)")
     lib.fs2_lr_tune(4)
+    # plain fp32 expansion on the bulk-copy engine (cp.async.bulk in and out of shared memory), rows per CTA swept;
+    # 0 = the SIMT kernel measured above
+    for rows in [int(x) for x in os.environ.get("LR_BULK", "0,8,16,32,64,128").split(",")]:
+        lib.fs2_lr_bulk_rows(rows)
+        us = timeit(lambda i: L.call("fs2_lr_expand", feats[i], Tp, 0, ends, mel_lens, None, B, Tp, Tm, D, outs[i], None, 0,
+                                     Tm, 0, None), R)
+        report("lr_expand fp32 (B=64,Tp=128,Tm=800,D=384)" + (f" [bulk-copy engine, {rows} rows per CTA]" if rows else " [SIMT kernel]"),
+               B * Tp * D * 4 + B * Tm * D * 4 + B * Tp * 4, us, "SURVEY 8d K10: read B*Tp*D*4 + write B*Tm*D*4")
+    lib.fs2_lr_bulk_rows(8)
     del feats, outs, of, oa, fin, df, dph
 
     # ------------------------------------------------------------------------ average_over_durations (K8)
@@ -166,18 +177,25 @@ def main():
     o16 = [torch.empty(rows, C, device=dev, dtype=torch.bfloat16) for _ in range(R4)]
     gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
-    us = timeit(lambda i: model._ln_fwd(B3, Tm3, C, xs[i], gam, bet, 1e-6, branch=brs[i], drop_b=(0.1, 11), out_f32=o32[i],
-                                        out_act=o16[i], halo=4, mean=mean, rstd=rstd), R4)
-    report("ln_fwd (residual + dropout + LN -> fp32 + bf16, B=32,Tm=800,C=384)", rows * C * (4 + 4 + 4 + 2) + rows * 8, us,
-           "read x fp32 + branch fp32, write fp32 stream + bf16 operand + mean/rstd")
+    raw = L.load()
+    raw.fs2_ln_tune.argtypes = [L.C.c_int]
+    for pf in (0, 1):                                 # next-row L2 prefetch off / on (on is the default)
+        raw.fs2_ln_tune(pf)
+        us = timeit(lambda i: model._ln_fwd(B3, Tm3, C, xs[i], gam, bet, 1e-6, branch=brs[i], drop_b=(0.1, 11), out_f32=o32[i],
+                                            out_act=o16[i], halo=4, mean=mean, rstd=rstd), R4)
+        report("ln_fwd (residual + dropout + LN -> fp32 + bf16, B=32,Tm=800,C=384)" + ("" if pf else " [no L2 prefetch]"),
+               rows * C * (4 + 4 + 4 + 2) + rows * 8, us,
+               "read x fp32 + branch fp32, write fp32 stream + bf16 operand + mean/rstd")
     dys = [torch.randn(rows, C, device=dev) for _ in range(R4)]
     dx = [torch.empty(rows, C, device=dev) for _ in range(R4)]
     da = [torch.empty(rows, C, device=dev, dtype=torch.bfloat16) for _ in range(R4)]
     dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
-    us = timeit(lambda i: model._ln_bwd(B3, Tm3, C, xs[i], gam, bet, 1e-6, mean, rstd, dy=dys[i], branch=brs[i],
-                                        drop_b=(0.1, 11), dx_f32=dx[i], dact=da[i], dgamma=dg, dbeta=db), R4)
-    report("ln_bwd (B=32,Tm=800,C=384)", rows * C * (4 + 4 + 4 + 4 + 2) + rows * 8, us,
-           "read dy fp32 + x fp32 + branch fp32, write dx fp32 + dbranch bf16")
+    for pf in (0, 1):
+        raw.fs2_ln_tune(pf)
+        us = timeit(lambda i: model._ln_bwd(B3, Tm3, C, xs[i], gam, bet, 1e-6, mean, rstd, dy=dys[i], branch=brs[i],
+                                            drop_b=(0.1, 11), dx_f32=dx[i], dact=da[i], dgamma=dg, dbeta=db), R4)
+        report("ln_bwd (B=32,Tm=800,C=384)" + ("" if pf else " [no L2 prefetch]"), rows * C * (4 + 4 + 4 + 4 + 2) + rows * 8, us,
+               "read dy fp32 + x fp32 + branch fp32, write dx fp32 + dbranch bf16")
     cs = torch.zeros(1536, device=dev)
     big = [torch.randn(rows, 1536, device=dev).bfloat16() for _ in range(3)]
     us = timeit(lambda i: L.call("fs2_colsum", big[i], 1, rows, 1536, 1536, cs), 3)
