@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p, int pf) {
   TA* oa = (TA*)p.out_act;
   const unsigned long long bump = p.seed_dev ? mix64(*p.seed_dev) : 0ull;
   const DropCfg db{p.drop_b_p, p.drop_b_seed ^ bump}, da{p.drop_a_p, p.drop_a_seed ^ bump};
+  int pf_first = 1;                                           // the first live row also asks for the rows in between
   for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
     int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
     const long long ro = r * C;
@@ -152,14 +153,15 @@ __global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p, int pf) {
         s += z[i].x + z[i].y + z[i].z + z[i].w;
       }
     }
-    if (pf) {
-      const long long rn = r + (long long)gridDim.x * WARPS;
+    for (int k = pf_first; k <= pf; ++k) {                    // pf = prefetch distance in rows of this warp (0 = off)
+      const long long rn = r + (long long)k * gridDim.x * WARPS;
       if (rn < rows) {
         prefetch_row_l2(p.x, rn * C, C, lane);
         prefetch_row_l2(p.branch, rn * C, C, lane);
         prefetch_row_l2(p.post_add, rn * C, C, lane);
       }
     }
+    pf_first = pf;
     const float mean = warp_sum(s) * invC;
     float q = 0.f;
 #pragma unroll
@@ -270,6 +272,7 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
 #pragma unroll
   for (int i = 0; i < (HEAD ? NV : 1); ++i) dhw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float dhb = 0.f;
+  int pf_first = 1;
   for (long long r = (long long)blockIdx.x * WARPS + warp; r < rows; r += (long long)gridDim.x * WARPS) {
     int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
     const long long ro = r * C;
@@ -350,8 +353,8 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
         gx[i] = g;
       }
     }
-    if (pf) {
-      const long long rn = r + (long long)gridDim.x * WARPS;
+    for (int k = pf_first; k <= pf; ++k) {                    // pf = prefetch distance in rows of this warp (0 = off)
+      const long long rn = r + (long long)k * gridDim.x * WARPS;
       if (rn < rows) {
         prefetch_row_l2(p.x, rn * C, C, lane);
         prefetch_row_l2(p.branch, rn * C, C, lane);
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
         prefetch_row_l2(p.dy3, rn * C, C, lane);
       }
     }
+    pf_first = pf;
     if (HEAD && p.head_w && lane == 0) dhb += dh;
     s1 = warp_sum(s1) * invC;
     s2 = warp_sum(s2) * invC;
@@ -991,6 +995,11 @@ __global__ void __launch_bounds__(ROWS) lr_expand_bulk_kernel(const float* __res
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // shared memory must outlive the engine's reads
 }
 
+// (The fused form the model uses -- pos-enc add, fp32 + bf16 outputs -- was also tried on this engine: bulk loads of the
+// phoneme rows and the pos-enc slice, the add in shared memory, one bulk store per output tile.  Bit-exact, but 34.6 us
+// at 8 rows per CTA and 52.1 us at 16 against 27.6 us for lr_expand_kernel at batch 64: the load -> add -> fence ->
+// store chain inside one short-lived CTA costs more than the engine saves.  It stays on lr_expand_kernel.)
+
 // backward of the expansion = per-phoneme sums over its frames.  Frame-parallel (a phoneme-parallel kernel waits on
 // its longest segment): every warp reads LR_RPW consecutive frame rows, merges neighbours that belong to the same
 // phoneme in registers and flushes each run with one 16-byte vector atomic.  dphon must be zero on entry.
@@ -1463,15 +1472,18 @@ extern "C" int fs2_embedding_bwd(const float* dx, const int64_t* tokens, int B, 
 }
 
 // L2 prefetch of a warp's next row in ln_fwd / ln_bwd: on unless FS2_LN_PREFETCH=0 (whole-step A/B) or fs2_ln_tune(0)
-int g_ln_prefetch = [] { const char* e = getenv("FS2_LN_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
+int g_ln_prefetch = [] { const char* e = getenv("FS2_LN_PREFETCH"); return (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 1; }();
 
-// resident waves of CTAs the LayerNorm grids are capped at (FS2_LN_WAVES = 1 or 2; fewer, longer-lived CTAs prefetch a
-// larger share of their rows and flush fewer partial parameter gradients)
-int g_ln_waves = [] { const char* e = getenv("FS2_LN_WAVES"); return (e && e[0] == '1') ? 1 : 2; }();
+// resident waves of CTAs the LayerNorm grids are capped at.  Measured on B200 (profiles/r01_summary.md section 5): the
+// backward is fastest as ONE wave of long-lived CTAs (a warp prefetches 6 of its 7 rows, a third of the partial
+// parameter-gradient flushes), the forward as two.  FS2_LN_WAVES=1|2 forces both for A/B runs.
+int g_ln_waves_env = [] { const char* e = getenv("FS2_LN_WAVES"); return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }();
+int g_ln_fwd_waves = g_ln_waves_env ? g_ln_waves_env : 2;
+int g_ln_bwd_waves = g_ln_waves_env ? g_ln_waves_env : 1;
 
 /* measurement hook: next-row L2 prefetch in the LayerNorm kernels on (1, default) / off (0) */
 extern "C" int fs2_ln_tune(int prefetch) {
-  g_ln_prefetch = prefetch ? 1 : 0;
+  g_ln_prefetch = prefetch < 0 ? 0 : (prefetch > 4 ? 4 : prefetch);   // distance in rows of a warp
   return FS2_OK;
 }
 
@@ -1481,7 +1493,7 @@ extern "C" int fs2_ln_fwd(const Fs2LnFwd* p, void* stream) {
   REQUIRE(p->halo <= FS2_PAD && (p->halo == 0 || p->T > p->halo), "fs2_ln_fwd: halo too wide for T");
   const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
   int grid = grid_for_rows(rows);
-  if (grid > 148 * 4 * g_ln_waves) grid = 148 * 4 * g_ln_waves;   // four resident CTAs per SM (<= 64 registers)
+  if (grid > 148 * 4 * g_ln_fwd_waves) grid = 148 * 4 * g_ln_fwd_waves;   // four resident CTAs per SM (<= 64 registers)
   if (p->act_bf16) FS2_LAUNCH((ln_fwd_kernel<bf16>), grid, THREADS, 0, ST, *p, g_ln_prefetch);
   else FS2_LAUNCH((ln_fwd_kernel<float>), grid, THREADS, 0, ST, *p, g_ln_prefetch);
   return fs2_check_launch();
@@ -1492,12 +1504,14 @@ extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
   REQUIRE(p->C % 4 == 0 && p->C <= 128 * MAXV, "fs2_ln_bwd: C must be a multiple of 4 and <= 512");
   REQUIRE(p->dact_colsum == nullptr || (p->C <= 384 && p->dact != nullptr), "fs2_ln_bwd: dact_colsum needs dact and C <= 384");
   const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);
-  int grid = grid_for_rows(rows);
-  if (grid > 148 * 3 * g_ln_waves) grid = 148 * 3 * g_ln_waves;      // waves of three resident CTAs per SM
   const int nv = (p->C + 127) / 128;
   // "head" selects the general instantiation: the 384 -> 1 head, tanh, ReLU-of-x or dropout after the norm
   const bool head = p->head_w != nullptr || p->dhead_w != nullptr || p->dhead_b != nullptr || p->tanh_act || p->relu_x ||
                     p->drop_a_p > 0.f;
+  int grid = grid_for_rows(rows);
+  // FFT-block instantiation: waves of three resident CTAs per SM; the general one (two per SM) keeps its 148 * 6 cap
+  const int cap = (nv <= 3 && !head) ? 148 * 3 * g_ln_bwd_waves : 148 * 6;
+  if (grid > cap) grid = cap;
 #define LN_BWD_LAUNCH(TA, NV, HEAD) FS2_LAUNCH((ln_bwd_kernel<TA, NV, HEAD>), grid, THREADS, 0, ST, *p, g_ln_prefetch)
 #define LN_BWD_NV(TA, NV) do { if (head) LN_BWD_LAUNCH(TA, NV, true); else LN_BWD_LAUNCH(TA, NV, false); } while (0)
 #define LN_BWD_TA(TA) do { if (nv == 1) LN_BWD_NV(TA, 1); else if (nv == 2) LN_BWD_NV(TA, 2); else if (nv == 3) LN_BWD_NV(TA, 3); else LN_BWD_NV(TA, 4); } while (0)

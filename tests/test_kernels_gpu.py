@@ -94,12 +94,17 @@ def test_length_regulator_bit_exact(lib, lr_bulk_rows, B, Tp, pace):
     assert (dph.double().cpu() - ref_b).abs().max() <= 1e-4       # fp32 sums of <= 48 terms
 
 
-def test_length_regulator_with_posenc_and_padded_rows(lib):
+@pytest.mark.parametrize("B,Tp,maxd", [(4, 9, 6), (6, 61, 24)])
+def test_length_regulator_with_posenc_and_padded_rows(lib, B, Tp, maxd):
     """The fused form the model uses: padded row space in/out, + decoder pos-enc, bf16 operand copy."""
-    B, Tp, D = 4, 9, 384
-    g = torch.Generator().manual_seed(3)
-    dur = torch.randint(0, 6, (B, Tp), generator=g)
+    D = 384
+    g = torch.Generator().manual_seed(3 + Tp)
+    dur = torch.randint(0, maxd, (B, Tp), generator=g)
     dur[:, 0] += 1
+    if B > 4:
+        dur[1, 2:] = 0                               # a short utterance: most of its rows are zero rows
+        dur[2, 1:40] = 0                             # a long run of empty phonemes
+        dur[3, 5] = 70                               # one phoneme across many CTAs
     feats = torch.randn(B, Tp, D, generator=g)
     pe = O.PositionalEncoding(D).pe[0]
     ref, lens = O.upsample(feats, dur)

@@ -179,22 +179,23 @@ def main():
     mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
     raw = L.load()
     raw.fs2_ln_tune.argtypes = [L.C.c_int]
-    for pf in (0, 1):                                 # next-row L2 prefetch off / on (on is the default)
+    PFS = [int(x) for x in os.environ.get("LN_PF", "0,1").split(",")]   # L2 prefetch distance in rows of a warp (default 1)
+    for pf in PFS:
         raw.fs2_ln_tune(pf)
         us = timeit(lambda i: model._ln_fwd(B3, Tm3, C, xs[i], gam, bet, 1e-6, branch=brs[i], drop_b=(0.1, 11), out_f32=o32[i],
                                             out_act=o16[i], halo=4, mean=mean, rstd=rstd), R4)
-        report("ln_fwd (residual + dropout + LN -> fp32 + bf16, B=32,Tm=800,C=384)" + ("" if pf else " [no L2 prefetch]"),
+        report("ln_fwd (residual + dropout + LN -> fp32 + bf16, B=32,Tm=800,C=384)" + (f" [L2 prefetch distance {pf}]" if pf else " [no L2 prefetch]"),
                rows * C * (4 + 4 + 4 + 2) + rows * 8, us,
                "read x fp32 + branch fp32, write fp32 stream + bf16 operand + mean/rstd")
     dys = [torch.randn(rows, C, device=dev) for _ in range(R4)]
     dx = [torch.empty(rows, C, device=dev) for _ in range(R4)]
     da = [torch.empty(rows, C, device=dev, dtype=torch.bfloat16) for _ in range(R4)]
     dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
-    for pf in (0, 1):
+    for pf in PFS:
         raw.fs2_ln_tune(pf)
         us = timeit(lambda i: model._ln_bwd(B3, Tm3, C, xs[i], gam, bet, 1e-6, mean, rstd, dy=dys[i], branch=brs[i],
                                             drop_b=(0.1, 11), dx_f32=dx[i], dact=da[i], dgamma=dg, dbeta=db), R4)
-        report("ln_bwd (B=32,Tm=800,C=384)" + ("" if pf else " [no L2 prefetch]"), rows * C * (4 + 4 + 4 + 4 + 2) + rows * 8, us,
+        report("ln_bwd (B=32,Tm=800,C=384)" + (f" [L2 prefetch distance {pf}]" if pf else " [no L2 prefetch]"), rows * C * (4 + 4 + 4 + 4 + 2) + rows * 8, us,
                "read dy fp32 + x fp32 + branch fp32, write dx fp32 + dbranch bf16")
     cs = torch.zeros(1536, device=dev)
     big = [torch.randn(rows, 1536, device=dev).bfloat16() for _ in range(3)]
