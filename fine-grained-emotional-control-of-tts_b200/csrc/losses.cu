@@ -145,17 +145,37 @@ __global__ void __launch_bounds__(512) ssim_minmax_kernel(const float* pred, con
   const float* t = tgt + (long long)b * Tm * W;
   unsigned long long kmin = ~0ull, kmax = 0ull;
   float tmn = INFINITY, tmx = -INFINITY;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    float v = p[i];
-    unsigned o = orderable(v);
-    unsigned long long k1 = ((unsigned long long)o << 32) | (unsigned)i;
-    unsigned long long k2 = ((unsigned long long)o << 32) | (unsigned)(~(unsigned)i);
+  auto take = [&](float v, float tv, unsigned i) {
+    const unsigned o = orderable(v);
+    const unsigned long long k1 = ((unsigned long long)o << 32) | i;
+    const unsigned long long k2 = ((unsigned long long)o << 32) | (unsigned)(~i);
     kmin = k1 < kmin ? k1 : kmin;
     kmax = k2 > kmax ? k2 : kmax;
-    float tv = t[i];
     tmn = fminf(tmn, tv);
     tmx = fmaxf(tmx, tv);
+  };
+  long long done = 0;
+  if ((((uintptr_t)p | (uintptr_t)t) & 15) == 0) {
+    // 16-byte loads, two per operand in flight (one CTA per sample: the scalar loop was bound by load latency);
+    // the (value, index) keys make the result independent of the visiting order
+    const long long n4 = n >> 2;
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    const float4* t4 = reinterpret_cast<const float4*>(t);
+    long long i = threadIdx.x;
+    for (; i + blockDim.x < n4; i += 2 * blockDim.x) {
+      const float4 a = p4[i], b2 = p4[i + blockDim.x], c = t4[i], d = t4[i + blockDim.x];
+      const unsigned e = (unsigned)(4 * i), g = (unsigned)(4 * (i + blockDim.x));
+      take(a.x, c.x, e); take(a.y, c.y, e + 1); take(a.z, c.z, e + 2); take(a.w, c.w, e + 3);
+      take(b2.x, d.x, g); take(b2.y, d.y, g + 1); take(b2.z, d.z, g + 2); take(b2.w, d.w, g + 3);
+    }
+    if (i < n4) {
+      const float4 a = p4[i], c = t4[i];
+      const unsigned e = (unsigned)(4 * i);
+      take(a.x, c.x, e); take(a.y, c.y, e + 1); take(a.z, c.z, e + 2); take(a.w, c.w, e + 3);
+    }
+    done = n4 << 2;
   }
+  for (long long i = done + threadIdx.x; i < n; i += blockDim.x) take(p[i], t[i], (unsigned)i);
   for (int o = 16; o > 0; o >>= 1) {
     unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), c = __shfl_xor_sync(0xffffffffu, kmax, o);
     kmin = a < kmin ? a : kmin;
