@@ -128,7 +128,8 @@ typedef struct {
   const float* dy3;     /* optional second half of dy2 (same layout, same fold): the other partial result of a split-K dgrad */
 } Fs2LnBwd;
 int fs2_ln_bwd(const Fs2LnBwd* p, void* stream);
-/* measurement hook: the LayerNorm kernels ask L2 for a warp's next row while the current one is reduced (1, default) */
+/* measurement hook: the LayerNorm kernels ask L2 for a warp's next row while the current one is reduced; `prefetch` =
+ * distance in rows of a warp, 0 (off) .. 4, default 1 (measured best on B200; FS2_LN_PREFETCH sets it at load time) */
 int fs2_ln_tune(int prefetch);
 
 /* softmax over keys with the reference's attn_mask quirk (model.py:338-343, 414-419):
