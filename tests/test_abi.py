@@ -77,3 +77,16 @@ def test_no_cpu_fallback(built):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(tok, torch.zeros(2, dtype=torch.long), torch.ones(2, 8, dtype=torch.long), torch.zeros(2, 8), torch.zeros(2, 8),
           intensity=torch.zeros(2, 8, 5))
+
+
+def test_measurement_hooks_validate_their_arguments(built):
+    """The kernel-selection hooks are host-only state setters: bad values return a non-zero status, good ones 0."""
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for fn in (lib.fs2_lr_bulk_rows, lib.fs2_lr_tune, lib.fs2_ln_tune):
+        fn.argtypes = [ctypes.c_int]
+        fn.restype = ctypes.c_int
+    assert lib.fs2_lr_bulk_rows(7) != 0 and lib.fs2_lr_bulk_rows(256) != 0
+    for rows in (0, 16, 32, 64, 128, 8):             # ends on the default
+        assert lib.fs2_lr_bulk_rows(rows) == 0
+    assert lib.fs2_lr_tune(3) != 0 and lib.fs2_lr_tune(4) == 0
+    assert lib.fs2_ln_tune(0) == 0 and lib.fs2_ln_tune(1) == 0
