@@ -22,7 +22,13 @@ stock torch op exactly as in speechbrain, so the oracle's arithmetic *is*
 torch's.  The pins that do exist are (a) the shape doctest in model.py:102-146
 and (b) the reference's own call sites; both are exercised in
 `tests/test_oracle.py`, and seeded outputs of this oracle are frozen under
-`tests/golden/` by `tests/golden/make_golden.py`.
+`tests/golden/` by `tests/golden/make_golden.py`.  In addition the glue half
+of this file (class FastSpeech2, class Loss) IS pinned: `tests/reference_glue.py`
+executes the reference's model.py / loss.py unmodified with the leaf classes
+below standing in for speechbrain, and `tests/test_reference_glue.py` requires
+the same state_dict (keys, order, seeded init), outputs, losses and gradients.
+The leaves stay unpinned; `tests/test_oracle_first_principles.py` re-derives
+each of them in numpy float64 from the published definitions.
 
 state_dict layout is key-for-key the reference's.
 """

@@ -1,4 +1,4 @@
-"""Generates tests/golden/*.pt from the oracle (oracle/fs2_oracle.py), in this container.
+"""Generates tests/golden/{docstring_case,synthetic_b4}.pt from the oracle (oracle/fs2_oracle.py), in this container.
 
 The reference itself cannot be imported (its arithmetic lives in speechbrain, which is absent and un-pinned:
 SURVEY.md 8c), so these vectors freeze the ORACLE's outputs on seeded inputs; the known-answer cases that the

@@ -1,0 +1,89 @@
+"""Runs the REAL reference glue -- emo_rank_tts/fastspeech2/model.py (FastSpeech2.__init__ / forward, model.py:149-441)
+and fastspeech2/loss.py (Loss, loss.py:6-186) -- from where it lies under /root/reference, with the speechbrain leaf
+symbols it imports (model.py:13-27, loss.py:3) supplied by the oracle's restatements.
+
+speechbrain itself is absent from this image, so the leaves stay a restatement; but everything the
+reference's own files do -- module construction and naming (hence the state_dict layout), the mask quirk, the
+conditioning cat/projection, the variance adaptor order, the loss slicing and weighting -- is then the reference's
+code, executed unmodified, and the oracle's FastSpeech2 / Loss glue can be checked against it instead of against a
+reading of it.  Test infrastructure only (imports oracle/); needs /root/reference, i.e. the build container.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import fs2_oracle as O  # noqa: E402
+
+REF_DIR = "/root/reference/emo_rank_tts/fastspeech2"
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_DIR, "model.py")) and os.path.isfile(os.path.join(REF_DIR, "loss.py"))
+
+
+class _Conv1d(O.SBConv1d):
+    """speechbrain.nnet.CNN.Conv1d call signature (model.py:226-240)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, padding="same", skip_transpose=False):
+        assert padding == "same"
+        super().__init__(in_channels, out_channels, kernel_size, skip_transpose=skip_transpose)
+
+
+class _TransformerEncoder(O.TransformerEncoder):
+    """speechbrain TransformerEncoder call signature (model.py:241-267)."""
+
+    def __init__(self, num_layers, nhead, d_ffn, d_model=None, kdim=None, vdim=None, dropout=0.0, activation=nn.ReLU,
+                 normalize_before=False, ffn_type="regularFFN", ffn_cnn_kernel_size_list=(3, 3)):
+        assert activation is nn.ReLU and ffn_type == "1dcnn"
+        super().__init__(num_layers, nhead, d_ffn, d_model, kdim, vdim, dropout, normalize_before,
+                         list(ffn_cnn_kernel_size_list))
+
+
+def _stub_modules():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        return m
+
+    cnn = mod("speechbrain.nnet.CNN", Conv1d=_Conv1d)
+    lin = mod("speechbrain.nnet.linear", Linear=O.SBLinear)
+    emb = mod("speechbrain.nnet.embedding", Embedding=O.SBEmbedding)
+    nnet = mod("speechbrain.nnet", CNN=cnn, linear=lin, embedding=emb)
+    tr = mod("speechbrain.lobes.models.transformer.Transformer", PositionalEncoding=O.PositionalEncoding,
+             TransformerEncoder=_TransformerEncoder, get_key_padding_mask=O.get_key_padding_mask,
+             get_mask_from_lengths=O.get_mask_from_lengths)
+    trp = mod("speechbrain.lobes.models.transformer", Transformer=tr)
+    fs2 = mod("speechbrain.lobes.models.FastSpeech2", EncoderPreNet=O.EncoderPreNet,
+              DurationPredictor=O.DurationPredictor, PostNet=O.PostNet, upsample=O.upsample,
+              average_over_durations=O.average_over_durations, SSIMLoss=O.SSIMLoss)
+    models = mod("speechbrain.lobes.models", transformer=trp, FastSpeech2=fs2)
+    lobes = mod("speechbrain.lobes", models=models)
+    sb = mod("speechbrain", nnet=nnet, lobes=lobes)
+    return {m.__name__: m for m in (sb, nnet, cnn, lin, emb, lobes, models, trp, tr, fs2)}
+
+
+def load():
+    """-> (reference FastSpeech2 class, reference Loss class), executed from /root/reference with stubbed leaves."""
+    assert available(), "the reference tree is not mounted"
+    stubs = _stub_modules()
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        out = []
+        for fname, alias in (("model.py", "_ref_fs2_model"), ("loss.py", "_ref_fs2_loss")):
+            spec = importlib.util.spec_from_file_location(alias, os.path.join(REF_DIR, fname))
+            m = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(m)
+            out.append(m)
+    finally:
+        for k, v in saved.items():                       # speechbrain must not appear importable to anything else
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return out[0].FastSpeech2, out[1].Loss
