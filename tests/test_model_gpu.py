@@ -85,6 +85,14 @@ def test_forward_loss_backward_vs_oracle_and_golden(pkg, lib, oracle64, case, pr
     tol_loss = 1e-5 if precision == "fp32" else 5e-3
     for k, v in g["losses"].items():
         assert abs(float(losses[k]) - v) <= tol_loss * max(1.0, abs(v)), (k, float(losses[k]), v)
+    # the same case through the reference's OWN model.py / loss.py (speechbrain leaves = oracle restatements), frozen by
+    # tests/golden/make_glue_golden.py: fp64 forward, and the fp32 loss dict the reference's Loss returns
+    rg = torch.load(os.path.join(GOLD, "reference_glue.pt"))[case]
+    assert torch.equal(preds[7], rg["fwd64"]["mel_lens"])
+    for n, a, ref in zip(NAMES, preds[:7], rg["fwd64"]["preds"]):
+        assert rel(a, ref) <= tol_out + 1e-6, (n, "reference glue", rel(a, ref))
+    for k, v in rg["train"]["losses"].items():
+        assert abs(float(losses[k]) - v) <= 2 * tol_loss * max(1.0, abs(v)), (k, "reference glue", float(losses[k]), v)
     # gradients
     flat_a, flat_b = [], []
     for k, p in model.named_parameters():
