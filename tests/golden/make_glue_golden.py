@@ -54,8 +54,11 @@ def main():
     out = {}
     for name, case in cases.items():
         out[name] = {m: run_reference(case, m) for m in MODES}
+    # train.py:16-51 run from its source with a stand-in extractor (tests/reference_glue.py)
+    batch, frames = RG.intensity_case()
+    out["intensity_rep"] = RG.load_get_intensity_representation()(lambda x, l, e: frames, batch, torch.device("cpu"))
     torch.save(out, os.path.join(HERE, "reference_glue.pt"))
-    print({k: {m: list(v[m]["mel_lens"].tolist()) for m in v} for k, v in out.items()})
+    print({k: {m: list(v[m]["mel_lens"].tolist()) for m in v} for k, v in out.items() if k != "intensity_rep"})
 
 
 if __name__ == "__main__":

@@ -87,3 +87,37 @@ def load():
             else:
                 sys.modules[k] = v
     return out[0].FastSpeech2, out[1].Loss
+
+
+def load_get_intensity_representation():
+    """train.py:16-51 executed from its own source text (the module's top-level imports need speechbrain, tensorboard
+    and the dataset stack, none of which the function uses)."""
+    import ast
+    import torch
+    path = os.path.join(REF_DIR, "train.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_intensity_representation")
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["get_intensity_representation"]
+
+
+def intensity_case(seed=11, B=5, Tp=23, D=5):
+    """A collate-shaped 12-tuple (train.py:18-21) with ragged phoneme lengths, zero durations and padding, plus the frame
+    intensities a stand-in extractor returns."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    phon_len = torch.tensor([23, 17, 9, 1, 12])
+    dur = torch.randint(0, 7, (B, Tp), generator=g)
+    dur[0, 3] = 0
+    dur[3, 0] = 4
+    for b in range(B):
+        dur[b, int(phon_len[b]):] = 0
+    mel_len = dur.sum(1)
+    Tm = int(mel_len.max())
+    frames = torch.randn(B, Tm, D, generator=g)
+    phoneme = torch.randint(1, 90, (B, Tp), generator=g)
+    rank_X = torch.randn(B, 82, Tm, generator=g)
+    emo = torch.randint(0, 5, (B,), generator=g)
+    batch = (phoneme, None, phon_len, None, None, None, dur, mel_len, None, None, rank_X, emo)
+    return batch, frames

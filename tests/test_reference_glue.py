@@ -117,3 +117,30 @@ def test_live_reference_glue_in_training_mode_with_dropout():
     for k in gr:
         scale = max(float(gr[k].abs().max()), 1e-6)
         assert float((gr[k] - go[k]).abs().max()) <= 2e-3 * scale, k
+
+
+@needs_reference
+def test_intensity_segment_mean_against_the_reference_function():
+    """oracle.intensity_segment_mean (what fs2_intensity_segment_mean is compared with on the GPU)
+    against train.py:16-51 itself, run with a stand-in extractor that returns fixed frame intensities."""
+    fn = RG.load_get_intensity_representation()
+    batch, frames = RG.intensity_case()
+    seen = {}
+
+    def extractor(rank_X, mel_len, emo_ids):
+        seen["args"] = (rank_X, mel_len, emo_ids)
+        return frames
+
+    ref = fn(extractor, batch, torch.device("cpu"))
+    assert seen["args"][0] is batch[10] and seen["args"][1] is batch[7] and seen["args"][2] is batch[11]
+    got = O.intensity_segment_mean(frames, batch[2], batch[6], batch[0].shape[1])
+    assert ref.shape == got.shape == (5, 23, 5)
+    assert torch.equal(ref, got)                               # same torch ops in the same order: bit-identical
+    frozen = torch.load(os.path.join(GOLD, "reference_glue.pt"))["intensity_rep"]
+    assert torch.equal(ref, frozen)
+
+
+def test_intensity_segment_mean_against_frozen_reference_output():
+    batch, frames = RG.intensity_case()
+    frozen = torch.load(os.path.join(GOLD, "reference_glue.pt"))["intensity_rep"]
+    assert torch.equal(O.intensity_segment_mean(frames, batch[2], batch[6], batch[0].shape[1]), frozen)
