@@ -121,3 +121,27 @@ def intensity_case(seed=11, B=5, Tp=23, D=5):
     emo = torch.randint(0, 5, (B,), generator=g)
     batch = (phoneme, None, phon_len, None, None, None, dur, mel_len, None, None, rank_X, emo)
     return batch, frames
+
+
+def run_reference_prototype_binning(entries_by_cell, speaker_list, emotion_list, bucket_size, feat_dim):
+    """rank_model/inference.py:91-110 -- the `prototypes = np.zeros(...)` statement and the "Binning and averaging" loop
+    of bucketize() -- executed from the reference's source on a caller-built `intensity_storage` (the part of the
+    function before them is the dataloader / model loop).  The reference sizes the feature axis with n_emo; here it is
+    passed as `n_emo` only for that statement via `feat_dim` when the two differ in a test."""
+    import ast
+    import warnings
+    import numpy as np
+    path = os.path.join(os.path.dirname(REF_DIR), "rank_model", "inference.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "bucketize")
+    alloc = next(n for n in fn.body if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "prototypes")
+    loop = next(n for n in fn.body if isinstance(n, ast.For) and isinstance(n.iter, ast.Call)
+                and "speaker_list" in ast.dump(n.iter) and "array_split" in ast.dump(n))
+    ns = {"np": np, "intensity_storage": entries_by_cell, "speaker_list": speaker_list, "emotion_list": emotion_list,
+          "n_spk": len(speaker_list), "n_emo": feat_dim, "bucket_size": bucket_size}
+    exec(compile(ast.Module(body=[alloc], type_ignores=[]), path, "exec"), ns)
+    assert ns["prototypes"].shape == (len(speaker_list), feat_dim, bucket_size, feat_dim)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                     # numpy: mean of an empty slice -> NaN, as in the reference
+        exec(compile(ast.Module(body=[loop], type_ignores=[]), path, "exec"), ns)
+    return ns["prototypes"]

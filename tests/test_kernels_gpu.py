@@ -517,35 +517,13 @@ def test_fused_adamw_ranges_equal_one_launch(pkg):
 
 def test_intensity_prototypes_match_the_reference_binning(pkg):
     """rank_model/inference.py:80-114 restated with its own tools (python lists, list.sort on the score, numpy
-    concatenate / array_split / mean) against the device version -- including a (speaker, emotion) cell with fewer frames
+    concatenate / array_split / mean; tests/prototype_case.py, itself checked against the reference's own lines in
+    tests/test_reference_glue.py) against the device version -- including a (speaker, emotion) cell with fewer frames
     than buckets (numpy: NaN for the empty slices) and a cell without utterances (stays zero)."""
     import numpy as np
-    g = torch.Generator().manual_seed(21)
-    N, Tmax, D, n_spk, n_emo, k = 40, 37, 5, 3, 4, 6
-    length = torch.randint(1, Tmax + 1, (N,), generator=g)
-    I = torch.randn(N, Tmax, D, generator=g)
-    r = torch.randn(N, generator=g)
-    r[5] = r[9]                                                   # a tie: list.sort is stable
-    spk = torch.randint(0, n_spk, (N,), generator=g)
-    emo = torch.randint(0, n_emo - 1, (N,), generator=g)          # emotion 3 never occurs -> all-zero cells
-    spk[0], emo[0], length[0] = 2, 2, 3                           # make (2, 2) a cell with 3 frames < 6 buckets
-    keep = ~((spk == 2) & (emo == 2))
-    keep[0] = True
-    I, length, r, spk, emo = I[keep], length[keep], r[keep], spk[keep], emo[keep]
-    store = {(s, e): [] for s in range(n_spk) for e in range(n_emo)}
-    for i in range(I.shape[0]):
-        store[(int(spk[i]), int(emo[i]))].append((float(r[i]), I[i, : int(length[i])].numpy()))
-    ref = np.zeros((n_spk, n_emo, k, D), dtype=np.float32)
-    import warnings
-    for (s, e), entries in store.items():
-        if not entries:
-            continue
-        entries.sort(key=lambda x: x[0])
-        feats = np.concatenate([x[1] for x in entries], axis=0)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            for bi, idxs in enumerate(np.array_split(np.arange(len(feats)), k)):
-                ref[s, e, bi] = feats[idxs].mean(axis=0)
+    import prototype_case as PC
+    I, length, r, spk, emo, n_spk, n_emo, k = PC.inputs()
+    ref = PC.restated(I, length, r, spk, emo, n_spk, n_emo, k)
     out = pkg.intensity_prototypes(I.cuda(), length.cuda(), r.cuda(), spk.cuda(), emo.cuda(), n_spk, n_emo, k).cpu().numpy()
     assert out.shape == ref.shape
     assert np.array_equal(np.isnan(out), np.isnan(ref)) and np.isnan(ref[2, 2]).any()

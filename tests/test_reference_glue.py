@@ -144,3 +144,22 @@ def test_intensity_segment_mean_against_frozen_reference_output():
     batch, frames = RG.intensity_case()
     frozen = torch.load(os.path.join(GOLD, "reference_glue.pt"))["intensity_rep"]
     assert torch.equal(O.intensity_segment_mean(frames, batch[2], batch[6], batch[0].shape[1]), frozen)
+
+
+@needs_reference
+def test_prototype_binning_procedure_against_the_reference_lines():
+    """the list / numpy procedure the GPU test compares fs2_prototype_buckets with
+    (tests/prototype_case.restated) against the reference's own statements (rank_model/inference.py:91-110), incl. the
+    stable sort on tied scores, NaN for empty buckets and zeros for cells without utterances."""
+    import numpy as np
+    import prototype_case as PC
+    I, length, r, spk, emo, n_spk, n_emo, k = PC.inputs(D=4)               # the reference's feature axis is n_emo wide
+    speakers, emotions = [f"s{i}" for i in range(n_spk)], [f"e{i}" for i in range(n_emo)]
+    storage = {s: {e: [] for e in emotions} for s in speakers}
+    for i in range(I.shape[0]):                                            # inference.py:81-88
+        storage[speakers[int(spk[i])]][emotions[int(emo[i])]].append((r.numpy()[i], I.numpy()[i, : int(length[i]), :]))
+    ref = RG.run_reference_prototype_binning(storage, speakers, emotions, k, n_emo)
+    got = PC.restated(I, length, r, spk, emo, n_spk, n_emo, k)
+    assert ref.dtype == got.dtype == np.float32 and ref.shape == got.shape
+    assert np.array_equal(ref, got, equal_nan=True)
+    assert np.isnan(ref[2, 2]).any() and (ref[:, 3] == 0).all()
