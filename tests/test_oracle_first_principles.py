@@ -245,3 +245,63 @@ def test_mse_terms_brute_force():
     assert abs(float(out["energy_loss"]) - want["energy"] * cfg["energy_loss_weight"]) < 1e-12
     parts = sum(float(out[k]) for k in ("ssim_loss", "mel_loss", "postnet_mel_loss", "dur_loss", "pitch_loss", "energy_loss"))
     assert abs(float(out["total_loss"]) - parts) < 1e-12
+
+
+# ------------------------------------------------------------------ ragged / empty inputs (property tests)
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@st.composite
+def ragged_durations(draw):
+    B = draw(st.integers(1, 4))
+    Tp = draw(st.integers(1, 9))
+    dur = [[draw(st.integers(0, 6)) for _ in range(Tp)] for _ in range(B)]
+    if sum(dur[0]) == 0:
+        dur[0][0] = 1                                        # pad_sequence needs one non-empty item
+    return torch.tensor(dur)
+
+
+@settings(max_examples=60, deadline=None)
+@given(ragged_durations(), st.sampled_from([0.8, 1.0, 1.2]))
+def test_upsample_is_repeat_by_truncated_scaled_duration(dur, pace):
+    """LengthRegulator: item b, phoneme p occupies (pace * dur).long() frames (fp32 product, truncation), items are
+    zero-padded to the longest; utterances may be empty."""
+    B, Tp = dur.shape
+    feats = torch.arange(B * Tp * 3, dtype=torch.float32).reshape(B, Tp, 3) + 1.0
+    out, lens = O.upsample(feats, dur, pace=pace)
+    frames = (torch.tensor(pace, dtype=torch.float32) * dur.float()).long()
+    assert lens == frames.sum(1).tolist() and out.shape == (B, max(lens), 3)
+    for b in range(B):
+        f = 0
+        for p in range(Tp):
+            for _ in range(int(frames[b, p])):
+                assert torch.equal(out[b, f], feats[b, p])
+                f += 1
+        assert (out[b, f:] == 0).all()
+
+
+@settings(max_examples=60, deadline=None)
+@given(ragged_durations(), st.integers(0, 2 ** 31 - 1))
+def test_segment_means_on_ragged_batches(dur, seed):
+    """average_over_durations (mean over NON-ZERO frames, 0 for empty segments) and the intensity segment mean
+    (train.py:16-51: plain mean, 0 for zero-duration phonemes) against per-phoneme loops."""
+    B, Tp = dur.shape
+    g = torch.Generator().manual_seed(seed)
+    Tm = int(dur.sum(1).max())
+    vals = torch.randn(B, 1, Tm, generator=g, dtype=F64)
+    vals[torch.rand(B, 1, Tm, generator=g) < 0.25] = 0.0
+    avg = O.average_over_durations(vals, dur)
+    inten = torch.randn(B, Tm, 5, generator=g, dtype=F64)
+    phon_len = torch.tensor([Tp] * B)
+    rep = O.intensity_segment_mean(inten, phon_len, dur, Tp)
+    for b in range(B):
+        f = 0
+        for p in range(Tp):
+            d = int(dur[b, p])
+            seg = vals[b, 0, f:f + d]
+            nz = seg[seg != 0]
+            want = float(nz.mean()) if nz.numel() else 0.0
+            assert abs(float(avg[b, 0, p]) - want) < 1e-10
+            want_i = inten[b, f:f + d].mean(0) if d else torch.zeros(5, dtype=F64)
+            assert torch.allclose(rep[b, p], want_i, atol=1e-12)
+            f += d
