@@ -59,6 +59,7 @@ SIGNATURES = {
     "fs2_mse_losses": "pppppppppppiiiippppppppp",
     "fs2_ssim_loss": "pppiiifpppp",
     "fs2_adamw": "ppppqfffffifp",
+    "fs2_adamw_fused": "ppppqfffffifpqqqiiqip",
     "fs2_intensity_segment_mean": "pppiiiipp",
 }
 

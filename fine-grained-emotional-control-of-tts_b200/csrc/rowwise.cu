@@ -1234,11 +1234,25 @@ __global__ void add_kernel(float* d, const float* s, long long n) {
   } else for (; i < n; ++i) d[i] += s[i];
 }
 
+// AdamW over a slice [base, base + n) of the flat parameter buffer.  In the same pass (the updated value is in
+// registers anyway) it refreshes the bf16 operand MIRROR of the flat buffer (params.py: the tensor-core GEMMs read the
+// mirror, so no separate weight-packing pass runs per step) and the one gathered operand (a column block of a wider
+// matrix, copied to the mirror's tail).  `err`: the tcgen05 kernels' mbarrier-timeout word -- when it is set the step's
+// gradients are not trustworthy and the update is skipped (the host raises at its next check, optim.py).
+struct AdamMirror {
+  bf16* mirror;           // nullptr: no mirror
+  long long base;         // flat index of p[0]
+  long long g_src_off, g_src_ld, g_dst_off;
+  int g_rows, g_cols;     // g_rows == 0: no gathered operand
+};
 __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
-                             float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+                             float eps, float wd, float bc1, float bc2_sqrt, float gscale, AdamMirror mr, const int* err) {
   pdl_wait();
+  if (err != nullptr && *err != 0) return;
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
+  float out[4];
+  int cnt;
   if (i + 3 < n) {
     float4 P = ld4(p + i), G = ld4(g + i), M = ld4(m + i), V = ld4(v + i);
     float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
@@ -1250,16 +1264,34 @@ __global__ void adamw_kernel(float* p, const float* g, float* m, float* v, long 
       vv[q] = b2 * vv[q] + (1.f - b2) * gr * gr;
       float denom = sqrtf(vv[q]) / bc2_sqrt + eps;
       pp[q] -= (lr / bc1) * (mm[q] / denom);
+      out[q] = pp[q];
     }
     st4(p + i, P); st4(m + i, M); st4(v + i, V);
+    if (mr.mirror) st4(mr.mirror + mr.base + i, P);
+    cnt = 4;
   } else {
-    for (; i < n; ++i) {
-      float gr = g[i] * gscale;
-      float P = p[i] * (1.f - lr * wd);
-      float M = b1 * m[i] + (1.f - b1) * gr;
-      float V = b2 * v[i] + (1.f - b2) * gr * gr;
+    cnt = (int)(n - i);
+    for (int q = 0; q < cnt; ++q) {
+      float gr = g[i + q] * gscale;
+      float P = p[i + q] * (1.f - lr * wd);
+      float M = b1 * m[i + q] + (1.f - b1) * gr;
+      float V = b2 * v[i + q] + (1.f - b2) * gr * gr;
       P -= (lr / bc1) * (M / (sqrtf(V) / bc2_sqrt + eps));
-      p[i] = P; m[i] = M; v[i] = V;
+      p[i + q] = P; m[i + q] = M; v[i + q] = V;
+      out[q] = P;
+      if (mr.mirror) mr.mirror[mr.base + i + q] = __float2bfloat16_rn(P);
+    }
+  }
+  if (mr.mirror && mr.g_rows > 0) {
+    const long long f0 = mr.base + i - mr.g_src_off;            // position inside the source matrix
+    if (f0 + cnt > 0 && f0 < (long long)mr.g_rows * mr.g_src_ld) {
+      for (int q = 0; q < cnt; ++q) {
+        const long long f = f0 + q;
+        if (f < 0 || f >= (long long)mr.g_rows * mr.g_src_ld) continue;
+        const long long r = f / mr.g_src_ld;
+        const int c = (int)(f - r * mr.g_src_ld);
+        if (c < mr.g_cols) mr.mirror[mr.g_dst_off + r * mr.g_cols + c] = __float2bfloat16_rn(out[q]);
+      }
     }
   }
 }
@@ -1751,13 +1783,34 @@ extern "C" int fs2_memset(void* dst, int value, long long nbytes, void* stream) 
   return FS2_OK;
 }
 
-extern "C" int fs2_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                         float eps, float wd, int step, float grad_scale, void* stream) {
+int fs2_tc_error_ptr(int** out);      // gemm_tc.cu
+
+extern "C" int fs2_adamw_fused(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                               float beta2, float eps, float wd, int step, float grad_scale, void* mirror_bf16,
+                               long long base, long long g_src_off, long long g_src_ld, int g_rows, int g_cols,
+                               long long g_dst_off, int guard_tc_error, void* stream) {
   REQUIRE(p && g && m && v && step >= 1, "fs2_adamw: bad arguments");
+  REQUIRE(mirror_bf16 == nullptr || base % 4 == 0, "fs2_adamw_fused: slice start must be a multiple of 4 elements");
   float bc1 = 1.0f - powf(beta1, (float)step);
   float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
-  FS2_LAUNCH((adamw_kernel), (unsigned)((n / 4 + 256) / 256), 256, 0, ST, p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale);
+  AdamMirror mr;
+  mr.mirror = (bf16*)mirror_bf16;
+  mr.base = base;
+  mr.g_src_off = g_src_off; mr.g_src_ld = g_src_ld > 0 ? g_src_ld : 1; mr.g_dst_off = g_dst_off;
+  mr.g_rows = g_rows; mr.g_cols = g_cols;
+  int* err = nullptr;
+  if (guard_tc_error) {
+    int rc = fs2_tc_error_ptr(&err);
+    if (rc) return rc;
+  }
+  FS2_LAUNCH((adamw_kernel), (unsigned)((n / 4 + 256) / 256), 256, 0, ST, p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2,
+             grad_scale, mr, (const int*)err);
   return fs2_check_launch();
+}
+
+extern "C" int fs2_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                         float eps, float wd, int step, float grad_scale, void* stream) {
+  return fs2_adamw_fused(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, grad_scale, nullptr, 0, 0, 1, 0, 0, 0, 0, stream);
 }
 
 extern "C" int fs2_intensity_segment_mean(const float* I, const int64_t* dur, const int64_t* phon_len, int B, int Tp,

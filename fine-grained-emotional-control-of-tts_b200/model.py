@@ -176,6 +176,13 @@ class FastSpeech2(nn.Module):
         self._pre = None
         self.fused_attention = True   # bf16, head_dim 192: fs2_attn_fwd / fs2_attn_bwd instead of GEMM + softmax + GEMM
         self.async_mel_lens = False   # opt-in: no host sync; Tm is taken from pitch.shape[1], mel_lens arrives in pinned memory
+        # opt-in, inference with predicted durations in precision="bf16": frame counts are trunc(pace * expm1(pred)), which is
+        # discontinuous -- a bf16 encoder moves ~1 % of the phonemes across an integer boundary (tests/
+        # test_parity_bench_configs_gpu.py).  With exact_durations the phoneme encoder, the conditioning and the duration
+        # predictor are evaluated a second time on the exact fp32 path and THAT prediction drives the LengthRegulator (and is
+        # returned as predict_durations); everything at mel-frame length stays on the tensor cores.
+        self.exact_durations = False
+        self._arenas_exact = None
         self._async_bufs = None
         self.replayed_launches = 0    # kernels launched through graph replays (fs2_launch_count only sees captures)
         self.trace = None        # set to a dict to collect unpadded intermediates (debug / parity tests)
@@ -222,6 +229,13 @@ class FastSpeech2(nn.Module):
     def _bf16(self):
         return self.precision == "bf16"
 
+    def _sync_operands(self):
+        st = self.store
+        if st.flat.is_cuda:
+            if not st.views_intact():
+                st.reflatten()
+            st.sync_operands(self._bf16)
+
     def _P(self, key):
         return self.store.params[key]
 
@@ -252,10 +266,11 @@ class FastSpeech2(nn.Module):
     def _conv(self, x, B, T, wname, out, *, c_bf16, bias=None, relu=0, lens=None, halo=0):
         """y[r] = sum_j x[r + j - p] . W_j (+bias, ReLU, row mask, reflect-halo mirror): model.py Conv1d/Linear sites."""
         w = self.store.pw(wname)
+        wbuf, woff, wld = self.store.operand(wname, self._bf16)
         rows = B * (T + 2 * PAD)
         p = (w.k - 1) // 2
         L.gemm(mode=0, M=rows, N=w.cout, K=w.cin, taps=w.k, A=x, lda=w.cin, a_rows=rows, a_inner=w.cin,
-               a_row_off=-p, a_tap_step=1, B=self.store.packed_buf, B_off=w.off, ldb=w.k * w.cin, b_rows=w.cout,
+               a_row_off=-p, a_tap_step=1, B=wbuf, B_off=woff, ldb=wld, b_rows=w.cout,
                b_inner=w.k * w.cin, b_tap_step=w.cin, Cout=out, ldc=w.cout, c_bf16=c_bf16, ab_bf16=self._bf16,
                bias=bias, relu=relu, rs_T=T, rs_Tp=T + 2 * PAD, lens=lens, halo=halo)
 
@@ -264,11 +279,12 @@ class FastSpeech2(nn.Module):
         split = 2: `out` is (2, rows, Cin); each half of the reduction is STORED to its own slice (deterministic split-K,
         the consumer adds the two) -- used where one wave of tiles leaves SMs idle, see _dgrad_split."""
         w = self.store.pw(wname)
+        wbuf, woff, wld = self.store.operand(wname, self._bf16)
         rows = B * (T + 2 * PAD)
         p = (w.k - 1) // 2
         self._wait_side(out)
         L.gemm(mode=1, M=rows, N=w.cin, K=w.cout, taps=w.k, A=dy, lda=w.cout, a_rows=rows, a_inner=w.cout,
-               a_row_off=p, a_tap_step=-1, B=self.store.packed_buf, B_off=w.off, ldb=w.k * w.cin, b_rows=w.cout,
+               a_row_off=p, a_tap_step=-1, B=wbuf, B_off=woff, ldb=wld, b_rows=w.cout,
                b_inner=w.k * w.cin, b_tap_step=w.cin, Cout=out, ldc=w.cin, c_bf16=c_bf16, ab_bf16=self._bf16,
                relu_aux=relu_aux, aux_bf16=int(self._bf16), split_k=split,
                c_split_stride=rows * w.cin if split > 1 else 0)
@@ -328,16 +344,21 @@ class FastSpeech2(nn.Module):
         self._side_last = done
 
     def _conv_wgrad_launch(self, dy, x, B, T, wname, wkey, bkey=None):
-        """dW[co, ci, j] += sum_r dy[r, co] * x[r + j - p, ci];  db[co] += sum_r dy[r, co]."""
+        """dW[co, ci, j] += sum_r dy[r, co] * x[r + j - p, ci];  db[co] += sum_r dy[r, co].  The gradient buffer has the
+        master's layout (params.py): tap-major [Cout][k][Cin] for k > 1, so every tap's (Cout, Cin) block is contiguous
+        in n and the split-K partial sums go out as 16-byte vector atomics."""
         w = self.store.pw(wname)
         rows = B * (T + 2 * PAD)
         p = (w.k - 1) // 2
         split = 0            # auto: chosen by fs2_gemm_tc from the tile count and the SM count
         o, _ = self.store.offsets[wkey]
-        src_ld = w.src_ld
+        if w.gather:         # a column block of a wider (Cout, src_ld) matrix
+            c_off, ldc, tap_stride = o + w.src_col0, w.src_ld, 1
+        else:
+            c_off, ldc, tap_stride = o, w.k * w.cin, w.cin
         L.gemm(mode=2, M=w.cout, N=w.cin, K=rows, taps=w.k, A=dy, lda=w.cout, a_rows=rows, a_inner=w.cout,
                B=x, ldb=w.cin, b_rows=rows, b_inner=w.cin, b_row_off=-p, b_tap_step=1,
-               Cout=self.store.flat_grad, C_off=o + w.src_col0, ldc=src_ld, c_tap_stride=1, c_col_stride=w.k,
+               Cout=self.store.flat_grad, C_off=c_off, ldc=ldc, c_tap_stride=tap_stride, c_col_stride=1,
                c_bf16=False, ab_bf16=self._bf16, accumulate=1, split_k=split)
         if bkey is not None:
             L.call("fs2_colsum", dy, int(self._bf16), rows, w.cout, w.cout, self._G(bkey))
@@ -572,7 +593,7 @@ class FastSpeech2(nn.Module):
         return dy_a, dy_b
 
     # ---------------------------------------------------------------- variance predictor
-    def _pred_fwd(self, pname, x_act, B, T, lens, scale, base_seed, site, training):
+    def _pred_fwd(self, pname, x_act, B, T, lens, scale, base_seed, site, training, out):
         D = self.D
         rows = B * (T + 2 * PAD)
         h = (self.kd - 1) // 2
@@ -593,7 +614,6 @@ class FastSpeech2(nn.Module):
         self._conv(sv.a1, B, T, f"{pname}.conv2.conv.weight", sv.h2, c_bf16=False,
                    bias=self._P(f"{pname}.conv2.conv.bias"), relu=1)
         sv.mean2, sv.rstd2 = self._f32(rows), self._f32(rows)
-        out = torch.empty(B, T, device=x_act.device, dtype=torch.float32)
         self._ln_fwd(B, T, D, sv.h2, self._P(f"{pname}.ln2.norm.weight"), self._P(f"{pname}.ln2.norm.bias"), 1e-5,
                      drop_a=(p, sv.seeds[1]), lens=lens, mean=sv.mean2, rstd=sv.rstd2,
                      head=(self._P(f"{pname}.linear.w.weight"), self._P(f"{pname}.linear.w.bias"), out, sv.scale))
@@ -621,6 +641,35 @@ class FastSpeech2(nn.Module):
         self._conv_wgrad(d1_act, sv.x_act, B, T, f"{pname}.conv1.conv.weight", f"{pname}.conv1.conv.weight",
                          f"{pname}.conv1.conv.bias")
         self._conv_dgrad(d1_act, B, T, f"{pname}.conv1.conv.weight", dx_out)
+
+    def _exact_log_durations(self, tokens, speakers, intensity, out):
+        """Encoder + conditioning + duration predictor on the fp32 path (model.py:331-372), into `out` (B, Tp)."""
+        saved = (self.precision, self._arenas)
+        if self._arenas_exact is None:
+            self._arenas_exact = (Arena(torch.float32), Arena(torch.float32), Arena(torch.int32))
+        try:
+            self.precision = "fp32"
+            self._arenas = self._arenas_exact
+            for a in self._arenas:
+                a.reset(tokens.device)
+            self.store.sync_operands(False)
+            B, Tp = tokens.shape
+            D = self.D
+            rowsP = B * (Tp + 2 * PAD)
+            src_lens = self._i32(B)
+            x_f32, x_act = self._f32(rowsP, D), self._act(rowsP, D)
+            L.call("fs2_embed_posenc", tokens, self._P("encPreNet.token_embedding.Embedding.weight"),
+                   self.sinusoidal_positional_embed_encoder.pe, B, Tp, D, self.padding_idx, x_f32, x_act, 0, src_lens)
+            _, enc_act, _, _ = self._stack_fwd(self.enc, x_f32, x_act, B, Tp, src_lens, src_lens, 0, self._seed_base, 100,
+                                               False, keep_p=False)
+            G = self._f32(rowsP, D)
+            self._conv(enc_act, B, Tp, "concat_proj.tok", G, c_bf16=False)
+            c_f32, c_act = self._f32(rowsP, D), self._act(rowsP, D)
+            L.call("fs2_cond_finish", G, self._P("concat_proj.w.weight"), self._P("speaker_emb.Embedding.weight"), speakers,
+                   intensity, src_lens, B, Tp, D, self._f32(B, D), c_f32, c_act, 0, (self.kd - 1) // 2)
+            self._pred_fwd("durPred", c_act, B, Tp, src_lens, 1.0, self._seed_base, 10, False, out)
+        finally:
+            self.precision, self._arenas = saved
 
     # --------------------------------------------------------------------------- forward
     def forward(self, tokens, speakers, durations=None, pitch=None, energy=None, pace=1.0, pitch_rate=1.0,
@@ -658,7 +707,6 @@ class FastSpeech2(nn.Module):
             L.call("fs2_counter_add", self._ctr, 1)
         bf = self._bf16
         D, n_mels = self.D, self.n_mels
-        st.pack(bf)
         tokens = tokens.contiguous().long()
         speakers = speakers.contiguous().long()
         intensity = intensity.contiguous().float()
@@ -719,9 +767,15 @@ class FastSpeech2(nn.Module):
         self._tr("cond", c_f32, B, Tp, D)
 
         # ---- variance adaptor (model.py:365-403)
-        pred_dur, ctx.sv_dur = self._pred_fwd("durPred", c_act, B, Tp, src_lens, 1.0, base_seed, 10, training)
-        pred_pitch, ctx.sv_pitch = self._pred_fwd("pitchPred", c_act, B, Tp, src_lens, pitch_rate, base_seed, 12, training)
-        avg_pitch = torch.zeros(B, Tp, device=dev, dtype=torch.float32)
+        # the five (B, Tp) outputs share one buffer (one clone hands them out under graph replay, see _FS2Function)
+        out5 = torch.zeros(5, B, Tp, device=dev, dtype=torch.float32)
+        ctx.out5 = out5
+        pred_dur, ctx.sv_dur = self._pred_fwd("durPred", c_act, B, Tp, src_lens, 1.0, base_seed, 10, training, out5[0])
+        if durations is None and self.exact_durations and bf and not training:
+            self._exact_log_durations(tokens, speakers, intensity, out5[0])       # overwrites the bf16 prediction
+        pred_pitch, ctx.sv_pitch = self._pred_fwd("pitchPred", c_act, B, Tp, src_lens, pitch_rate, base_seed, 12, training,
+                                                  out5[1])
+        avg_pitch = out5[2]
         if pitch is not None:
             if durations is None:
                 raise ValueError("pitch targets need durations (average_over_durations, model.py:383)")
@@ -735,8 +789,9 @@ class FastSpeech2(nn.Module):
         L.call("fs2_embed_add", c_f32, contour_p, self._P("pitchEmbed.conv.weight"), self._P("pitchEmbed.conv.bias"),
                self.kp, src_lens, B, Tp, D, ap_f32, ap_act, int(bf), hv)
         self._tr("after_pitch", ap_f32, B, Tp, D)
-        pred_energy, ctx.sv_energy = self._pred_fwd("energyPred", ap_act, B, Tp, src_lens, energy_rate, base_seed, 14, training)
-        avg_energy = torch.zeros(B, Tp, device=dev, dtype=torch.float32)
+        pred_energy, ctx.sv_energy = self._pred_fwd("energyPred", ap_act, B, Tp, src_lens, energy_rate, base_seed, 14, training,
+                                                    out5[3])
+        avg_energy = out5[4]
         if energy is not None:
             if durations is None:
                 raise ValueError("energy targets need durations (average_over_durations, model.py:397)")
@@ -785,7 +840,9 @@ class FastSpeech2(nn.Module):
         hp = (self.kpn - 1) // 2
         mel_raw = self._f32(rowsM, n_mels)
         self._conv(dec_act, B, Tm, "linear.w.weight", mel_raw, c_bf16=False, bias=self._P("linear.w.bias"))
-        mel_post = torch.empty(B, Tm, n_mels, device=dev, dtype=torch.float32)
+        mel2 = torch.empty(2, B, Tm, n_mels, device=dev, dtype=torch.float32)      # mel_post, postnet_output
+        ctx.mel2 = mel2
+        mel_post = mel2[0]
         mel_f32, mel_act = self._f32(rowsM, n_mels), self._act(rowsM, n_mels)
         L.call("fs2_unpad_mask", mel_raw, mel_lens, B, Tm, n_mels, mel_post, mel_act, int(bf), hp)
         L.call("fs2_pad_rows", mel_post, None, B, Tm, n_mels, 1.0, mel_f32, None, int(bf))
@@ -828,7 +885,7 @@ class FastSpeech2(nn.Module):
         post_pad = self._f32(rowsM, n_mels)
         self._ln_fwd(B, Tm, n_mels, pn.c5, self._P("postnet.ln3.weight"), self._P("postnet.ln3.bias"), 1e-5,
                      drop_a=(pn.p, pn.seeds[2]), post_add=mel_f32, out_f32=post_pad, mean=pn.mean3, rstd=pn.rstd3)
-        postnet_out = torch.empty(B, Tm, n_mels, device=dev, dtype=torch.float32)
+        postnet_out = mel2[1]
         L.call("fs2_unpad_mask", post_pad, None, B, Tm, n_mels, postnet_out, None, int(bf), 0)
         ctx.pitch_rate, ctx.energy_rate = pitch_rate, energy_rate
         ctx.has_targets = (pitch is not None) and (energy is not None)
@@ -1017,6 +1074,7 @@ class FastSpeech2(nn.Module):
         tokens = tokens.contiguous().long()
         durations = durations.contiguous().long()
         B, Tp = tokens.shape
+        self._sync_operands()               # eager, outside the captured graphs: usually no launch at all (params.py)
         if self.async_mel_lens and B <= 256:
             self._check_async_flag()
             Tm = int(pitch.shape[1])
@@ -1082,6 +1140,7 @@ class _FS2Function(torch.autograd.Function):
                                                     energy_rate, intensity)
         else:
             tm = None
+            model._sync_operands()
             if model.async_mel_lens and durations is not None and pitch is not None and tokens.shape[0] <= 256:
                 model._check_async_flag()
                 tm = int(pitch.shape[1])
@@ -1089,8 +1148,10 @@ class _FS2Function(torch.autograd.Function):
                                             intensity, Tm_known=tm)
         fctx.model, fctx.ctx, fctx.entry = model, ctx, entry
         if entry is not None:
-            # static graph outputs: hand out views so autograd sees fresh tensors each step
-            outs = tuple(o.view_as(o) for o in outs)
+            # graph replays write into static buffers; the reference hands out fresh tensors every call and train.py:87-90
+            # still reads `predictions` after later steps, so the outputs are copied out (two launches, 16 MB at B = 32)
+            m2, o5 = ctx.mel2.clone(), ctx.out5.clone()
+            outs = (m2[0], m2[1], o5[0], o5[1].unsqueeze(-1), o5[2].unsqueeze(-1), o5[3].unsqueeze(-1), o5[4].unsqueeze(-1))
         fctx.mark_non_differentiable(outs[4], outs[6])
         return outs
 

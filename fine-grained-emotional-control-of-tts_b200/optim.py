@@ -1,6 +1,8 @@
 """Fused AdamW over the model's flat parameter / gradient buffers (reference: torch.optim.AdamW(lr=1e-4) with
 torch defaults, `/root/reference/emo_rank_tts/fastspeech2/train.py:232, 81`): one kernel per step instead of
-a foreach pass per parameter."""
+a foreach pass per parameter.  The same pass writes the bf16 operand mirror the tensor-core GEMMs read (params.py), so
+no weight re-packing pass runs between steps, and it refuses to apply a step whose tcgen05 kernels reported an mbarrier
+timeout (the device-side error word): the host raises at the next periodic check instead of training on garbage."""
 from __future__ import annotations
 
 import torch
@@ -15,6 +17,7 @@ class FusedAdamW:
         self.step_count = 0
         self.m = None
         self.v = None
+        self.error_check_interval = 32      # steps between host reads of the tcgen05 error word (one stream sync each)
 
     def zero_grad(self, set_to_none=True):
         st = self.model.store
@@ -33,6 +36,9 @@ class FusedAdamW:
             self.v = torch.zeros_like(st.flat)
         self.step_count += 1
         n = st.flat.numel()
+        mirror = st.mirror if (st.mirror is not None and st.mirror.device == st.flat.device) else None
+        gat = st.adamw_gather() if mirror is not None else None
+        covered = 0
         for r in (ranges or [(0, n)]):
             lo, hi = int(r[0]), int(r[1])
             if len(r) > 2 and r[2] is not None:
@@ -41,9 +47,22 @@ class FusedAdamW:
                 continue
             if lo % 4:
                 raise ValueError("FusedAdamW: range starts must be multiples of 4 elements (16-byte vector access)")
-            L.call("fs2_adamw", st.flat[lo:hi], st.flat_grad[lo:hi], self.m[lo:hi], self.v[lo:hi], hi - lo, float(self.lr),
-                   float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
-                   self.step_count, float(grad_scale))
+            g = gat or (0, 1, 0, 0, 0)
+            L.call("fs2_adamw_fused", st.flat[lo:hi], st.flat_grad[lo:hi], self.m[lo:hi], self.v[lo:hi], hi - lo,
+                   float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                   self.step_count, float(grad_scale), mirror, lo, g[0], g[1], g[2], g[3], g[4], 1)
+            covered += hi - lo
+        if mirror is not None and covered == n and (gat is not None or st.gather_total == 0):
+            st.mark_mirror_current()
+        if self.error_check_interval and self.step_count % self.error_check_interval == 0:
+            self.check_device_errors()
+
+    def check_device_errors(self):
+        """Read-and-clear the tcgen05 error word (synchronises the device).  While the word is set the AdamW kernel skips
+        its update, so the parameters still hold the last good step when this raises."""
+        if L.gemm_tc_error_flag() != 0:
+            raise RuntimeError("fs2_b200: a tcgen05 kernel reported an mbarrier timeout since the last check; the "
+                               "optimizer steps since then were NOT applied (parameters hold the last good state)")
 
     def state_dict(self):
         return {"step": self.step_count, "m": self.m, "v": self.v, "lr": self.lr, "betas": self.betas,

@@ -1,7 +1,18 @@
 """Parameter storage for the drop-in FastSpeech2: one flat fp32 buffer (so AdamW and the NCCL gradient
 all-reduce are single passes) exposed as nn.Parameters under exactly the reference's state_dict keys
-(`/root/reference/emo_rank_tts/fastspeech2/model.py:187-276`), plus the packed
-(tap-major, operand-dtype) weight copies that the implicit-GEMM kernels read.
+(`/root/reference/emo_rank_tts/fastspeech2/model.py:187-276`).
+
+Layout of a Conv1d weight with k > 1: the reference's parameter is (Cout, Cin, k).  The implicit-GEMM kernels read a
+weight tap-major, [Cout][k][Cin] (one K-slab of Cin per tap).  The fp32 MASTER is therefore stored tap-major inside the
+flat buffer and the nn.Parameter is the permuted view of it -- same key, same shape, same values, strides (k*Cin, 1, Cin).
+state_dict()/load_state_dict()/torch.optim see an ordinary (Cout, Cin, k) tensor; the kernels see their operand layout
+without a per-step re-packing pass:
+  * fp32 path: the GEMMs read the master directly;
+  * bf16 path: a bf16 MIRROR of the whole flat buffer (same element offsets) is the operand; FusedAdamW writes it in the
+    same pass that updates the master, any other change of the parameters is followed by one cast pass
+    (`sync_operands`).
+The only operand that is not a whole parameter -- the token columns [0:384) of `concat_proj.w.weight` (384 x 773, row
+pitch not TMA-aligned) -- is gathered into a small tail region of the mirror (bf16) / a side buffer (fp32).
 """
 from __future__ import annotations
 
@@ -14,16 +25,21 @@ import torch.nn as nn
 from . import _lib as L
 
 
+ALIGN = 64      # floats: parameter starts are 256-byte aligned, so the same offset in the bf16 mirror is 128-byte aligned (TMA)
+
+
 class PackedWeight:
-    """A GEMM weight in the packed operand buffer: rows = cout, row = [k taps][cin]."""
+    """A GEMM weight operand: rows = cout, row = [k taps][cin].  `gather`: a column block of a wider matrix (copied)."""
 
-    __slots__ = ("name", "cout", "cin", "k", "off", "src_ld", "src_col0")
+    __slots__ = ("name", "key", "cout", "cin", "k", "off", "src_ld", "src_col0", "gather", "goff")
 
-    def __init__(self, name, cout, cin, k, src_ld=None, src_col0=0):
-        self.name, self.cout, self.cin, self.k = name, cout, cin, k
-        self.off = 0
+    def __init__(self, name, key, cout, cin, k, src_ld=None, src_col0=0):
+        self.name, self.key, self.cout, self.cin, self.k = name, key, cout, cin, k
+        self.off = 0                 # element offset of the parameter in the flat buffer / mirror
         self.src_ld = src_ld if src_ld is not None else cin * k
         self.src_col0 = src_col0
+        self.gather = src_ld is not None and (src_ld != cin * k or src_col0 != 0)
+        self.goff = 0                # offset inside the gather region
 
 
 def _container(root: nn.Module, path: str) -> nn.Module:
@@ -47,17 +63,20 @@ class ParamStore:
         self.flat = None
         self.flat_grad = None
         self.params = {}         # key -> nn.Parameter
-        self.packed_buf = None
-        self.packed_total = 0
+        self.mirror = None           # bf16 copy of flat (+ gather tail): the tensor-core operand buffer
+        self.gather32 = None         # fp32 gather region (precision="fp32")
+        self.gather_total = 0
+        self.mirror_valid = False    # set by FusedAdamW.step (it wrote the mirror), consumed by sync_operands
+        self._mirror_token = -1
+        self.tapmajor = set()        # keys stored [Cout][k][Cin]
         self._items_dev = None
-        self._packed_dtype = None
 
     # ------------------------------------------------------------------ declaration
     def add(self, key, shape, init):
         self.specs.append((key, tuple(shape), init))
 
     def add_packed(self, key, cout, cin, k, src_ld=None, src_col0=0, name=None):
-        self.packed[name or key] = (key, PackedWeight(name or key, cout, cin, k, src_ld, src_col0))
+        self.packed[name or key] = (key, PackedWeight(name or key, key, cout, cin, k, src_ld, src_col0))
 
     def linear(self, prefix, cout, cin, bias=True):
         self.add(prefix + ".weight", (cout, cin), ("kaiming_uniform", cin))
@@ -70,6 +89,8 @@ class ParamStore:
         self.add(prefix + ".bias", (cout,), ("uniform_fan", cin * k))
         if pack:
             self.add_packed(prefix + ".weight", cout, cin, k)
+            if k > 1 and cin > 1:
+                self.tapmajor.add(prefix + ".weight")
 
     def layernorm(self, prefix, c):
         self.add(prefix + ".weight", (c,), ("ones",))
@@ -81,22 +102,39 @@ class ParamStore:
         for key, shape, _ in self.specs:
             n = int(math.prod(shape))
             self.offsets[key] = (off, n)
-            off += (n + 3) // 4 * 4          # 16-byte aligned parameter starts (float4 kernels)
+            off += (n + ALIGN - 1) // ALIGN * ALIGN
         self.total = off
+        self.shapes = {key: shape for key, shape, _ in self.specs}
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
         for key, shape, init in self.specs:
-            o, n = self.offsets[key]
-            view = self.flat[o:o + n].view(shape)
-            self._init(view, init)
+            view = self.view_of(self.flat, key)
+            if key in self.tapmajor:
+                tmp = torch.empty(shape)         # same RNG stream and values as a contiguous (Cout, Cin, k) parameter
+                self._init(tmp, init)
+                with torch.no_grad():
+                    view.copy_(tmp)
+            else:
+                self._init(view, init)
             p = nn.Parameter(view)
             path, _, leaf = key.rpartition(".")
             _container(self.root, path).register_parameter(leaf, p)
             self.params[key] = p
-        poff = 0
+        goff = 0
         for name, (key, pw) in self.packed.items():
-            pw.off = poff
-            poff += (pw.cout * pw.cin * pw.k + 63) // 64 * 64   # 128-byte aligned rows for TMA
-        self.packed_total = poff
+            pw.off = self.offsets[key][0]
+            if pw.gather:
+                pw.goff = goff
+                goff += (pw.cout * pw.cin * pw.k + ALIGN - 1) // ALIGN * ALIGN
+        self.gather_total = goff
+
+    def view_of(self, flat, key):
+        """The parameter-shaped view of `flat` (the master, the gradient buffer, ...) for `key`."""
+        o, n = self.offsets[key]
+        shape = self.shapes[key]
+        if key in self.tapmajor:
+            cout, cin, k = shape
+            return flat[o:o + n].view(cout, k, cin).permute(0, 2, 1)
+        return flat[o:o + n].view(shape)
 
     @staticmethod
     def _init(view, init):
@@ -130,13 +168,15 @@ class ParamStore:
             raise RuntimeError("fs2_b200: master parameters must stay fp32 (precision is chosen with precision=...)")
         new_flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
         for key, p in self.params.items():
-            o, n = self.offsets[key]
-            new_flat[o:o + n].copy_(p.data.reshape(-1))
-            p.data = new_flat[o:o + n].view(p.shape)
+            v = self.view_of(new_flat, key)
+            v.copy_(p.data)
+            p.data = v
             p.grad = None
         self.flat = new_flat
         self.flat_grad = None
-        self.packed_buf = None
+        self.mirror = None
+        self.gather32 = None
+        self.mirror_valid = False
         self._items_dev = None
 
     def views_intact(self):
@@ -169,32 +209,77 @@ class ParamStore:
             if not fresh:
                 L.call("fs2_memset", self.flat_grad, 0, self.flat_grad.numel() * 4)
             for key, p in self.params.items():
-                o, n = self.offsets[key]
-                p.grad = self.flat_grad[o:o + n].view(p.shape)
+                p.grad = self.view_of(self.flat_grad, key)
         return need_zero
 
     def grad(self, key):
         o, n = self.offsets[key]
         return self.flat_grad[o:o + n]
 
-    # -------------------------------------------------------------------- packing
-    def pack(self, bf16: bool):
-        """Refresh the packed operand copies from the fp32 masters (one kernel launch)."""
-        dt = torch.bfloat16 if bf16 else torch.float32
-        if self.packed_buf is None or self._packed_dtype != dt or self.packed_buf.device != self.flat.device:
-            self.packed_buf = torch.zeros(self.packed_total, dtype=dt, device=self.flat.device)
-            self._packed_dtype = dt
-            items = (L.Fs2PackItem * len(self.packed))()
-            for i, (name, (key, pw)) in enumerate(self.packed.items()):
-                o, _ = self.offsets[key]
-                items[i].src_off = o + pw.src_col0
-                items[i].dst_off = pw.off
+    # ------------------------------------------------------------------- operands
+    def _gather_items(self):
+        gl = [pw for _, (_, pw) in self.packed.items() if pw.gather]
+        if self._items_dev is None and gl:
+            items = (L.Fs2PackItem * len(gl))()
+            for i, pw in enumerate(gl):
+                items[i].src_off = pw.off + pw.src_col0
+                items[i].dst_off = pw.goff
                 items[i].src_ld = pw.src_ld
                 items[i].cout, items[i].cin, items[i].k = pw.cout, pw.cin, pw.k
-            raw = bytes(items)
-            host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+            host = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8)
             self._items_dev = host.to(self.flat.device)
-        L.call("fs2_pack_weights", self._items_dev, len(self.packed), self.flat, self.packed_buf, int(bf16))
+        return gl
+
+    def sync_operands(self, bf16: bool):
+        """Make the GEMM operand buffers current.  bf16: the mirror is rewritten by one cast pass unless FusedAdamW.step
+        has just produced it together with the parameter update (`mirror_valid`, consumed here: any parameter change
+        this class cannot see -- torch.optim, load_state_dict, .data edits -- is therefore followed by a fresh cast).
+        fp32: the masters are the operands; only the gathered column block is copied."""
+        dev = self.flat.device
+        gl = self._gather_items()
+        if bf16:
+            if self.mirror is None or self.mirror.device != dev:
+                self.mirror = torch.zeros(self.total + self.gather_total, dtype=torch.bfloat16, device=dev)
+                self.mirror_valid = False
+            if self.mirror_valid and self._mirror_token == self.version_token():
+                self.mirror_valid = False
+                return
+            self.mirror_valid = False
+            L.call("fs2_cast_bf16", self.flat, self.mirror, self.total)
+            if gl:
+                L.call("fs2_pack_weights", self._items_dev, len(gl), self.flat, self.mirror[self.total:], 1)
+        elif gl:
+            if self.gather32 is None or self.gather32.device != dev:
+                self.gather32 = torch.zeros(self.gather_total, dtype=torch.float32, device=dev)
+            L.call("fs2_pack_weights", self._items_dev, len(gl), self.flat, self.gather32, 0)
+
+    def version_token(self):
+        """Sum of the parameters' autograd version counters: changes with every in-place update made through torch
+        (optimizers, load_state_dict, p.copy_() ...); edits through `.data` are invisible to it."""
+        return sum(p._version for p in self.params.values())
+
+    def mark_mirror_current(self):
+        self.mirror_valid = True
+        self._mirror_token = self.version_token()
+
+    def pack(self, bf16: bool):          # former name
+        self.sync_operands(bf16)
+
+    def operand(self, name, bf16: bool):
+        """(buffer, element offset, row pitch) of a GEMM weight operand in the requested operand dtype."""
+        pw = self.packed[name][1]
+        if pw.gather:
+            return (self.mirror, self.total + pw.goff, pw.k * pw.cin) if bf16 else (self.gather32, pw.goff, pw.k * pw.cin)
+        return (self.mirror if bf16 else self.flat), pw.off, pw.k * pw.cin
+
+    def adamw_gather(self):
+        """The single gathered operand FusedAdamW keeps current inside its own pass: (src_off, src_ld, rows, cols, dst_off)
+        in flat / mirror elements, or None."""
+        gl = [pw for _, (_, pw) in self.packed.items() if pw.gather]
+        if len(gl) != 1 or gl[0].k != 1:
+            return None
+        pw = gl[0]
+        return (pw.off + pw.src_col0, pw.src_ld, pw.cout, pw.cin, self.total + pw.goff)
 
     def pw(self, name) -> PackedWeight:
         return self.packed[name][1]

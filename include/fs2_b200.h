@@ -253,6 +253,15 @@ int fs2_ssim_loss(const float* mel_out, const float* mel_tgt, const int64_t* mel
 /* train.py:81 AdamW (torch defaults: decoupled weight decay, bias correction) over one flat buffer */
 int fs2_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
               float beta2, float eps, float wd, int step, float grad_scale, void* stream);
+/* The same update over the slice [base, base+n) of the flat parameter buffer, which in the same pass also refreshes the
+ * bf16 operand mirror of that slice (mirror_bf16 = mirror of the WHOLE flat buffer, or NULL) and one gathered operand:
+ * columns [0, g_cols) of the g_rows x g_src_ld matrix at flat offset g_src_off, copied densely to mirror[g_dst_off..]
+ * (g_rows = 0: none).  guard_tc_error != 0: the update is skipped while the tcgen05 kernels' error word is set
+ * (fs2_gemm_tc_error_flag), so a step whose GEMMs timed out never reaches the parameters. */
+int fs2_adamw_fused(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float wd, int step, float grad_scale, void* mirror_bf16, long long base,
+                    long long g_src_off, long long g_src_ld, int g_rows, int g_cols, long long g_dst_off,
+                    int guard_tc_error, void* stream);
 
 /* Intensity extractor glue (rank_model/model.py:56-109).
  * fs2_frames_to_rows: frame features -> padded row space [B*(T+8), Cpad] in operand storage, columns >= C and the

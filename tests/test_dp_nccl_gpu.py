@@ -1,0 +1,42 @@
+"""N-GPU data-parallel parity over NCCL (needs >= 2 visible GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_dp_nccl_gpu.py`;
+skipped on a one-GPU box).  The worker is tests/dp_parity_worker.py; its measured numbers of the round are kept in
+profiles/r02_dp_parity_n2.json."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def test_dp_gradient_is_mean_of_per_rank_oracle_gradients_and_replicas_stay_identical():
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    world = 2
+    port = 29600 + os.getpid() % 1000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dp_parity_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("DPRESULT ")]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "dp_parity_r02.json"), "w") as f:
+        f.write("\n".join(ln[len("DPRESULT "):] for ln in lines) + "\n")
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert len(lines) == world
+    for ln in lines:
+        res = json.loads(ln[len("DPRESULT "):])
+        for precision, flat_tol, worst_tol in (("fp32", 1e-5, 1e-4), ("bf16", 0.05, None)):
+            p = res[precision]
+            assert p["tc_error_flag"] == 0
+            assert p["graphs_captured"] >= 1 and p["params_unchanged_at_lr0"]
+            for step in p["phase1"]:                 # eager, capture and replay steps alike
+                assert step["rl2"] <= flat_tol, (precision, p["phase1"])
+                if worst_tol is not None:
+                    assert step["worst_maxnorm"] <= worst_tol, (precision, p["phase1"])
+            assert p["replicas_bit_identical"], precision
+            assert p["max_param_move"] > 0
