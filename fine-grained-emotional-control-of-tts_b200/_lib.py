@@ -58,6 +58,8 @@ SIGNATURES = {
     "fs2_memset": "piqp",
     "fs2_mse_losses": "pppppppppppiiiippppppppp",
     "fs2_ssim_loss": "pppiiifpppp",
+    "fs2_loss_fused": "ppppppppppp" + "iiii" + "pppppppp" + "p",
+    "fs2_loss_scale_grads": "pppqpppqp",
     "fs2_adamw": "ppppqfffffifp",
     "fs2_adamw_fused": "ppppqfffffifpqqqiiqip",
     "fs2_intensity_segment_mean": "pppiiiipp",
@@ -137,6 +139,8 @@ def load():
     lib.fs2_launch_count.restype = C.c_longlong
     lib.fs2_ssim_ws_floats.restype = C.c_longlong
     lib.fs2_ssim_ws_floats.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.fs2_loss_ws_floats.restype = C.c_longlong
+    lib.fs2_loss_ws_floats.argtypes = [C.c_int]
     codes = {"p": C.c_void_p, "i": C.c_int, "f": C.c_float, "q": C.c_longlong, "Q": C.c_ulonglong}
     for name, sig in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly

@@ -528,25 +528,26 @@ __global__ void __launch_bounds__(256) loss_pass1_kernel(LossArgs a) {
   }
 }
 
-constexpr int LT = 16;                    // mel rows whose gradient one CTA produces
+constexpr int LT = 32;                    // mel rows whose gradient one CTA produces
+constexpr int LTHREADS = 512;
 constexpr int LNR = LT + 2 * (KS - 1);    // input rows staged (10-row halo either side)
 constexpr int LNF = LT + (KS - 1);        // map rows computed (10 recomputed + LT owned)
 constexpr int PW = MAXW;                  // row pitch of input tiles
 constexpr int PM = MAXW - (KS - 1);       // row pitch of map tiles
 constexpr int HB = 10;                    // outputs per thread along a horizontal pass
-constexpr int VB = 9;                     // map rows per thread in the vertical pass
+constexpr int VB = 7;                     // map rows per thread in the vertical pass
 constexpr int GB = 8;                     // rows per thread in the transposed vertical pass
-constexpr int SSIM_SMEM_FLOATS = 2 * LNR * PW + 5 * LNR * PM + 3 * LNF * PM + 8;
+constexpr int SSIM_SMEM_FLOATS = 2 * LNR * PW + 5 * LNR * PM + 3 * LNF * PM + 16;
 static_assert(3 * LT * PM + LT * PW <= 5 * LNR * PM, "vz + dq alias the moment tiles");
 
-__global__ void __launch_bounds__(256, 2) ssim_fused_kernel(LossArgs a) {
+__global__ void __launch_bounds__(LTHREADS, 1) ssim_fused_kernel(LossArgs a) {
   pdl_wait();
   extern __shared__ float sm[];
   float* q = sm;                          // [LNR][PW] normalised prediction
   float* tn = q + LNR * PW;               // [LNR][PW] normalised target
   float* hz = tn + LNR * PW;              // [5][LNR][PM] horizontal moments
   float* f = hz + 5 * LNR * PM;           // [3][LNF][PM] gradient fields of the map
-  float* sh = f + 3 * LNF * PM;           // [8]
+  float* sh = f + 3 * LNF * PM;           // [16]
   float* vz = hz;                         // [3][LT][PM]   (after the vertical pass the moments are dead)
   float* dqs = hz + 3 * LT * PM;          // [LT][PW]
   const int tid = threadIdx.x;
@@ -590,20 +591,21 @@ __global__ void __launch_bounds__(256, 2) ssim_fused_kernel(LossArgs a) {
     const int ncb = (Wm + HB - 1) / HB;
     for (int task = tid; task < LNR * ncb; task += blockDim.x) {
       const int r = task / ncb, c0 = (task - r * ncb) * HB;
-      float x[HB + KS - 1], y[HB + KS - 1];
+      float x[HB + KS - 1], y[HB + KS - 1], xx[HB + KS - 1], yy[HB + KS - 1], xy[HB + KS - 1];
 #pragma unroll
       for (int i = 0; i < HB + KS - 1; ++i) {
         const bool in = c0 + i < W;
         x[i] = in ? tn[r * PW + c0 + i] : 0.f;
         y[i] = in ? q[r * PW + c0 + i] : 0.f;
+        xx[i] = x[i] * x[i]; yy[i] = y[i] * y[i]; xy[i] = x[i] * y[i];
       }
 #pragma unroll
       for (int o = 0; o < HB; ++o) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
 #pragma unroll
         for (int k = 0; k < KS; ++k) {
-          const float gx = g[k] * x[o + k], gy = g[k] * y[o + k];
-          a0 += gx; a1 += gy; a2 += gx * x[o + k]; a3 += gy * y[o + k]; a4 += gx * y[o + k];
+          a0 = fmaf(g[k], x[o + k], a0); a1 = fmaf(g[k], y[o + k], a1); a2 = fmaf(g[k], xx[o + k], a2);
+          a3 = fmaf(g[k], yy[o + k], a3); a4 = fmaf(g[k], xy[o + k], a4);
         }
         if (c0 + o < Wm) {
           float* h = hz + r * PM + c0 + o;
@@ -651,13 +653,14 @@ __global__ void __launch_bounds__(256, 2) ssim_fused_kernel(LossArgs a) {
           // x = target, y = prediction (gradient wrt y)
           const float mx = m[o][0], my = m[o][1];
           const float sxx = m[o][2] - mx * mx, syy = m[o][3] - my * my, sxy = m[o][4] - mx * my;
-          const float denL = mx * mx + my * my + c1, denC = sxx + syy + c2;
-          const float Lm = (2.f * mx * my + c1) / denL, CS = (2.f * sxy + c2) / denC;
+          // two reciprocals instead of seven IEEE divisions (rcp.approx: <= 1 ulp, far inside the 2e-5 loss tolerance)
+          const float rL = __fdividef(1.0f, mx * mx + my * my + c1), rC = __fdividef(1.0f, sxx + syy + c2);
+          const float Lm = (2.f * mx * my + c1) * rL, CS = (2.f * sxy + c2) * rC;
           if (mlr >= KS - 1) acc_total += Lm * CS;                    // owned rows: mr >= t0
-          const float dL_dmy = (2.f * mx - 2.f * my * Lm) / denL;
-          fb = -Lm * CS / denC;                                       // d ss / d E[y^2]
-          fc = 2.f * Lm / denC;                                       // d ss / d E[xy]
-          fa = CS * dL_dmy + Lm * ((2.f / denC) * (-mx) + (-CS / denC) * (-2.f * my));
+          const float dL_dmy = (2.f * mx - 2.f * my * Lm) * rL;
+          fb = -Lm * CS * rC;                                         // d ss / d E[y^2]
+          fc = 2.f * Lm * rC;                                         // d ss / d E[xy]
+          fa = CS * dL_dmy + 2.f * Lm * rC * (CS * my - mx);
         }
         f[mlr * PM + c] = fa; f[LNF * PM + mlr * PM + c] = fb; f[2 * LNF * PM + mlr * PM + c] = fc;
       }
@@ -958,7 +961,7 @@ extern "C" int fs2_loss_fused(const float* mel_out, const float* post_out, const
   gx = gx < 1 ? 1 : (gx > 32 ? 32 : gx);
   FS2_LAUNCH((loss_pass1_kernel), dim3(gx, B), 256, 0, ST, a);
   if ((rc = fs2_check_launch())) return rc;
-  FS2_LAUNCH((ssim_fused_kernel), dim3((unsigned)((Tm + LT - 1) / LT), B), 256, smem, ST, a);
+  FS2_LAUNCH((ssim_fused_kernel), dim3((unsigned)((Tm + LT - 1) / LT), B), LTHREADS, smem, ST, a);
   if ((rc = fs2_check_launch())) return rc;
   FS2_LAUNCH((loss_finalize_kernel), dim3(FIN_X, B), 256, 0, ST, a);
   return fs2_check_launch();

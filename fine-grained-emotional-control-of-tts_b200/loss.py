@@ -1,7 +1,8 @@
 """Drop-in `Loss` for `/root/reference/emo_rank_tts/fastspeech2/loss.py:31-186`: five per-sample sliced MSE
-terms + speechbrain SSIMLoss, weighted sum, 7-key dict.  Forward values and the gradients wrt the five
-predictions come out of two fused CUDA passes (fs2_mse_losses, fs2_ssim_loss); no per-sample Python loop,
-no host synchronisation."""
+terms + speechbrain SSIMLoss, weighted sum, 7-key dict.  Forward values AND the gradients wrt the five
+predictions come out of one C-ABI call (`fs2_loss_fused`: three kernel launches, csrc/losses.cu); the backward is
+one more launch that only does work when autograd's upstream gradient is not 1.  No per-sample Python loop, no
+host synchronisation, no torch arithmetic kernels."""
 from __future__ import annotations
 
 import torch
@@ -10,7 +11,17 @@ import torch.nn as nn
 from . import _lib as L
 
 
-_WEIGHT_CACHE = {}
+_WS_CACHE = {}
+
+
+def _workspace(dev, B):
+    """Zero-initialised scratch of the fused loss; the kernels hand it back zeroed after every call."""
+    key = (dev, B)
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        ws = torch.zeros(int(L.load().fs2_loss_ws_floats(B)), device=dev, dtype=torch.float32)
+        _WS_CACHE[key] = ws
+    return ws
 
 
 class _LossFn(torch.autograd.Function):
@@ -33,44 +44,36 @@ class _LossFn(torch.autograd.Function):
         mel_len = mel_len.contiguous().long().to(dev)
         phon_len = phon_len.contiguous().long().to(dev)
         w_ssim, w_mel, w_post, w_dur, w_pitch, w_energy = weights
-        wh = (L.C.c_float * 5)(w_mel, w_post, w_dur, w_pitch, w_energy)
+        wh = (L.C.c_float * 6)(w_mel, w_post, w_dur, w_pitch, w_energy, w_ssim)
         need = any(ctx.needs_input_grad[:5])
         out = torch.empty(8, device=dev, dtype=torch.float32)
         dmel = torch.empty_like(mel_out) if need else None
         dpost = torch.empty_like(post_out) if need else None
-        ddur = torch.empty(B, Tp, device=dev) if need else None
-        dpitch = torch.empty(B, Tp, device=dev) if need else None
-        denergy = torch.empty(B, Tp, device=dev) if need else None
-        sums = torch.empty(5 * B, device=dev, dtype=torch.float32)
+        dph = torch.empty(3, B, Tp, device=dev) if need else None
         lib = L.load()
-        rc = lib.fs2_mse_losses(mel_out.data_ptr(), post_out.data_ptr(), mel_tgt.data_ptr(), log_dur.data_ptr(),
-                                dur_tgt.data_ptr(), pitch_pred.data_ptr(), pitch_tgt.data_ptr(), energy_pred.data_ptr(),
-                                energy_tgt.data_ptr(), mel_len.data_ptr(), phon_len.data_ptr(), B, Tp, Tm, n_mels,
-                                L.C.cast(wh, L.C.c_void_p), sums.data_ptr(), out.data_ptr(),
-                                dmel.data_ptr() if need else None, dpost.data_ptr() if need else None,
-                                ddur.data_ptr() if need else None, dpitch.data_ptr() if need else None,
-                                denergy.data_ptr() if need else None, torch.cuda.current_stream().cuda_stream)
-        L.check(rc, "fs2_mse_losses")
-        ws = torch.empty(int(lib.fs2_ssim_ws_floats(B, Tm, n_mels)) + 4, device=dev, dtype=torch.float32)
-        L.call("fs2_ssim_loss", mel_out, mel_tgt, mel_len, B, Tm, n_mels, float(w_ssim), out[5:], dmel, ws)
-        ctx.grads = (dmel, dpost, ddur, dpitch, denergy)
-        ctx.shapes = None
-        # out[0..4] = mel, postnet, dur, pitch, energy (un-weighted); out[5] = ssim
-        key = (weights, dev)
-        wv = _WEIGHT_CACHE.get(key)
-        if wv is None:
-            wv = torch.tensor([w_mel, w_post, w_dur, w_pitch, w_energy, w_ssim], device=dev, dtype=torch.float32)
-            _WEIGHT_CACHE[key] = wv
-        comps = out[:6] * wv
-        total = comps.sum()
+        P = lambda t: t.data_ptr() if t is not None else None
+        rc = lib.fs2_loss_fused(P(mel_out), P(post_out), P(mel_tgt), P(log_dur), P(dur_tgt), P(pitch_pred), P(pitch_tgt),
+                                P(energy_pred), P(energy_tgt), P(mel_len), P(phon_len), B, Tp, Tm, n_mels,
+                                L.C.cast(wh, L.C.c_void_p), P(_workspace(dev, B)), P(out), P(dmel), P(dpost),
+                                P(dph[0]) if need else None, P(dph[1]) if need else None, P(dph[2]) if need else None,
+                                torch.cuda.current_stream().cuda_stream)
+        L.check(rc, "fs2_loss_fused")
+        ctx.grads = (dmel, dpost, dph)
+        # out[0..4] = weighted mel, postnet, dur, pitch, energy; out[5] = weighted ssim; out[6] = total_loss
+        total, comps = out[6], out[:6]
         ctx.mark_non_differentiable(comps)
         return total, comps
 
     @staticmethod
     def backward(ctx, g_total, _g_comps):
-        dmel, dpost, ddur, dpitch, denergy = ctx.grads
-        return (dmel * g_total, dpost * g_total, ddur * g_total, (dpitch * g_total), (denergy * g_total),
-                None, None, None, None, None, None, None)
+        dmel, dpost, dph = ctx.grads
+        if dmel is None:
+            return (None,) * 12
+        # the gradients were produced for an upstream gradient of 1; anything else is applied in place (one launch that
+        # returns at once when *g_total == 1, the `total_loss.backward()` case)
+        L.call("fs2_loss_scale_grads", g_total.detach().contiguous().float(), dmel, dpost, dmel.numel(), dph[0], dph[1],
+               dph[2], dph[0].numel())
+        return (dmel, dpost, dph[0], dph[1], dph[2], None, None, None, None, None, None, None)
 
 
 class Loss(nn.Module):

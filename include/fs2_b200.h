@@ -250,6 +250,22 @@ long long fs2_ssim_ws_floats(int B, int Tm, int n_mels);
 int fs2_ssim_loss(const float* mel_out, const float* mel_tgt, const int64_t* mel_len, int B, int Tm, int n_mels,
                   float weight, float* out, float* dmel_out, float* ws, void* stream);
 
+/* The whole Loss.forward of loss.py:62-186 (+ the gradients wrt the five predictions) in three launches: one pass for the
+ * MSE sums / d(postnet) / SSIM min-max statistics, one fused SSIM map + gradient pass that also writes d(mel) (MSE + SSIM
+ * parts; the map never leaves shared memory), one finalize (7 values, arg-min/max corrections, SSIMLoss's out-of-range
+ * clamp).  w6 (HOST pointer) = weights of mel, postnet, dur, pitch, energy, ssim.  out8 = the six weighted components in
+ * that order, total_loss, un-clamped ssim value.  ws = fs2_loss_ws_floats(B) floats that are ZERO on entry (allocate once
+ * with zeros); every call leaves them zero again.  dmel..denergy: all NULL (values only) or all non-NULL. */
+long long fs2_loss_ws_floats(int B);
+int fs2_loss_fused(const float* mel_out, const float* post_out, const float* mel_tgt, const float* log_dur_pred,
+                   const int64_t* dur_tgt, const float* pitch_pred, const float* pitch_tgt,
+                   const float* energy_pred, const float* energy_tgt, const int64_t* mel_len, const int64_t* phon_len,
+                   int B, int Tp, int Tm, int n_mels, const float* w6, float* ws, float* out8, float* dmel, float* dpost,
+                   float* ddur, float* dpitch, float* denergy, void* stream);
+/* multiplies the five gradients by the device scalar *g_dev unless it is exactly 1 (autograd's upstream gradient) */
+int fs2_loss_scale_grads(const float* g_dev, float* dmel, float* dpost, long long n_mel, float* ddur, float* dpitch,
+                         float* denergy, long long n_ph, void* stream);
+
 /* train.py:81 AdamW (torch defaults: decoupled weight decay, bias correction) over one flat buffer */
 int fs2_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
               float beta2, float eps, float wd, int step, float grad_scale, void* stream);
