@@ -4,7 +4,12 @@ SURVEY 8f row 3).  Same call (`collate(list_of_samples)`), same 12-tuple, but th
 The reference pads on the host with 5 slice copies per utterance and then ships the padded rectangle (plus `rank_X`, a
 second copy of mel / pitch / energy) over PCIe.  Here the ragged arrays are concatenated into one pinned staging buffer,
 cross PCIe once (no padding, no duplicate), and ONE kernel (`fs2_collate`) writes every padded tensor -- including the
-(B, Tm, 80) transposed mel and the channels-first `rank_X` -- with zero padding.  The host only sorts B lengths."""
+(B, Tm, 80) transposed mel and the channels-first `rank_X` -- with zero padding.  The host only sorts B lengths.
+
+The staging copy is asynchronous (the training loop runs the host ahead of the GPU), so the pinned memory is a small ring:
+every buffer carries the event recorded after its host->device copy and is waited on before it is filled again -- back-to-
+back calls (a prefetching loader) can therefore never overwrite bytes whose DMA has not run yet.  Call it from the process
+that owns the CUDA context (the main process), not from forked DataLoader workers."""
 from __future__ import annotations
 
 import torch
@@ -13,14 +18,19 @@ from . import _lib as L
 
 
 class DeviceCollate:
-    def __init__(self, device="cuda"):
+    def __init__(self, device="cuda", n_staging=3):
         self.device = torch.device(device)
-        self._pin = None
+        self._ring = [[None, None] for _ in range(max(2, int(n_staging)))]      # [pinned buffer, event of its last copy]
+        self._next = 0
 
     def _staging(self, nbytes):
-        if self._pin is None or self._pin.numel() < nbytes:
-            self._pin = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
-        return self._pin
+        slot = self._ring[self._next]
+        self._next = (self._next + 1) % len(self._ring)
+        if slot[1] is not None:
+            slot[1].synchronize()            # the copy that last read this buffer has completed
+        if slot[0] is None or slot[0].numel() < nbytes:
+            slot[0] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        return slot
 
     def __call__(self, batch):
         if self.device.type != "cuda":
@@ -42,7 +52,8 @@ class DeviceCollate:
         o_en = o_pi + 4 * n_fr
         o_desc = o_en + 4 * n_fr
         total = o_desc + 16 * B
-        pin = self._staging(total)
+        slot = self._staging(total)
+        pin = slot[0]
         ph_v = pin[o_ph:o_du].view(torch.int64)
         du_v = pin[o_du:o_mel].view(torch.int64)
         mel_v = pin[o_mel:o_pi].view(torch.float32)
@@ -63,6 +74,8 @@ class DeviceCollate:
             f0 += nf
         dev = self.device
         stage = pin[:total].to(dev, non_blocking=True)                             # the batch's ONLY host->device copy
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
         base = stage.data_ptr()
         mk = lambda *s, dt=torch.float32: torch.empty(*s, device=dev, dtype=dt)
         phoneme, duration = mk(B, Tp, dt=torch.int64), mk(B, Tp, dt=torch.int64)

@@ -40,3 +40,24 @@ def test_device_collate_feeds_the_model_and_the_extractor(pkg):
     with torch.no_grad():
         out = model(phoneme, spk, dur, pitch, energy, intensity=rep)
     assert out[0].shape == mel.shape and torch.equal(out[7], mel_len.cpu())
+
+
+def test_back_to_back_collates_do_not_overwrite_each_others_staging(pkg):
+    """the H2D staging copy is asynchronous, so a second call must not refill pinned bytes whose DMA is still
+    queued behind running kernels.  Keep the stream busy, collate six different batches back to back, then compare every one
+    with a collate done in isolation."""
+    batches = [MG.samples(seed=20 + i, n=4) for i in range(6)]
+    solo = []
+    for b in batches:
+        solo.append(pkg.DeviceCollate("cuda")(b))
+        torch.cuda.synchronize()
+    coll = pkg.DeviceCollate("cuda", n_staging=2)
+    a = torch.randn(8192, 8192, device="cuda")
+    for _ in range(20):
+        a = (a @ a) * 1e-4                          # ~100 ms of queued work in front of the staging copies
+    outs = [coll(b) for b in batches]
+    torch.cuda.synchronize()
+    for o, s in zip(outs, solo):
+        for x, y in zip(o, s):
+            if torch.is_tensor(x):
+                assert torch.equal(x, y)

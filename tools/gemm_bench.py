@@ -67,6 +67,15 @@ def main():
     rec("fwd qkv 384->1152 bf16", 2.0 * rows * 3 * D * D, (lambda i: m._conv(xD[i % R], B, T, lay(i) + ".self_att.att.in_proj_weight", qkv[i % R], c_bf16=True)))
     rec("fwd out_proj 384->384 f32", 2.0 * rows * D * D, (lambda i: m._conv(xD[i % R], B, T, lay(i) + ".self_att.att.out_proj.weight", oD32[i % R], c_bf16=False)))
     rec("dgrad conv9 1536->384 f32", f9, (lambda i: m._conv_dgrad(xF[i % R], B, T, lay(i) + ".pos_ffn.0.conv.weight", oD32[i % R])))
+    # experiment: the same dgrad with a K-major ([Cin][tap][Cout]) weight copy, i.e. through the forward-mode kernel
+    wT = torch.randn(D, 9 * Fd, device="cuda").to(bf)
+    oS = [torch.empty(2, rows, D, device="cuda") for _ in range(2)]
+    for split in (1, 2):
+        rec(f"dgrad conv9 K-major weights split{split}", f9, (lambda i: L.gemm(
+            mode=0, M=rows, N=D, K=Fd, taps=9, A=xF[i % R], lda=Fd, a_rows=rows, a_inner=Fd, a_row_off=4, a_tap_step=-1,
+            B=wT, ldb=9 * Fd, b_rows=D, b_inner=9 * Fd, b_tap_step=Fd, Cout=oS[i % 2], ldc=D, c_bf16=False, ab_bf16=True,
+            split_k=split, c_split_stride=rows * D if split > 1 else 0)))
+        rec(f"dgrad conv9 MN-major (model) split{split}", f9, (lambda i: m._conv_dgrad(xF[i % R], B, T, lay(i) + ".pos_ffn.0.conv.weight", oS[i % 2] if split > 1 else oD32[i % R], split=split)))
     rec("dgrad conv1 384->1536 bf16 relu_aux", f1, (lambda i: m._conv_dgrad(xD[i % R], B, T, lay(i) + ".pos_ffn.2.conv.weight", oF[i % R], c_bf16=True, relu_aux=xF[(i + 1) % R])))
     rec("dgrad qkv 1152->384 f32", 2.0 * rows * 3 * D * D, (lambda i: m._conv_dgrad(qkv[i % R], B, T, lay(i) + ".self_att.att.in_proj_weight", oD32[i % R])))
     rec("wgrad conv9 (+colsum)", f9, (lambda i: m._conv_wgrad(xF[i % R], xD[i % R], B, T, lay(i) + ".pos_ffn.0.conv.weight", lay(i) + ".pos_ffn.0.conv.weight", lay(i) + ".pos_ffn.0.conv.bias")))
