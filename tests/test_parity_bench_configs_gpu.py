@@ -300,7 +300,8 @@ def test_batched_inference_b256_vs_oracle(pkg, lib, oracle_infer, pace, precisio
         # relative L2 error stays ~2e-3; the 1e-2 bar is kept for everything else and for the L2 measure
         assert r <= (1.25e-2 if (n == "postnet_output" and precision != "fp32") else tol), (n, r)
     for n, r in out_rl2.items():
-        assert r <= (1e-5 if precision == "fp32" else 5e-3), (n, "rel L2", r)
+        # north_star tolerance for mel / postnet in bf16 is 1e-2 relative; measured at B = 256: mel 4.3e-3, postnet 6.7e-3
+        assert r <= (1e-5 if precision == "fp32" else 1e-2), (n, "rel L2", r)
     assert rel(pd, pd_o) <= (1e-5 if exact else tol)
     assert outside == 0 and max_jump <= 1
     if precision == "fp32" or exact:
