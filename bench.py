@@ -199,28 +199,18 @@ def eager_gpu_reference_run(steps=4, warmup=4, batch=BATCH):
     del model, opt, batches
     torch.cuda.empty_cache()
     return {"value": frames / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "kind": "port",
+            "torch_backends": {"cuda.matmul.allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
+                               "cudnn.allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+                               "float32_matmul_precision": torch.get_float32_matmul_precision(),
+                               "cudnn.benchmark": bool(torch.backends.cudnn.benchmark)},
             "sample": f"{steps} training steps of batch {batch} on cuda:0 (oracle restatement of the reference, eager PyTorch "
-                      "fp32, TF32 off, dropout on, AdamW); same batches as the GPU workload"}
+                      "fp32 with torch's stock backend flags -- the reference sets none, see torch_backends --, dropout on, "
+                      "AdamW); same batches as the GPU workload"}
 
 
-# ------------------------------------------------------------------------------------------- dominant kernel
-def dominant_kernel_roofline(pkg, model, peaks, B=BATCH, Tm=800, iters=12):
-    """tcgen05 implicit-GEMM Conv1d k=9 (decoder FFN, 384 -> 1536 + bias + ReLU): the largest share of the step.
-    Timed alone with CUDA events on the launching stream, rotating over the 6 decoder layers' weights and 3
-    activation buffers so that operands are not L2-resident between launches."""
-    L = importlib.import_module(PKG + "._lib")
-    D, F = model.D, model.dec["F"]
-    rows = B * (Tm + 2 * L.PAD)
-    xs = [torch.randn(rows, D, device="cuda").to(torch.bfloat16) for _ in range(3)]
-    ys = [torch.empty(rows, F, device="cuda", dtype=torch.bfloat16) for _ in range(3)]
-    model.store.pack(True)
-    nl = model.dec["nl"]
-
-    def launch(i):
-        pre = f"decoder.layers.{i % nl}.pos_ffn.0.conv"
-        model._conv(xs[i % 3], B, Tm, pre + ".weight", ys[i % 3], c_bf16=True, bias=model._P(pre + ".bias"), relu=1)
-
-    for i in range(6):
+# ------------------------------------------------------------------------------------------- dominant kernels
+def _time_launches(launch, iters, warm=6):
+    for i in range(warm):
         launch(i)
     torch.cuda.synchronize()
     st = torch.cuda.current_stream()
@@ -230,22 +220,98 @@ def dominant_kernel_roofline(pkg, model, peaks, B=BATCH, Tm=800, iters=12):
         launch(i)
     e1.record(st)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    return e0.elapsed_time(e1) / iters
+
+
+def conv9_trio_roofline(pkg, model, peaks, B=BATCH, Tm=800, iters=12):
+    """The decoder FFN Conv1d k=9 (384 <-> 1536) as tcgen05 implicit GEMMs: forward (+bias+ReLU), dgrad and wgrad are 75 %
+    of the step's FLOPs.  Each is timed alone with CUDA events on the launching stream, rotating over the 6 decoder
+    layers' weights and 3 activation buffers so that operands are not L2-resident between launches.  `kernel` of the
+    roofline object is the dgrad: the largest share of the backward's critical path (the forward is the fastest of the
+    three, the wgrad runs on the side stream)."""
+    L = importlib.import_module(PKG + "._lib")
+    D, F = model.D, model.dec["F"]
+    rows = B * (Tm + 2 * L.PAD)
+    bf = torch.bfloat16
+    xs = [torch.randn(rows, D, device="cuda").to(bf) for _ in range(3)]
+    ys = [torch.randn(rows, F, device="cuda").to(bf) for _ in range(3)]
+    model.store.pack(True)
+    model.store.ensure_grads()
+    nl = model.dec["nl"]
+    split = model._dgrad_split(rows, D)
+    dxs = [torch.empty(split, rows, D, device="cuda") for _ in range(2)]
+    pre = lambda i: f"decoder.layers.{i % nl}.pos_ffn.0.conv"
     flops = 2.0 * rows * F * D * model.k0
-    achieved = flops / (ms * 1e-3) / 1e12
-    traffic = None
+    traffic = {}
     pj = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(pj):
         try:
-            traffic = json.load(open(pj)).get("dram_bytes_per_launch")
+            traffic = json.load(open(pj))
         except Exception:
-            traffic = None
-    return {"bound": "tensor", "kernel": "tc_gemm_kernel<mode0> decoder FFN Conv1d k=9 384->1536 (+bias+ReLU), "
-            f"M={rows} N={F} K={D}x{model.k0}", "achieved": achieved, "peak": peaks["tc_burst"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tc_burst"], "traffic": traffic,
+            traffic = {}
+
+    def one(name, kernel, launch, alg_bytes):
+        ms = _time_launches(launch, iters)
+        ach = flops / (ms * 1e-3) / 1e12
+        t = traffic.get(name, {}) if isinstance(traffic.get(name), dict) else {}
+        return {"kernel": kernel, "achieved": ach, "frac": ach / peaks["tc_burst"], "ms_per_launch": ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "traffic": t.get("dram_bytes_per_launch"),
+                "tensor_pipe_active_pct_ncu": t.get("tensor_pipe_active_pct")}
+
+    w_bytes = F * D * model.k0 * 2
+    trio = {
+        "forward": one("forward", "tcx_gemm_kernel<0,256,1,6,2> (CTA pair, 256x256 tiles): y = relu(conv9(x) + b), bf16 out",
+                       lambda i: model._conv(xs[i % 3], B, Tm, pre(i) + ".weight", ys[i % 3], c_bf16=True,
+                                             bias=model._P(pre(i) + ".bias"), relu=1),
+                       rows * D * 2 + w_bytes + rows * F * 2),
+        "dgrad": one("dgrad", f"tcx_gemm_kernel<1,128,3,5,2> (CTA pair, 256x384 tiles, deterministic split-K {split}): dx = conv9^T(dy), fp32 out",
+                     lambda i: model._conv_dgrad(ys[i % 3], B, Tm, pre(i) + ".weight", dxs[i % 2] if split > 1 else dxs[i % 2][0],
+                                                 split=split),
+                     rows * F * 2 + w_bytes + split * rows * D * 4),
+        "wgrad": one("wgrad", "tc_gemm_kernel<2,192,5> (split-K over the SMs, fp32 vector atomics): dW = dy^T x",
+                     lambda i: model._conv_wgrad_launch(ys[i % 3], xs[i % 3], B, Tm, pre(i) + ".weight", pre(i) + ".weight"),
+                     rows * F * 2 + rows * D * 2 + F * D * model.k0 * 4),
+    }
+    d = trio["dgrad"]
+    return {"bound": "tensor", "kernel": d["kernel"] + f", decoder FFN Conv1d k=9, M={rows} N={D} K={F}x{model.k0}",
+            "achieved": d["achieved"], "peak": peaks["tc_burst"], "unit": "TFLOP/s", "frac": d["frac"],
+            "traffic": d["traffic"],
             "traffic_note": "DRAM read+write bytes of one launch, ncu --set full (profiles/dominant_kernel_traffic.json)",
-            "algorithmic_bytes_per_launch": rows * D * 2 + F * D * model.k0 * 2 + rows * F * 2, "ms_per_launch": ms,
-            "flops_per_launch": flops, "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
+            "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "ms_per_launch": d["ms_per_launch"],
+            "flops_per_launch": flops, "peak_source": peaks["src"] + " (burst: kernel timed alone)",
+            "trio": trio}
+
+
+def memory_kernels(peaks):
+    """HBM fractions of the memory-bound kernels, measured in this run (tools/hbm_bench.py through the C ABI, rings of
+    buffers larger than L2): LengthRegulator plain / fused / backward, LayerNorm forward / backward, losses, AdamW."""
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ.setdefault("LR_BULK", "8")
+    os.environ.setdefault("LN_PF", "1")
+    os.environ.setdefault("HBM_ITERS", "24")
+    hb = importlib.import_module("hbm_bench")
+    with contextlib.redirect_stdout(io.StringIO()):
+        rows = hb.main()
+    torch.cuda.empty_cache()
+    return [{"kernel": r["kernel"], "us": r["us"], "GB/s": r["GB/s"], "frac_of_hbm_peak": r["frac_of_hbm_peak"],
+             "alg_bytes": r["alg_bytes"]} for r in rows]
+
+
+def inference_b256():
+    """BASELINE configs[4] in the same run: batch 256, predicted durations, pace 0.8 / 1.0 / 1.2 (tools/infer_bench.py)."""
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ.setdefault("INFER_STEPS", "8")
+    ib = importlib.import_module("infer_bench")
+    with contextlib.redirect_stdout(io.StringIO()):
+        rows = ib.main()
+    torch.cuda.empty_cache()
+    return [{"pace": r["config"]["pace"], "value": r["value"], "unit": r["unit"], "ms_per_step": r["ms_per_step"],
+             "valid_frames_per_step": r["config"]["valid_frames_per_step"], "padded_Tm": r["config"]["padded_Tm_last"],
+             "tflops": r.get("tflops")} for r in rows]
 
 
 # ------------------------------------------------------------------------------------------------------ main
@@ -259,6 +325,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-mel-lens", action="store_true", help="read mel_lens back synchronously every step (the reference's contract)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained / strict-contract / memory-kernel / inference legs")
+    ap.add_argument("--sustained-steps", type=int, default=320)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -399,6 +467,25 @@ def main():
     ms_e, tot_e, _ = timed(args.steps, 0, True)      # back to back with the resident run: no idle gap, same clocks
     clocks = sampler.stop() if rank == 0 else None
 
+    extras = {}
+    if world == 1 and not args.no_extras:
+        # (a) the strict drop-in contract: mel_lens read back synchronously every step (reference model.py:440), e2e loop
+        if model.async_mel_lens:
+            model.async_mel_lens = False
+            run(N_DISTINCT + 2, 0, True)
+            ms_s, tot_s, _ = timed(args.steps, 0, True)
+            model.async_mel_lens = True
+            extras["e2e_sync_mel_lens"] = {"value": tot_s / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / args.steps,
+                                           "note": "same e2e loop with model.async_mel_lens = False: one host sync per step for "
+                                                   "mel_lens, as the reference returns it"}
+        # (b) sustained: a long timed region with its own clock / power record
+        s2 = ClockSampler(local)
+        s2.start()
+        ms_l, tot_l, _ = timed(args.sustained_steps, 0, False)
+        c2 = s2.stop()
+        extras["sustained"] = {"value": tot_l / (ms_l * 1e-3), "unit": UNIT, "steps": args.sustained_steps,
+                               "ms_per_step": ms_l / args.sustained_steps, "timed_region_s": ms_l * 1e-3, "clocks": c2}
+
     if rank != 0:
         return
     value = tot / (ms * 1e-3)
@@ -407,7 +494,7 @@ def main():
     # whole-step tensor-core utilisation (explains `value`): algorithmic FLOPs of the padded rectangles
     fl = sum(step_flops(BATCH, tp, tm, pkg.DEFAULT_MODEL_CONFIG) for tp, tm in shapes) / N_DISTINCT
     step_tflops = fl * world / (ms * 1e-3 / args.steps) / 1e12
-    roof = dominant_kernel_roofline(pkg, model, peaks)
+    roof = conv9_trio_roofline(pkg, model, peaks)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -434,6 +521,13 @@ def main():
                              "frac": step_tflops / (peaks["tc_sustained"] * world),
                              "flops_per_step_per_gpu": fl, "peak_source": peaks["src"] + " (sustained)"},
     }
+    line.update(extras)
+    if world == 1 and not args.no_extras:
+        for key, fn in (("memory_kernels", lambda: memory_kernels(peaks)), ("inference_b256", inference_b256)):
+            try:
+                line[key] = fn()
+            except Exception as e:                   # an evidence leg must never take the product number down with it
+                line[key] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(8, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}

@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfs2_b200.so")
+# FS2_B200_LIB: measurement tools load the probe build (make -C csrc probe) instead; never a fallback -- a missing file raises
+LIB_PATH = os.environ.get("FS2_B200_LIB") or os.path.join(_HERE, "libfs2_b200.so")
 
 PAD = 4  # FS2_PAD: halo rows either side of every batch item in the padded row space
 
@@ -43,6 +44,9 @@ SIGNATURES = {
     "fs2_collate": "pppppppppiiiipppppp" + "p",
     "fs2_intensity_head": "ppppppiiiipp",
     "fs2_attn_bwd": "pppppiiiiiffQpppp",
+    "fs2_flash_attn_fwd": "ppiiiiffQpppip",
+    "fs2_flash_attn_bwd": "pppppiiiiffQpppip",
+    "fs2_flash_attn_mask": "iifQppp",
     "fs2_dur_decode": "pqpp",
     "fs2_lr_prepare": "ppfiippp",
     "fs2_lr_finalize": "piippp",

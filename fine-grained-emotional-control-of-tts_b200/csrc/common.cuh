@@ -129,6 +129,42 @@ __device__ __forceinline__ float4 drop_scale4(const DropCfg& d, uint64_t group) 
   return o;
 }
 
+// Attention-probability dropout (nn.MultiheadAttention's dropout on the softmax output): one 32-bit hash per element,
+// symmetric in (query t, key c).  The forward and the dQ kernel walk the keys of a query row, the dK/dV kernel walks the
+// queries of a key row; both regenerate the same mask with one thread-constant term hoisted out of the loop.
+struct ADrop {
+  uint32_t s;     // key of this (launch, item, head)
+  uint32_t thr;   // drop iff hash < thr = p * 2^32
+  float ks;       // 1 / (1 - p)
+};
+constexpr uint32_t ADROP_KT = 0x9E3779B1u, ADROP_KC = 0x85EBCA6Bu;
+__device__ __forceinline__ ADrop adrop_make(float p, unsigned long long seed, const unsigned long long* seed_dev, int bh) {
+  ADrop d;
+  if (seed_dev) seed ^= mix64(*seed_dev);
+  d.s = (uint32_t)(mix64(seed ^ (0xA24BAED4963EE407ull * (uint64_t)(bh + 1))) >> 32);
+  d.thr = p > 0.f ? (uint32_t)fminf(p * 4294967296.0f, 4294967040.0f) : 0u;
+  d.ks = 1.0f / (1.0f - p);
+  return d;
+}
+// x = d.s ^ (t * ADROP_KT) ^ (c * ADROP_KC)
+__device__ __forceinline__ bool adrop_keep(uint32_t x, uint32_t thr) {
+  uint32_t h = x * 0xCC9E2D51u;
+  h ^= h >> 15;
+  h *= 0x1B873593u;
+  return h >= thr;
+}
+
+// keep-scales (0 or 1/(1-p)) of keys c .. c+3 of one query row; tpart = d.s ^ (t * ADROP_KT)
+__device__ __forceinline__ float4 adrop_scale4(const ADrop& d, uint32_t tpart, int c) {
+  if (d.thr == 0u) return make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 o;
+  o.x = adrop_keep(tpart ^ ((uint32_t)c * ADROP_KC), d.thr) ? d.ks : 0.f;
+  o.y = adrop_keep(tpart ^ ((uint32_t)(c + 1) * ADROP_KC), d.thr) ? d.ks : 0.f;
+  o.z = adrop_keep(tpart ^ ((uint32_t)(c + 2) * ADROP_KC), d.thr) ? d.ks : 0.f;
+  o.w = adrop_keep(tpart ^ ((uint32_t)(c + 3) * ADROP_KC), d.thr) ? d.ks : 0.f;
+  return o;
+}
+
 // (b, t) <-> flat padded row helpers
 struct RowSpace {
   int T;      // valid rows per batch item

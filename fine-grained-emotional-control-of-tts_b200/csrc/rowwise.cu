@@ -443,11 +443,13 @@ __global__ void __launch_bounds__(THREADS) softmax_fwd_kernel(const float* S, co
                                                               int ldk, float scale, DropCfg dc, const unsigned long long* seed_dev, TA* P, TA* Pd) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  if (seed_dev) dc.seed ^= mix64(*seed_dev);
   const long long rows = (long long)B * H * T;
   for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
     const int bh = (int)(r / T);
     const int kv = quirk_kv(lens, B, H, bh);
+    // the same per-element dropout hash as the flash-style kernels (flash_attention.cu), so both paths draw one mask
+    const ADrop dr = adrop_make(dc.p, dc.seed, seed_dev, bh);
+    const uint32_t tpart = dr.s ^ ((uint32_t)(r - (long long)bh * T) * ADROP_KT);
     const float* s = S + r * ldk;
     float mx = -INFINITY;
     for (int c = lane * 4; c < kv; c += 128) {
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(THREADS) softmax_fwd_kernel(const float* S, co
       }
       st4(P + r * ldk + c, o);
       if (Pd) {
-        float4 k = drop_scale4(dc, (uint64_t)(r * ldk + c) >> 2);
+        const float4 k = adrop_scale4(dr, tpart, c);
         st4(Pd + r * ldk + c, make_float4(o.x * k.x, o.y * k.y, o.z * k.z, o.w * k.w));
       }
     }
@@ -491,16 +493,17 @@ __global__ void __launch_bounds__(THREADS) softmax_bwd_kernel(const TA* P, const
                                                               const unsigned long long* seed_dev, TA* dS) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  if (seed_dev) dc.seed ^= mix64(*seed_dev);
   const long long rows = (long long)B * H * T;
   for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
     const int bh = (int)(r / T);
     const int kv = quirk_kv(lens, B, H, bh);
+    const ADrop dr = adrop_make(dc.p, dc.seed, seed_dev, bh);
+    const uint32_t tpart = dr.s ^ ((uint32_t)(r - (long long)bh * T) * ADROP_KT);
     const long long ro = r * ldk;
     float dot = 0.f;
     for (int c = lane * 4; c < kv; c += 128) {
       float4 pv = ld4(P + ro + c), g = ld4(dPd + ro + c);
-      float4 k = drop_scale4(dc, (uint64_t)(ro + c) >> 2);
+      const float4 k = adrop_scale4(dr, tpart, c);
       dot += pv.x * g.x * k.x + pv.y * g.y * k.y + pv.z * g.z * k.z + pv.w * g.w * k.w;   // P is 0 beyond kv
     }
     dot = warp_sum(dot);
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(THREADS) softmax_bwd_kernel(const TA* P, const
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < kv) {
         float4 pv = ld4(P + ro + c), g = ld4(dPd + ro + c);
-        float4 k = drop_scale4(dc, (uint64_t)(ro + c) >> 2);
+        const float4 k = adrop_scale4(dr, tpart, c);
         o.x = scale * pv.x * (g.x * k.x - dot);
         o.y = scale * pv.y * (g.y * k.y - dot);
         o.z = scale * pv.z * (g.z * k.z - dot);

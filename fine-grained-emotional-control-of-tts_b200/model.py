@@ -427,9 +427,9 @@ class FastSpeech2(nn.Module):
         ldk = _rup(T, 8)
         bf = self._bf16
         if S is None:
-            # fused tcgen05 attention: scores, softmax, dropout and PV in one kernel (attention.cu)
-            L.call("fs2_attn_fwd", qkv, lens, B, H, T, D, ldk, 1.0 / math.sqrt(hd), p_drop, seed, self._ctr, P,
-                   Pd if (p_drop > 0 and P is not None) else None, O)
+            # flash-style tcgen05 attention: scores, softmax, dropout and PV in one kernel, nothing T x T in HBM
+            # (flash_attention.cu); P is the per-row log-sum-exp statistic here (None: inference)
+            L.call("fs2_flash_attn_fwd", qkv, lens, B, H, T, D, 1.0 / math.sqrt(hd), p_drop, seed, self._ctr, P, O, 0)
             return
         # S[b,h] = Q K^T
         L.gemm(mode=0, M=T, N=T, K=hd, A=qkv, A_off=PAD * ld, lda=ld, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * ld,
@@ -461,8 +461,10 @@ class FastSpeech2(nn.Module):
             sv.qkv = self._act(rows, 3 * D)
             self._conv(x_act, B, T, f"{pre}.self_att.att.in_proj_weight", sv.qkv, c_bf16=bf,
                        bias=self._P(f"{pre}.self_att.att.in_proj_bias"))
-            if fused and not keep_p:
-                sv.P = sv.Pd = None             # no backward can follow (inference): the probabilities stay on chip
+            if fused:
+                # the probabilities stay on chip; the backward recomputes them from one fp32 statistic per query row
+                sv.P = self._f32(B * H, _rup(T, 128)) if keep_p else None
+                sv.Pd = None
             else:
                 sv.P = self._act(B * H, T, ldk)
                 sv.Pd = self._act(B * H, T, ldk) if p > 0 else sv.P
@@ -516,7 +518,7 @@ class FastSpeech2(nn.Module):
         # scratch shared by all layers
         fused = self._fused_attn(H)
         dPd = None if fused else self._f32(B * H, T, ldk)
-        dS = self._act(B * H, T, ldk)
+        dS = self._f32(B * H, _rup(T, 128)) if fused else self._act(B * H, T, ldk)    # fused: rowsum(dO * O) scratch
         dqkv = self._act(rows, ld)
         dF_act, dH_act = self._act(rows, D), self._act(rows, F)
         dHc = self._f32(rows, F) if h2 > 0 else None
@@ -563,25 +565,25 @@ class FastSpeech2(nn.Module):
                 L.gemm(mode=0, M=T, N=T, K=hd, A=dO_act, A_off=PAD * D, lda=D, a_rows=T, a_inner=hd, a_s1=hd, a_s2=TP * D,
                        B=sv.qkv, B_off=PAD * ld + 2 * D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld,
                        batch1=H, batch2=B, Cout=dPd, ldc=ldk, c_s1=T * ldk, c_s2=H * T * ldk, c_bf16=False, ab_bf16=bf)
-            # dV = Pd^T dO
             self._wait_side(dqkv)
-            L.gemm(mode=2, M=T, N=hd, K=T, A=sv.Pd, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
-                   B=dO_act, B_off=PAD * D, ldb=D, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * D, batch1=H, batch2=B,
-                   Cout=dqkv, C_off=PAD * ld + 2 * D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
             if fused:
-                # dPd (TMEM) -> dS -> global, dQ = dS K accumulated in TMEM (attention.cu)
-                L.call("fs2_attn_bwd", dO_act, sv.O, sv.qkv, sv.P, lens, B, H, T, D, ldk, scale, p, sv.seeds[0], self._ctr,
-                       dS, dqkv)
+                # dQ kernel (recomputes P from the saved row statistic, dS stays in tensor memory) + dK/dV kernel
+                L.call("fs2_flash_attn_bwd", dO_act, sv.O, sv.qkv, sv.P, lens, B, H, T, D, scale, p, sv.seeds[0], self._ctr,
+                       dS, dqkv, 0)
             else:
+                # dV = Pd^T dO
+                L.gemm(mode=2, M=T, N=hd, K=T, A=sv.Pd, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
+                       B=dO_act, B_off=PAD * D, ldb=D, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * D, batch1=H, batch2=B,
+                       Cout=dqkv, C_off=PAD * ld + 2 * D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
                 L.call("fs2_softmax_bwd", sv.P, dPd, lens, B, H, T, ldk, scale, p, sv.seeds[0], self._ctr, dS, int(bf))
                 # dQ = dS K
                 L.gemm(mode=1, M=T, N=hd, K=T, A=dS, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
                        B=sv.qkv, B_off=PAD * ld + D, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
                        Cout=dqkv, C_off=PAD * ld, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
-            # dK = dS^T Q
-            L.gemm(mode=2, M=T, N=hd, K=T, A=dS, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
-                   B=sv.qkv, B_off=PAD * ld, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
-                   Cout=dqkv, C_off=PAD * ld + D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
+                # dK = dS^T Q
+                L.gemm(mode=2, M=T, N=hd, K=T, A=dS, lda=ldk, a_rows=T, a_inner=T, a_s1=T * ldk, a_s2=H * T * ldk,
+                       B=sv.qkv, B_off=PAD * ld, ldb=ld, b_rows=T, b_inner=hd, b_s1=hd, b_s2=TP * ld, batch1=H, batch2=B,
+                       Cout=dqkv, C_off=PAD * ld + D, ldc=ld, c_s1=hd, c_s2=TP * ld, c_bf16=bf, ab_bf16=bf)
             self._conv_wgrad(dqkv, sv.x_act, B, T, f"{pre}.self_att.att.in_proj_weight",
                              f"{pre}.self_att.att.in_proj_weight", f"{pre}.self_att.att.in_proj_bias")
             self._conv_dgrad(dqkv, B, T, f"{pre}.self_att.att.in_proj_weight", dXa)

@@ -156,7 +156,7 @@ class IntensityExtractor(nn.Module):
         for ly in pk["layers"]:
             # self-attention (model.py:34-36): key-padding mask only, dropout inactive
             self._gemm(cur_act, ly["wqkv"], ws["qkv"], rows=rows, cin=D, cout=3 * D, k=1, T=T, bias=ly["bqkv"], c_bf16=True)
-            L.call("fs2_attn_fwd_ex", ws["qkv"], lens, B, H, T, D, ldk, scale, 0.0, 0, None, None, None, ws["o"], 1)
+            L.call("fs2_flash_attn_fwd", ws["qkv"], lens, B, H, T, D, scale, 0.0, 0, None, None, ws["o"], 1)
             self._gemm(ws["o"], ly["wo"], ws["proj"], rows=rows, cin=D, cout=D, k=1, T=T, bias=ly["bo"], c_bf16=False)
             self._ln(B, T, D, cur_f32, ws["proj"], ly["g1"], ly["be1"], ly["eps1"], nxt_f32, nxt_act)
             cur_f32, cur_act, nxt_f32, nxt_act = nxt_f32, nxt_act, cur_f32, cur_act

@@ -159,6 +159,28 @@ int fs2_attn_fwd_ex(const void* qkv, const int* lens, int B, int H, int T, int D
 int fs2_attn_bwd(const void* dO, const void* O, const void* qkv, const void* P, const int* lens, int B, int H, int T,
                  int D, int ldk, float scale, float drop_p, unsigned long long seed,
                  const unsigned long long* seed_dev, void* dS, void* dqkv, void* stream);
+/* Flash-style attention (flash_attention.cu; reference model.py:344-346, 425-427 through nn.MultiheadAttention's math
+ * path): nothing of size T x T reaches HBM.  qkv (B*(T+8), 3D) bf16 padded rows [Q | K | V], head_dim 192.
+ * forward: O (B*(T+8), D) bf16, rows t < T written; lse (B*H, fs2_flash_attn_lse_len(T)) fp32 = per query row
+ * max + log2(sum 2^(s - max)) of the scaled scores in the log2 domain (NULL: inference, not kept).
+ * Dropout on the probabilities: one 32-bit counter hash per (item, head, query, key), regenerated by the backward
+ * (fs2_flash_attn_mask returns the keep mask as bytes (B*H, T, T) for tests).  plain_mask as in fs2_attn_fwd_ex.
+ * backward: dQ, dK, dV into columns [0,D), [D,2D), [2D,3D) of dqkv (B*(T+8), 3D) bf16, rows t < T written;
+ * two launches: the dQ kernel (also writes dvec = rowsum(dO*O), same shape as lse, scratch) and the dK/dV kernel. */
+int fs2_flash_attn_lse_len(int T);
+int fs2_flash_attn_fwd(const void* qkv, const int* lens, int B, int H, int T, int D, float scale, float drop_p,
+                       unsigned long long seed, const unsigned long long* seed_dev, float* lse, void* O, int plain_mask,
+                       void* stream);
+int fs2_flash_attn_bwd(const void* dO, const void* O, const void* qkv, const float* lse, const int* lens, int B, int H,
+                       int T, int D, float scale, float drop_p, unsigned long long seed,
+                       const unsigned long long* seed_dev, float* dvec, void* dqkv, int plain_mask, void* stream);
+int fs2_flash_attn_mask(int BH, int T, float drop_p, unsigned long long seed, const unsigned long long* seed_dev,
+                        unsigned char* keep, void* stream);
+/* measurement hook: 1 (default) = probabilities go to the second contraction through tensor memory, 0 = through shared memory */
+int fs2_flash_attn_tune(int p_in_tmem);
+/* measurement hook: when non-NULL, CTA 0 of every flash-attention launch writes a 64-slot cycle breakdown (library built
+ * with -DFS2_TC_PROBE only; tools/flash_bench.py FLASH_DBG=1) */
+int fs2_flash_attn_set_debug(long long* dev_buf);
 /* measurement hook: when non-NULL, CTA 0 of every fused-attention launch writes a 16-slot cycle breakdown (attention.cu) */
 int fs2_attn_set_debug(long long* dev_buf);
 /* *ctr += inc (the device-side dropout step counter; first node of a captured forward graph) */

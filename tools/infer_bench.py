@@ -18,6 +18,18 @@ sys.path.insert(0, ROOT)
 PKG = "fine-grained-emotional-control-of-tts_b200"
 
 
+def fwd_flops(B, Tp, Tm, cfg):
+    """Algorithmic dense FLOPs of one forward on the padded rectangle."""
+    D, F, H = cfg["enc_d_model"], cfg["enc_ffn_dim"], cfg["enc_num_head"]
+    k0, k1 = cfg["ffn_cnn_kernel_size_list"]
+    layer = lambda T: B * T * (2 * D * 3 * D + 2 * D * D + 2 * D * F * k0 + 2 * F * D * k1) + B * H * (2 * T * T * (D // H)) * 2
+    f = cfg["enc_num_layers"] * layer(Tp) + cfg["dec_num_layers"] * layer(Tm)
+    f += 3 * B * Tp * (2 * 2 * D * D * cfg["dur_pred_kernel_size"])
+    E, kp, nm = cfg["postnet_embedding_dim"], cfg["postnet_kernel_size"], cfg["n_mels"]
+    f += B * Tm * 2 * kp * (nm * E + (cfg["postnet_n_convolutions"] - 2) * E * E + E * nm)
+    return f + B * Tp * 2 * D * (2 * D + 5) + B * Tm * 2 * D * nm
+
+
 def main():
     pkg = importlib.import_module(PKG)
     B = int(os.environ.get("INFER_BATCH", "256"))
@@ -47,6 +59,7 @@ def main():
         mel_host = out[0].to("cpu", non_blocking=True)        # (B, Tm, 80) -> vocoder side
         return out, mel_host
 
+    rows = []
     for pace in (0.8, 1.0, 1.2):
         for i in range(2 * R):                      # every batch shape twice: the workspace arenas reach their final size
             run(batches[i % R], pace)
@@ -54,23 +67,28 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         frames = 0
         d2h = 0
+        flops = 0.0
         e0.record()
         for i in range(steps):
             out, mel_host = run(batches[i % R], pace)
             frames += int(out[7].sum())
             d2h += mel_host.numel() * 4
+            flops += fwd_flops(B, batches[i % R][0].shape[1], int(out[0].shape[1]), pkg.DEFAULT_MODEL_CONFIG)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        print(json.dumps({
+        rows.append({
             "metric": "fastspeech2_inference_mel_frames_per_sec", "value": frames / (ms * 1e-3), "unit": "mel_frames/s",
             "n_gpus": 1, "steps": steps, "ms_per_step": ms / steps, "dtype": "bf16", "data": "synthetic",
+            "tflops": flops / (ms * 1e-3) / 1e12,
             "config": {"workload": "FastSpeech2 batched inference (BASELINE configs[4])", "batch": B, "pace": pace,
                        "phonemes": "U{24..128} per utterance", "valid_frames_per_step": frames // steps,
                        "padded_Tm_last": int(out[0].shape[1]),
                        "intensity": "per-utterance (5,) prototype broadcast over Tp",
                        "e2e": "pinned host inputs -> device, mel (B,Tm,80) fp32 + mel_lens -> host inside the timed region",
-                       "d2h_bytes_per_step": d2h // steps}}), flush=True)
+                       "d2h_bytes_per_step": d2h // steps}})
+        print(json.dumps(rows[-1]), flush=True)
+    return rows
 
 
 if __name__ == "__main__":
