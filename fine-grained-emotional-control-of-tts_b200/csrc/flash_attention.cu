@@ -66,6 +66,12 @@ __device__ __forceinline__ float ex2f_(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// one thread of a converged warp (the compiler then knows the region runs single-threaded: no election loop per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -82,13 +88,86 @@ __device__ __forceinline__ void tmem_free512(uint32_t base) {
 __device__ __forceinline__ uint32_t fa_idesc(int n, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(AQ >> 4) << 24);
 }
-// K-major operand tile [rows x 192]: K step k (16 columns) of the atom k / 4
-__device__ __forceinline__ uint64_t fa_desc_k(uint32_t base, int rows, int k) {
-  return smem_desc(base + (k >> 2) * (rows * 128) + (k & 3) * 32, 16, 1024);
+// Shared-memory descriptors: everything but the 14-bit start-address field is constant, and that field only ever moves by
+// (bytes >> 4) -- one descriptor per operand tile, then plain 64-bit adds of compile-time constants (the MMA-issuing
+// thread shares its scheduler with softmax warps: every instruction between two tcgen05.mma counts).
+// K-major operand tile [rows x 192]: K step k (16 columns) of the 64-column atom k / 4
+__device__ __forceinline__ uint64_t fa_base_k(uint32_t base) { return smem_desc(base, 16, 1024); }
+__host__ __device__ constexpr uint64_t fa_off_k(int rows, int k) {
+  return (uint64_t)(((k >> 2) * (rows * 128) + (k & 3) * 32) >> 4);
 }
 // the same tile as an MN-major B operand (N = the 192 columns, K = its rows): K step k = rows [16k, 16k + 16)
-__device__ __forceinline__ uint64_t fa_desc_mn(uint32_t base, int rows, int k) {
-  return smem_desc(base + k * 2048, rows * 128, 1024);
+__device__ __forceinline__ uint64_t fa_base_mn(uint32_t base, int rows) { return smem_desc(base, rows * 128, 1024); }
+__host__ __device__ constexpr uint64_t fa_off_mn(int k) { return (uint64_t)((k * 2048) >> 4); }
+
+// ---- per-job math of the softmax threads, specialised on (block fully inside the valid range, dropout on): the generic
+// form costs two compares and a select more per element, and these threads are instruction-issue bound
+template <int CW, bool FULL, bool DROP>
+__device__ __forceinline__ float fwd_probs(const uint32_t* r, float* v, float sc2, float mx, int c0, int kv, uint32_t tpart,
+                                           uint32_t thr) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < CW; i += 4) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x = ex2f_(fmaf(__uint_as_float(r[i + e]), sc2, -mx));
+      if (!FULL) x = (c0 + i + e < kv) ? x : 0.f;
+      v[i + e] = x;
+    }
+    a0 += v[i]; a1 += v[i + 1]; a2 += v[i + 2]; a3 += v[i + 3];
+  }
+  if (DROP) {
+    const uint32_t ck = (uint32_t)c0 * ADROP_KC;
+#pragma unroll
+    for (int i = 0; i < CW; ++i)           // keep or zero; the 1 / (1 - p) factor is folded into the final normalisation
+      v[i] = adrop_keep(tpart ^ (ck + (uint32_t)i * ADROP_KC), thr) ? v[i] : 0.f;
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+// dS = scale * P * (dPd * keep / (1 - p) - D) = P * fma(dPd, keep ? scale / (1 - p) : 0, -scale * D)
+template <int CW, bool FULL, bool DROP>
+__device__ __forceinline__ void dq_ds(const uint32_t* r, const uint32_t* g, float* v, float sc2, float lse, float ks_s, float ds_s,
+                                      int c0, int kv, uint32_t tpart, uint32_t thr) {
+  const uint32_t ck = (uint32_t)c0 * ADROP_KC;
+#pragma unroll
+  for (int i = 0; i < CW; ++i) {
+    float pr = ex2f_(fmaf(__uint_as_float(r[i]), sc2, -lse));
+    if (!FULL) pr = (c0 + i < kv) ? pr : 0.f;
+    float mul = ks_s;
+    if (DROP) mul = adrop_keep(tpart ^ (ck + (uint32_t)i * ADROP_KC), thr) ? ks_s : 0.f;
+    v[i] = pr * fmaf(__uint_as_float(g[i]), mul, -ds_s);
+  }
+}
+// the dK/dV kernel's 16 queries of one key row: P^T (keep or zero) and dS^T, packed bf16 pairs
+template <bool FULL, bool DROP>
+__device__ __forceinline__ void dkv_pt(const uint32_t* r, const uint32_t* d, const float* stat_l, const float* stat_d, uint32_t* pp,
+                                       uint32_t* ps, float sc2, float ks_s, int t0, int T, uint32_t cpart, uint32_t thr) {
+  const uint32_t tk = (uint32_t)t0 * ADROP_KT;
+#pragma unroll
+  for (int e4 = 0; e4 < 4; ++e4) {
+    const float4 l4 = reinterpret_cast<const float4*>(stat_l)[e4], d4 = reinterpret_cast<const float4*>(stat_d)[e4];
+    const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};     // dd = scale * rowsum(dO * O)
+    float pd[4], ds[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * e4 + e;
+      float pr = ex2f_(fmaf(__uint_as_float(r[j]), sc2, -ls[e]));
+      float ddv = dd[e];
+      if (!FULL) { const bool ok_t = t0 + j < T; pr = ok_t ? pr : 0.f; ddv = ok_t ? ddv : 0.f; }
+      float mul = ks_s;
+      pd[e] = pr;                              // keep or zero; 1 / (1 - p) is applied to dV in the epilogue
+      if (DROP) {
+        const bool keep = adrop_keep(cpart ^ (tk + (uint32_t)j * ADROP_KT), thr);
+        mul = keep ? ks_s : 0.f;
+        pd[e] = keep ? pr : 0.f;
+      }
+      ds[e] = pr * fmaf(__uint_as_float(d[j]), mul, -ddv);
+    }
+    pp[2 * e4] = pack_bf16x2(pd[0], pd[1]);
+    pp[2 * e4 + 1] = pack_bf16x2(pd[2], pd[3]);
+    ps[2 * e4] = pack_bf16x2(ds[0], ds[1]);
+    ps[2 * e4 + 1] = pack_bf16x2(ds[2], ds[3]);
+  }
 }
 
 // ===================================================================================================== forward
@@ -155,12 +234,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // warp-uniform for the compiler: no per-MMA election loop
   pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------ TMA producer
-    if (lane == 0 && nkb > 0) {
+    if (nkb > 0 && elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
       mbar_expect_tx(smem_u32(qfull), T128);
@@ -191,8 +270,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && nkb > 0) {
+    if (nkb > 0 && elect_one()) {
       const uint32_t idescS = fa_idesc(AK, 0), idescO = fa_idesc(HD, 1);
+      const uint64_t dQ0 = fa_base_k(smem_u32(sQ)), dK0 = fa_base_k(smem_u32(sK)), dV0 = fa_base_mn(smem_u32(sV), AK);
+      const uint64_t dP0 = fa_base_k(smem_u32(sP));
       bool ok = mbar_wait(smem_u32(qfull), 0, err);
       int s = 0, sv = 0;
       uint32_t ph = 0, phv = 0;
@@ -207,11 +288,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
           if (!mbar_wait(smem_u32(&sempty[sb]), ((job >> 1) & 1) ^ 1, err)) break;
           PROBE_T(w_se);
           tc_fence_after();
-          const uint32_t sk = smem_u32(sK + s * T64);
+          const uint64_t dk = dK0 + (uint64_t)s * (T64 >> 4);
+          const uint32_t ts = tmem_base + F_TMEM_S + sb * AK;
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(tmem_base + F_TMEM_S + sb * AK, fa_desc_k(smem_u32(sQ), AQ, k), fa_desc_k(sk, AK, k), idescS,
-                      k > 0 ? 1u : 0u);
+            umma_bf16(ts, dQ0 + fa_off_k(AQ, k), dk + fa_off_k(AK, k), idescS, k > 0 ? 1u : 0u);
           umma_commit(smem_u32(&kempty[s]));
           umma_commit(smem_u32(&sfull[sb]));
           if (++s == KST) { s = 0; ph ^= 1; }
@@ -225,15 +306,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
           if (!mbar_wait(smem_u32(&vfull[sv]), phv, err)) break;
           PROBE_T(w_v);
           tc_fence_after();
-          const uint32_t svb = smem_u32(sV + sv * T64);
+          const uint64_t dv = dV0 + (uint64_t)sv * (T64 >> 4);
+          const uint32_t tp = tmem_base + F_TMEM_P + pb * 32;
+          const uint64_t dp = dP0 + (uint64_t)pb * ((AQ * 128) >> 4);
 #pragma unroll
           for (int k = 0; k < AK / 16; ++k) {
             const uint32_t acc = (jv > 0 || k > 0) ? 1u : 0u;
-            if constexpr (PT)
-              umma_bf16_ts(tmem_base + F_TMEM_O, tmem_base + F_TMEM_P + pb * 32 + k * 8, fa_desc_mn(svb, AK, k), idescO, acc);
-            else
-              umma_bf16(tmem_base + F_TMEM_O, smem_desc(smem_u32(sP + pb * (AQ * 128)) + k * 32, 16, 1024),
-                        fa_desc_mn(svb, AK, k), idescO, acc);
+            if constexpr (PT) umma_bf16_ts(tmem_base + F_TMEM_O, tp + k * 8, dv + fa_off_mn(k), idescO, acc);
+            else umma_bf16(tmem_base + F_TMEM_O, dp + (uint64_t)(k * 2), dv + fa_off_mn(k), idescO, acc);
           }
           umma_commit(smem_u32(&pempty[pb]));
           umma_commit(smem_u32(&vempty[sv]));
@@ -305,29 +385,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
       }
       // ---- main pass: un-normalised probabilities, their sum, dropout
       float v[CW];
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      if (full) {
-#pragma unroll
-        for (int i = 0; i < CW; i += 4) {
-          v[i] = ex2f_(fmaf(__uint_as_float(r[i]), sc2, -mx));
-          v[i + 1] = ex2f_(fmaf(__uint_as_float(r[i + 1]), sc2, -mx));
-          v[i + 2] = ex2f_(fmaf(__uint_as_float(r[i + 2]), sc2, -mx));
-          v[i + 3] = ex2f_(fmaf(__uint_as_float(r[i + 3]), sc2, -mx));
-          a0 += v[i]; a1 += v[i + 1]; a2 += v[i + 2]; a3 += v[i + 3];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < CW; ++i) {
-          v[i] = (c0 + i < kv) ? ex2f_(fmaf(__uint_as_float(r[i]), sc2, -mx)) : 0.f;
-          a0 += v[i];
-        }
-      }
-      sum += (a0 + a1) + (a2 + a3);
-      if (dr.thr != 0u) {
-#pragma unroll
-        for (int i = 0; i < CW; ++i)
-          v[i] = adrop_keep(tpart ^ ((uint32_t)(c0 + i) * ADROP_KC), dr.thr) ? v[i] * dr.ks : 0.f;
-      }
+      const bool drop = dr.thr != 0u;
+      if (full) sum += drop ? fwd_probs<CW, true, true>(r, v, sc2, mx, c0, kv, tpart, dr.thr)
+                            : fwd_probs<CW, true, false>(r, v, sc2, mx, c0, kv, tpart, dr.thr);
+      else sum += drop ? fwd_probs<CW, false, true>(r, v, sc2, mx, c0, kv, tpart, dr.thr)
+                       : fwd_probs<CW, false, false>(r, v, sc2, mx, c0, kv, tpart, dr.thr);
       uint32_t pk[CW / 2];
 #pragma unroll
       for (int i = 0; i < CW / 2; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -364,7 +426,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
       float tot = 0.f;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) tot += xch[c * AQ + row].x;
-      const float inv = 1.0f / tot;
+      const float inv = (dr.thr != 0u ? dr.ks : 1.0f) / tot;
       if (p.lse && ch == 0 && row_valid) p.lse[(long long)bh * p.Tl + t] = mx + log2f(tot);
       if (mbar_wait(smem_u32(ofull), 0, err)) {
         tc_fence_after();
@@ -456,11 +518,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // warp-uniform for the compiler: no per-MMA election loop
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0 && nkb > 0) {
+    if (nkb > 0 && elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmdO) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
@@ -490,8 +552,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nkb > 0) {
+    if (nkb > 0 && elect_one()) {
       const uint32_t idescS = fa_idesc(AK, 0), idescO = fa_idesc(HD, 1);
+      const uint64_t dQ0 = fa_base_k(smem_u32(sQ)), dO0 = fa_base_k(smem_u32(sdO)), dK0 = fa_base_k(smem_u32(sK));
+      const uint64_t dV0 = fa_base_k(smem_u32(sV)), dKm0 = fa_base_mn(smem_u32(sK), AK);
       bool ok = mbar_wait(smem_u32(qfull), 0, err);
       int s = 0, sv = 0, sd = 0;                   // K stage of the score MMA, V stage, K stage of the dQ MMA
       uint32_t ph = 0, phv = 0;
@@ -508,13 +572,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
           if (!mbar_wait(smem_u32(&sempty[sb]), ((job >> 1) & 1) ^ 1, err)) break;
           PROBE_T(w_se);
           tc_fence_after();
-          const uint32_t sk = smem_u32(sK + s * T64), svb = smem_u32(sV + sv * T64);
+          const uint64_t dk = dK0 + (uint64_t)s * (T64 >> 4), dv = dV0 + (uint64_t)sv * (T64 >> 4);
+          const uint32_t ts = tmem_base + A_TMEM_S + sb * AK, tdp = tmem_base + A_TMEM_DP + sb * AK;
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(tmem_base + A_TMEM_S + sb * AK, fa_desc_k(smem_u32(sQ), AQ, k), fa_desc_k(sk, AK, k), idescS, k > 0 ? 1u : 0u);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(ts, dQ0 + fa_off_k(AQ, k), dk + fa_off_k(AK, k), idescS, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(tmem_base + A_TMEM_DP + sb * AK, fa_desc_k(smem_u32(sdO), AQ, k), fa_desc_k(svb, AK, k), idescS, k > 0 ? 1u : 0u);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(tdp, dO0 + fa_off_k(AQ, k), dv + fa_off_k(AK, k), idescS, k > 0 ? 1u : 0u);
           umma_commit(smem_u32(&vempty[sv]));
           umma_commit(smem_u32(&sfull[sb]));
           if (++s == KST) { s = 0; ph ^= 1; }
@@ -527,11 +590,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
           if (!mbar_wait(smem_u32(&pfull[pb]), (jv >> 1) & 1, err)) break;
           PROBE_T(w_pf);
           tc_fence_after();
-          const uint32_t sk = smem_u32(sK + sd * T64);
+          const uint64_t dkm = dKm0 + (uint64_t)sd * (T64 >> 4);
+          const uint32_t tds = tmem_base + A_TMEM_DS + pb * 32;
 #pragma unroll
           for (int k = 0; k < AK / 16; ++k)
-            umma_bf16_ts(tmem_base + A_TMEM_DQ, tmem_base + A_TMEM_DS + pb * 32 + k * 8, fa_desc_mn(sk, AK, k), idescO,
-                         (jv > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ts(tmem_base + A_TMEM_DQ, tds + k * 8, dkm + fa_off_mn(k), idescO, (jv > 0 || k > 0) ? 1u : 0u);
           umma_commit(smem_u32(&kempty[sd]));
           umma_commit(smem_u32(&pempty[pb]));
           if (++sd == KST) sd = 0;
@@ -573,8 +636,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
     dsum = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) dsum += xch[c * AQ + row];
-    if (ch == 0 && row_valid) p.dvec[(long long)bh * p.Tl + t] = dsum;
-    const float lse = row_valid ? p.lse[(long long)bh * p.Tl + t] : 0.f;
+    const float ds_s = dsum * scale;               // the dK/dV kernel reads the row term pre-multiplied by the softmax scale
+    if (ch == 0 && row_valid) p.dvec[(long long)bh * p.Tl + t] = ds_s;
+    const float ks_s = (dr.thr != 0u ? dr.ks : 1.0f) * scale;
+    // rows past T: lse = +inf makes every probability 2^-inf = 0 without a per-element test
+    const float lse = row_valid ? p.lse[(long long)bh * p.Tl + t] : INFINITY;
     const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
     long long w_sf = 0, w_ld = 0, w_m = 0, w_pe = 0, w_st = 0, t_all = clock64(), tt = t_all;
     for (int j = 0; j < nkb; ++j) {
@@ -593,12 +659,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
       if (lane == 0) mbar_arrive(smem_u32(&sempty[sb]));
       PROBE_T(w_ld);
       float v[CW];
-#pragma unroll
-      for (int i = 0; i < CW; ++i) {
-        const float pr = (row_valid && c0 + i < kv) ? ex2f_(fmaf(__uint_as_float(r[i]), sc2, -lse)) : 0.f;
-        float gd = __uint_as_float(g[i]);
-        if (dr.thr != 0u) gd = adrop_keep(tpart ^ ((uint32_t)(c0 + i) * ADROP_KC), dr.thr) ? gd * dr.ks : 0.f;
-        v[i] = scale * pr * (gd - dsum);
+      const bool full = (c0 + CW <= kv), drop = dr.thr != 0u;
+      if (full) {
+        if (drop) dq_ds<CW, true, true>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, dr.thr);
+        else dq_ds<CW, true, false>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, dr.thr);
+      } else {
+        if (drop) dq_ds<CW, false, true>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, dr.thr);
+        else dq_ds<CW, false, false>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, dr.thr);
       }
       uint32_t pk[CW / 2];
 #pragma unroll
@@ -700,11 +767,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // warp-uniform for the compiler: no per-MMA election loop
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0 && nq > 0) {
+    if (nq > 0 && elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKV) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmdO) : "memory");
@@ -732,8 +799,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nq > 0) {
+    if (nq > 0 && elect_one()) {
       const uint32_t idescS = fa_idesc(BQ, 0), idescO = fa_idesc(HD, 1);
+      const uint64_t dK0 = fa_base_k(smem_u32(sK)), dV0 = fa_base_k(smem_u32(sV)), dQ0 = fa_base_k(smem_u32(sQ));
+      const uint64_t dO0 = fa_base_k(smem_u32(sdO)), dQm0 = fa_base_mn(smem_u32(sQ), BQ), dOm0 = fa_base_mn(smem_u32(sdO), BQ);
       bool ok = mbar_wait(smem_u32(kvfull), 0, err);
       int s = 0, sd = 0;
       uint32_t ph = 0;
@@ -748,13 +817,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
           if (!mbar_wait(smem_u32(&bfree[g]), ((job >> 1) & 1) ^ 1, err)) break;
           PROBE_T(w_bf);
           tc_fence_after();
-          const uint32_t sq = smem_u32(sQ + s * T32), sdo = smem_u32(sdO + s * T32);
+          const uint64_t dq = dQ0 + (uint64_t)s * (T32 >> 4), ddo = dO0 + (uint64_t)s * (T32 >> 4);
+          const uint32_t tst = tmem_base + B_TMEM_ST + g * BQ, tdp = tmem_base + B_TMEM_DPT + g * BQ;
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(tmem_base + B_TMEM_ST + g * BQ, fa_desc_k(smem_u32(sK), AQ, k), fa_desc_k(sq, BQ, k), idescS, k > 0 ? 1u : 0u);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(tst, dK0 + fa_off_k(AQ, k), dq + fa_off_k(BQ, k), idescS, k > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16(tmem_base + B_TMEM_DPT + g * BQ, fa_desc_k(smem_u32(sV), AQ, k), fa_desc_k(sdo, BQ, k), idescS, k > 0 ? 1u : 0u);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16(tdp, dV0 + fa_off_k(AQ, k), ddo + fa_off_k(BQ, k), idescS, k > 0 ? 1u : 0u);
           umma_commit(smem_u32(&sfull[g]));
           if (++s == QST) { s = 0; ph ^= 1; }
         }
@@ -765,15 +833,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
           if (!mbar_wait(smem_u32(&pfull[g]), (jv >> 1) & 1, err)) break;
           PROBE_T(w_pf);
           tc_fence_after();
-          const uint32_t sq = smem_u32(sQ + sd * T32), sdo = smem_u32(sdO + sd * T32);
+          const uint64_t dqm = dQm0 + (uint64_t)sd * (T32 >> 4), ddom = dOm0 + (uint64_t)sd * (T32 >> 4);
+          const uint32_t tst = tmem_base + B_TMEM_ST + g * BQ, tdp = tmem_base + B_TMEM_DPT + g * BQ;
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k)
-            umma_bf16_ts(tmem_base + B_TMEM_DV, tmem_base + B_TMEM_ST + g * BQ + k * 16, fa_desc_mn(sdo, BQ, k), idescO,
-                         (jv > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ts(tmem_base + B_TMEM_DV, tst + k * 16, ddom + fa_off_mn(k), idescO, (jv > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k)
-            umma_bf16_ts(tmem_base + B_TMEM_DK, tmem_base + B_TMEM_DPT + g * BQ + k * 16, fa_desc_mn(sq, BQ, k), idescO,
-                         (jv > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ts(tmem_base + B_TMEM_DK, tdp + k * 16, dqm + fa_off_mn(k), idescO, (jv > 0 || k > 0) ? 1u : 0u);
           umma_commit(smem_u32(&qempty[sd]));
           umma_commit(smem_u32(&bfree[g]));
           if (++sd == QST) sd = 0;
@@ -794,7 +861,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
     const ADrop dr = adrop_make(p.drop_p, p.seed, p.seed_dev, bh);
     const uint32_t cpart = dr.s ^ ((uint32_t)c * ADROP_KC);
     const float sc2 = p.scale * LOG2E;
-    const float scale = p.scale;
+    const float ks_s = (dr.thr != 0u ? dr.ks : 1.0f) * p.scale;
     const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
     long long w_sf = 0, w_ld = 0, w_m = 0, w_st = 0, t_all = clock64(), tt = t_all;
     for (int i = g; i < nq; i += 2) {
@@ -809,34 +876,22 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
       tmem_ld16_nw(lane_addr + (uint32_t)(B_TMEM_DPT + g * BQ + ch * 16), d);
       tmem_wait_ld();
       PROBE_T(w_ld);
-      const float4* st_l = reinterpret_cast<const float4*>(sStat + s * 64 + ch * 16);
-      const float4* st_d = reinterpret_cast<const float4*>(sStat + s * 64 + 32 + ch * 16);
+      const float* st_l = sStat + s * 64 + ch * 16;
+      const float* st_d = sStat + s * 64 + 32 + ch * 16;
       const int t0 = i * BQ + ch * 16;
+      const bool full = (i * BQ + BQ <= p.T), drop = dr.thr != 0u;        // full: every query of the block exists
       uint32_t pp[8], ps[8];
-#pragma unroll
-      for (int e4 = 0; e4 < 4; ++e4) {
-        const float4 l4 = st_l[e4], d4 = st_d[e4];
-        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
-        float pd[4], ds[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int t = t0 + 4 * e4 + e;
-          const bool valid = key_valid && t < p.T;
-          const float pr = valid ? ex2f_(fmaf(__uint_as_float(r[4 * e4 + e]), sc2, -ls[e])) : 0.f;
-          float gd = __uint_as_float(d[4 * e4 + e]);
-          float pk = pr;
-          if (dr.thr != 0u) {
-            const bool keep = adrop_keep(cpart ^ ((uint32_t)t * ADROP_KT), dr.thr);
-            gd = keep ? gd * dr.ks : 0.f;
-            pk = keep ? pr * dr.ks : 0.f;
-          }
-          pd[e] = pk;
-          ds[e] = valid ? scale * pr * (gd - dd[e]) : 0.f;
+      if (key_valid) {
+        if (full) {
+          if (drop) dkv_pt<true, true>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, dr.thr);
+          else dkv_pt<true, false>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, dr.thr);
+        } else {
+          if (drop) dkv_pt<false, true>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, dr.thr);
+          else dkv_pt<false, false>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, dr.thr);
         }
-        pp[2 * e4] = pack_bf16x2(pd[0], pd[1]);
-        pp[2 * e4 + 1] = pack_bf16x2(pd[2], pd[3]);
-        ps[2 * e4] = pack_bf16x2(ds[0], ds[1]);
-        ps[2 * e4 + 1] = pack_bf16x2(ds[2], ds[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pp[e] = ps[e] = 0u;
       }
       // P^T / dS^T overwrite the first half of this thread's own score columns (already in registers)
       PROBE_T(w_m);
@@ -854,6 +909,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
     const int coff = (w4 & 1) * 96;
     bf16* orow = p.out + (long long)(row_base + c) * (3LL * p.D) + (is_dv ? 2 * p.D : p.D) + h * HD + coff;
     const bool wr = c < p.T;
+    const float osc = (is_dv && dr.thr != 0u) ? dr.ks : 1.0f;      // dV = (keep-or-zero P)^T dO / (1 - p)
     if (nq > 0) {
       if (mbar_wait(smem_u32(ofull), 0, err)) {
         tc_fence_after();
@@ -865,10 +921,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
             uint4* dst = reinterpret_cast<uint4*>(orow + cc * 16);
 #pragma unroll
             for (int i = 0; i < 2; ++i)
-              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1])),
-                                  pack_bf16x2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])),
-                                  pack_bf16x2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])),
-                                  pack_bf16x2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
+              dst[i] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * i]) * osc, __uint_as_float(r[8 * i + 1]) * osc),
+                                  pack_bf16x2(__uint_as_float(r[8 * i + 2]) * osc, __uint_as_float(r[8 * i + 3]) * osc),
+                                  pack_bf16x2(__uint_as_float(r[8 * i + 4]) * osc, __uint_as_float(r[8 * i + 5]) * osc),
+                                  pack_bf16x2(__uint_as_float(r[8 * i + 6]) * osc, __uint_as_float(r[8 * i + 7]) * osc));
           }
         }
       }
