@@ -435,13 +435,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);     // warp-uniform for the compiler
   pdl_wait();      // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   // Persistent tile loop: tile t -> (n-tile fastest so CTAs running together share the A rows in L2).
   // Every role walks the same sequence; smem stage / phase counters run across tiles.
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       // The issue loops of this thread and of the MMA thread are single-thread instruction streams: every k-block must
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       if (prof) { p.dbg[2] = clock64() - t_all; p.dbg[3] = w_empty; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -745,12 +745,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
   tc_fence_before();
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);     // warp-uniform for the compiler
   pdl_wait();      // prologue above overlaps the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs of the pair)
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       int s = 0;
@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tcx_gemm_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only, one thread)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BNS >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
       uint32_t tc = 0, ph = 0;

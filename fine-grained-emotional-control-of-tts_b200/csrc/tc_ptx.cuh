@@ -12,6 +12,16 @@ int fs2_tc_error_ptr(int** out);
 namespace {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// One thread of a CONVERGED warp.  Single-thread issue loops (TMA producer, tcgen05.mma issuer) enter through this
+// instead of `lane == 0`: ptxas then knows the region runs with exactly one active thread and emits the uniform-datapath
+// instructions (UTCHMMA, UTMALDG, UTCBAR) back to back; under a plain lane test it wraps EVERY one of them in an
+// ELECT / BRA.U.ANY loop (~10 instructions and a branch per MMA: 60-100 cycles of issue latency per tcgen05.mma,
+// which bounded every MMA narrower than ~N = 192; measured in profiles/r02_summary.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
