@@ -36,14 +36,11 @@ SIGNATURES = {
     "fs2_avg_over_durations": "ppiiippppp",
     "fs2_embed_add": "ppppipiiippiip",
     "fs2_embed_add_bwd": "ppiiiippp",
-    "fs2_attn_fwd": "ppiiiiiffQppppp",
-    "fs2_attn_fwd_ex": "ppiiiiiffQppppip",
     "fs2_frames_to_rows": "piiiiipip",
     "fs2_gelu": "pqip",
     "fs2_prototype_buckets": "pppppiiiiipp",
     "fs2_collate": "pppppppppiiiipppppp" + "p",
     "fs2_intensity_head": "ppppppiiiipp",
-    "fs2_attn_bwd": "pppppiiiiiffQpppp",
     "fs2_flash_attn_fwd": "ppiiiiffQpppip",
     "fs2_flash_attn_bwd": "pppppiiiiffQpppip",
     "fs2_flash_attn_mask": "iifQppp",

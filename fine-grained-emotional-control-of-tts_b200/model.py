@@ -174,7 +174,7 @@ class FastSpeech2(nn.Module):
         self._graphs = {}
         self._seen = set()
         self._pre = None
-        self.fused_attention = True   # bf16, head_dim 192: fs2_attn_fwd / fs2_attn_bwd instead of GEMM + softmax + GEMM
+        self.fused_attention = True   # bf16, head_dim 192: fs2_flash_attn_fwd / _bwd instead of GEMM + softmax + GEMM
         self.async_mel_lens = False   # opt-in: no host sync; Tm is taken from pitch.shape[1], mel_lens arrives in pinned memory
         # opt-in, inference with predicted durations in precision="bf16": frame counts are trunc(pace * expm1(pred)), which is
         # discontinuous -- a bf16 encoder moves ~1 % of the phonemes across an integer boundary (tests/

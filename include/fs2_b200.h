@@ -141,30 +141,14 @@ int fs2_softmax_fwd(const float* S, const int* lens, int B, int H, int T, int ld
 int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens, int B, int H, int T, int ldk, float scale,
                     float drop_p, unsigned long long seed, const unsigned long long* seed_dev, void* dS, int act_bf16,
                     void* stream);
-/* Fused attention for head_dim 192, bf16 (tcgen05: scores and the output accumulator live in TMEM; the fp32 score
- * matrix never reaches HBM).  Replaces the QK^T GEMM + fs2_softmax_fwd + PV GEMM sequence; same mask quirk, same
- * counter-based dropout stream (keyed by the element index in P), so it can be mixed with the unfused kernels.
- * qkv: (B*(T+8), 3D) bf16 padded rows [Q | K | V]; P, Pd: (B*H, T, ldk) bf16, kept for the backward only -- either
- * may be NULL (inference: nothing but O is written; Pd is only meaningful when drop_p > 0);
- * O: (B*(T+8), D) bf16 padded rows, rows t < T written. */
-int fs2_attn_fwd(const void* qkv, const int* lens, int B, int H, int T, int D, int ldk, float scale, float drop_p,
-                 unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd, void* O, void* stream);
-/* Backward companion: dPd = dO.V^T (TMEM) -> dS = scale*P*(dPd*keep - rowsum(dO*O)) -> dS (B*H, T, ldk) bf16 and
- * dQ = dS.K written into columns [0, D) of dqkv (B*(T+8), 3D).  dK = dS^T Q and dV = Pd^T dO stay batched GEMMs. */
-/* same, with the mask selectable: plain_mask = 1 is an ordinary key-padding mask (keys [0, lens[b]) for every head),
- * as nn.MultiheadAttention(key_padding_mask=...) in the intensity extractor (rank_model/model.py:34, 103) */
-int fs2_attn_fwd_ex(const void* qkv, const int* lens, int B, int H, int T, int D, int ldk, float scale, float drop_p,
-                    unsigned long long seed, const unsigned long long* seed_dev, void* P, void* Pd, void* O,
-                    int plain_mask, void* stream);
-int fs2_attn_bwd(const void* dO, const void* O, const void* qkv, const void* P, const int* lens, int B, int H, int T,
-                 int D, int ldk, float scale, float drop_p, unsigned long long seed,
-                 const unsigned long long* seed_dev, void* dS, void* dqkv, void* stream);
 /* Flash-style attention (flash_attention.cu; reference model.py:344-346, 425-427 through nn.MultiheadAttention's math
  * path): nothing of size T x T reaches HBM.  qkv (B*(T+8), 3D) bf16 padded rows [Q | K | V], head_dim 192.
  * forward: O (B*(T+8), D) bf16, rows t < T written; lse (B*H, fs2_flash_attn_lse_len(T)) fp32 = per query row
  * max + log2(sum 2^(s - max)) of the scaled scores in the log2 domain (NULL: inference, not kept).
  * Dropout on the probabilities: one 32-bit counter hash per (item, head, query, key), regenerated by the backward
- * (fs2_flash_attn_mask returns the keep mask as bytes (B*H, T, T) for tests).  plain_mask as in fs2_attn_fwd_ex.
+ * (fs2_flash_attn_mask returns the keep mask as bytes (B*H, T, T) for tests).  plain_mask = 1: an ordinary
+ * key-padding mask (keys [0, lens[b]) for every head) as nn.MultiheadAttention(key_padding_mask=...) in the intensity
+ * extractor (rank_model/model.py:34, 103); 0: FastSpeech2's attn_mask quirk, keys [0, min(len[b], len[(b*H+h) % B])).
  * backward: dQ, dK, dV into columns [0,D), [D,2D), [2D,3D) of dqkv (B*(T+8), 3D) bf16, rows t < T written;
  * two launches: the dQ kernel (also writes dvec = rowsum(dO*O), same shape as lse, scratch) and the dK/dV kernel. */
 int fs2_flash_attn_lse_len(int T);
@@ -181,8 +165,6 @@ int fs2_flash_attn_tune(int p_in_tmem);
 /* measurement hook: when non-NULL, CTA 0 of every flash-attention launch writes a 64-slot cycle breakdown (library built
  * with -DFS2_TC_PROBE only; tools/flash_bench.py FLASH_DBG=1) */
 int fs2_flash_attn_set_debug(long long* dev_buf);
-/* measurement hook: when non-NULL, CTA 0 of every fused-attention launch writes a 16-slot cycle breakdown (attention.cu) */
-int fs2_attn_set_debug(long long* dev_buf);
 /* *ctr += inc (the device-side dropout step counter; first node of a captured forward graph) */
 int fs2_counter_add(unsigned long long* ctr, unsigned long long inc, void* stream);
 
