@@ -129,39 +129,38 @@ __device__ __forceinline__ float4 drop_scale4(const DropCfg& d, uint64_t group) 
   return o;
 }
 
-// Attention-probability dropout (nn.MultiheadAttention's dropout on the softmax output): one 32-bit hash per element,
-// symmetric in (query t, key c).  The forward and the dQ kernel walk the keys of a query row, the dK/dV kernel walks the
-// queries of a key row; both regenerate the same mask with one thread-constant term hoisted out of the loop.
+// Attention-probability dropout (nn.MultiheadAttention's dropout on the softmax output).  keep(t, c) of query t and key
+// c is decided by the top bits of a 32-bit PRODUCT of one well-mixed odd word per query and one per key:
+//     keep = (row(t) * col(c) mod 2^32) >= p * 2^32 ,   row(t) = mix64(key ^ 2t) | 1 ,  col(c) = mix64(key ^ (2c + 1)) | 1
+// -- one IMAD and one compare per element once the words are at hand.  The forward and the dQ kernel hold row(t) in a
+// register and read col(.) from a table in shared memory, the dK/dV kernel the other way round, so all kernels (and the
+// unfused softmax kernels) regenerate the same mask.  Measured against numpy's generator on 800 x 800 masks: same drop
+// rate, same maximum row-pair / column-pair correlation (0.18-0.20), flat 2-D spectrum (tests/test_flash_attention_gpu.py).
 struct ADrop {
-  uint32_t s;     // key of this (launch, item, head)
-  uint32_t thr;   // drop iff hash < thr = p * 2^32
+  uint64_t key;   // of this (launch, item, head)
+  uint32_t thr;   // drop iff product < thr = p * 2^32
   float ks;       // 1 / (1 - p)
 };
-constexpr uint32_t ADROP_KT = 0x9E3779B1u, ADROP_KC = 0x85EBCA6Bu;
 __device__ __forceinline__ ADrop adrop_make(float p, unsigned long long seed, const unsigned long long* seed_dev, int bh) {
   ADrop d;
   if (seed_dev) seed ^= mix64(*seed_dev);
-  d.s = (uint32_t)(mix64(seed ^ (0xA24BAED4963EE407ull * (uint64_t)(bh + 1))) >> 32);
+  d.key = mix64(seed ^ (0xA24BAED4963EE407ull * (uint64_t)(bh + 1)));
   d.thr = p > 0.f ? (uint32_t)fminf(p * 4294967296.0f, 4294967040.0f) : 0u;
   d.ks = 1.0f / (1.0f - p);
   return d;
 }
-// x = d.s ^ (t * ADROP_KT) ^ (c * ADROP_KC)
-__device__ __forceinline__ bool adrop_keep(uint32_t x, uint32_t thr) {
-  uint32_t h = x * 0xCC9E2D51u;
-  h ^= h >> 15;
-  h *= 0x1B873593u;
-  return h >= thr;
-}
+__device__ __forceinline__ uint32_t adrop_row(const ADrop& d, int t) { return (uint32_t)mix64(d.key ^ (uint64_t)(2 * t)) | 1u; }
+__device__ __forceinline__ uint32_t adrop_col(const ADrop& d, int c) { return (uint32_t)mix64(d.key ^ (uint64_t)(2 * c + 1)) | 1u; }
+__device__ __forceinline__ bool adrop_keep(uint32_t row, uint32_t col, uint32_t thr) { return row * col >= thr; }
 
-// keep-scales (0 or 1/(1-p)) of keys c .. c+3 of one query row; tpart = d.s ^ (t * ADROP_KT)
-__device__ __forceinline__ float4 adrop_scale4(const ADrop& d, uint32_t tpart, int c) {
+// keep-scales (0 or 1/(1-p)) of keys c .. c+3 of one query row (slow form: the column words are computed on the spot)
+__device__ __forceinline__ float4 adrop_scale4(const ADrop& d, uint32_t row, int c) {
   if (d.thr == 0u) return make_float4(1.f, 1.f, 1.f, 1.f);
   float4 o;
-  o.x = adrop_keep(tpart ^ ((uint32_t)c * ADROP_KC), d.thr) ? d.ks : 0.f;
-  o.y = adrop_keep(tpart ^ ((uint32_t)(c + 1) * ADROP_KC), d.thr) ? d.ks : 0.f;
-  o.z = adrop_keep(tpart ^ ((uint32_t)(c + 2) * ADROP_KC), d.thr) ? d.ks : 0.f;
-  o.w = adrop_keep(tpart ^ ((uint32_t)(c + 3) * ADROP_KC), d.thr) ? d.ks : 0.f;
+  o.x = adrop_keep(row, adrop_col(d, c), d.thr) ? d.ks : 0.f;
+  o.y = adrop_keep(row, adrop_col(d, c + 1), d.thr) ? d.ks : 0.f;
+  o.z = adrop_keep(row, adrop_col(d, c + 2), d.thr) ? d.ks : 0.f;
+  o.w = adrop_keep(row, adrop_col(d, c + 3), d.thr) ? d.ks : 0.f;
   return o;
 }
 

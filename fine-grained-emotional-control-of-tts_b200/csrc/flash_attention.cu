@@ -30,6 +30,8 @@ constexpr int T128 = 3 * AQ * 128;     // 49152: [128 rows x 192] bf16 as three 
 constexpr int T64 = 3 * AK * 128;      // 24576
 constexpr int T32 = 3 * BQ * 128;      // 12288
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr int FA_MAXT = 1536;          // longest sequence the dropout word table in shared memory covers (training only)
+constexpr int FA_TAB = FA_MAXT * 4;
 
 // cycle probe of tools/flash_bench.py (FLASH_DBG=1): compiled in with `make EXTRA=-DFS2_TC_PROBE` only
 long long* g_fa_dbg = nullptr;
@@ -97,8 +99,8 @@ __host__ __device__ constexpr uint64_t fa_off_mn(int k) { return (uint64_t)((k *
 // ---- per-job math of the softmax threads, specialised on (block fully inside the valid range, dropout on): the generic
 // form costs two compares and a select more per element, and these threads are instruction-issue bound
 template <int CW, bool FULL, bool DROP>
-__device__ __forceinline__ float fwd_probs(const uint32_t* r, float* v, float sc2, float mx, int c0, int kv, uint32_t tpart,
-                                           uint32_t thr) {
+__device__ __forceinline__ float fwd_probs(const uint32_t* r, float* v, float sc2, float mx, int c0, int kv, uint32_t rw,
+                                           const uint32_t* colw, uint32_t thr) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
   for (int i = 0; i < CW; i += 4) {
@@ -111,35 +113,48 @@ __device__ __forceinline__ float fwd_probs(const uint32_t* r, float* v, float sc
     a0 += v[i]; a1 += v[i + 1]; a2 += v[i + 2]; a3 += v[i + 3];
   }
   if (DROP) {
-    const uint32_t ck = (uint32_t)c0 * ADROP_KC;
 #pragma unroll
-    for (int i = 0; i < CW; ++i)           // keep or zero; the 1 / (1 - p) factor is folded into the final normalisation
-      v[i] = adrop_keep(tpart ^ (ck + (uint32_t)i * ADROP_KC), thr) ? v[i] : 0.f;
+    for (int i = 0; i < CW; i += 4) {      // keep or zero; the 1 / (1 - p) factor is folded into the final normalisation
+      const uint4 cw = *reinterpret_cast<const uint4*>(colw + c0 + i);
+      v[i] = adrop_keep(rw, cw.x, thr) ? v[i] : 0.f;
+      v[i + 1] = adrop_keep(rw, cw.y, thr) ? v[i + 1] : 0.f;
+      v[i + 2] = adrop_keep(rw, cw.z, thr) ? v[i + 2] : 0.f;
+      v[i + 3] = adrop_keep(rw, cw.w, thr) ? v[i + 3] : 0.f;
+    }
   }
   return (a0 + a1) + (a2 + a3);
 }
 // dS = scale * P * (dPd * keep / (1 - p) - D) = P * fma(dPd, keep ? scale / (1 - p) : 0, -scale * D)
 template <int CW, bool FULL, bool DROP>
 __device__ __forceinline__ void dq_ds(const uint32_t* r, const uint32_t* g, float* v, float sc2, float lse, float ks_s, float ds_s,
-                                      int c0, int kv, uint32_t tpart, uint32_t thr) {
-  const uint32_t ck = (uint32_t)c0 * ADROP_KC;
+                                      int c0, int kv, uint32_t rw, const uint32_t* colw, uint32_t thr) {
 #pragma unroll
-  for (int i = 0; i < CW; ++i) {
-    float pr = ex2f_(fmaf(__uint_as_float(r[i]), sc2, -lse));
-    if (!FULL) pr = (c0 + i < kv) ? pr : 0.f;
-    float mul = ks_s;
-    if (DROP) mul = adrop_keep(tpart ^ (ck + (uint32_t)i * ADROP_KC), thr) ? ks_s : 0.f;
-    v[i] = pr * fmaf(__uint_as_float(g[i]), mul, -ds_s);
+  for (int i4 = 0; i4 < CW; i4 += 4) {
+    uint4 cw = make_uint4(0, 0, 0, 0);
+    if (DROP) cw = *reinterpret_cast<const uint4*>(colw + c0 + i4);
+    const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = i4 + e;
+      float pr = ex2f_(fmaf(__uint_as_float(r[i]), sc2, -lse));
+      if (!FULL) pr = (c0 + i < kv) ? pr : 0.f;
+      float mul = ks_s;
+      if (DROP) mul = adrop_keep(rw, cws[e], thr) ? ks_s : 0.f;
+      v[i] = pr * fmaf(__uint_as_float(g[i]), mul, -ds_s);
+    }
   }
 }
 // the dK/dV kernel's 16 queries of one key row: P^T (keep or zero) and dS^T, packed bf16 pairs
 template <bool FULL, bool DROP>
 __device__ __forceinline__ void dkv_pt(const uint32_t* r, const uint32_t* d, const float* stat_l, const float* stat_d, uint32_t* pp,
-                                       uint32_t* ps, float sc2, float ks_s, int t0, int T, uint32_t cpart, uint32_t thr) {
-  const uint32_t tk = (uint32_t)t0 * ADROP_KT;
+                                       uint32_t* ps, float sc2, float ks_s, int t0, int T, uint32_t cw, const uint32_t* roww,
+                                       uint32_t thr) {
 #pragma unroll
   for (int e4 = 0; e4 < 4; ++e4) {
     const float4 l4 = reinterpret_cast<const float4*>(stat_l)[e4], d4 = reinterpret_cast<const float4*>(stat_d)[e4];
+    uint4 rw4 = make_uint4(0, 0, 0, 0);
+    if (DROP) rw4 = *reinterpret_cast<const uint4*>(roww + t0 + 4 * e4);
+    const uint32_t rws[4] = {rw4.x, rw4.y, rw4.z, rw4.w};
     const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};     // dd = scale * rowsum(dO * O)
     float pd[4], ds[4];
 #pragma unroll
@@ -151,7 +166,7 @@ __device__ __forceinline__ void dkv_pt(const uint32_t* r, const uint32_t* d, con
       float mul = ks_s;
       pd[e] = pr;                              // keep or zero; 1 / (1 - p) is applied to dV in the epilogue
       if (DROP) {
-        const bool keep = adrop_keep(cpart ^ (tk + (uint32_t)j * ADROP_KT), thr);
+        const bool keep = adrop_keep(rws[e], cw, thr);
         mul = keep ? ks_s : 0.f;
         pd[e] = keep ? pr : 0.f;
       }
@@ -169,7 +184,7 @@ constexpr int FWD_NCH = 2;                       // threads per query row (colum
 constexpr int FWD_THREADS = 32 * (2 + 4 * FWD_NCH);
 template <bool PT> struct FwdCfg {
   static constexpr int KST = PT ? 4 : 3, VST = PT ? 3 : 2;
-  static constexpr int SMEM = T128 + (KST + VST) * T64 + (PT ? 0 : 2 * AQ * 128) + 1024 + 512 + FWD_NCH * AQ * 8;
+  static constexpr int SMEM = T128 + (KST + VST) * T64 + (PT ? 0 : 2 * AQ * 128) + FA_TAB + 1024 + 512 + FWD_NCH * AQ * 8;
 };
 constexpr int F_TMEM_S = 0, F_TMEM_O = 128, F_TMEM_P = 320;      // S: 2 x 64 columns, O: 192, P: 2 x 32 (bf16 pairs)
 
@@ -184,7 +199,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
   uint8_t* sK = sQ + T128;
   uint8_t* sV = sK + KST * T64;
   uint8_t* sP = sV + VST * T64;                              // !PT only: two [128 x 64] bf16 tiles
-  uint64_t* bars = (uint64_t*)(sP + (PT ? 0 : 2 * AQ * 128));
+  uint32_t* sTab = (uint32_t*)(sP + (PT ? 0 : 2 * AQ * 128));     // dropout: one word per key of this (item, head)
+  uint64_t* bars = (uint64_t*)(sTab + FA_MAXT);
   uint64_t* qfull = bars;
   uint64_t* kfull = qfull + 1;
   uint64_t* kempty = kfull + KST;
@@ -326,7 +342,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
     const bool row_valid = t < p.T;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const ADrop dr = adrop_make(p.drop_p, p.seed, p.seed_dev, bh);
-    const uint32_t tpart = dr.s ^ ((uint32_t)t * ADROP_KT);
+    const uint32_t tpart = adrop_row(dr, t);
+    if (dr.thr != 0u) {
+      for (int c = (warp - 2) * 32 + lane; c < nkb * AK; c += 128 * NCH) sTab[c] = adrop_col(dr, c);
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * NCH) : "memory");
+    }
     const float sc2 = p.scale * LOG2E;             // scores in the log2 domain: exp(x) = 2^(x * log2 e)
     float mx = -INFINITY, sum = 0.f;
     const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
@@ -380,10 +400,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
       // ---- main pass: un-normalised probabilities, their sum, dropout
       float v[CW];
       const bool drop = dr.thr != 0u;
-      if (full) sum += drop ? fwd_probs<CW, true, true>(r, v, sc2, mx, c0, kv, tpart, dr.thr)
-                            : fwd_probs<CW, true, false>(r, v, sc2, mx, c0, kv, tpart, dr.thr);
-      else sum += drop ? fwd_probs<CW, false, true>(r, v, sc2, mx, c0, kv, tpart, dr.thr)
-                       : fwd_probs<CW, false, false>(r, v, sc2, mx, c0, kv, tpart, dr.thr);
+      if (full) sum += drop ? fwd_probs<CW, true, true>(r, v, sc2, mx, c0, kv, tpart, sTab, dr.thr)
+                            : fwd_probs<CW, true, false>(r, v, sc2, mx, c0, kv, tpart, sTab, dr.thr);
+      else sum += drop ? fwd_probs<CW, false, true>(r, v, sc2, mx, c0, kv, tpart, sTab, dr.thr)
+                       : fwd_probs<CW, false, false>(r, v, sc2, mx, c0, kv, tpart, sTab, dr.thr);
       uint32_t pk[CW / 2];
 #pragma unroll
       for (int i = 0; i < CW / 2; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -455,7 +475,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
 constexpr int BWD_NCH = 4;
 constexpr int BWD_THREADS = 32 * (2 + 4 * BWD_NCH);             // 576
 constexpr int DQ_KST = 3, DQ_VST = 2;
-constexpr int DQ_SMEM = 2 * T128 + (DQ_KST + DQ_VST) * T64 + 1024 + 512 + BWD_NCH * AQ * 4;
+constexpr int DQ_SMEM = 2 * T128 + (DQ_KST + DQ_VST) * T64 + FA_TAB + 1024 + 512 + BWD_NCH * AQ * 4;
 constexpr int A_TMEM_S = 0, A_TMEM_DP = 128, A_TMEM_DQ = 256, A_TMEM_DS = 448;   // 2 x 64, 2 x 64, 192, 2 x 32 columns
 
 __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -469,7 +489,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
   uint8_t* sdO = sQ + T128;
   uint8_t* sK = sdO + T128;
   uint8_t* sV = sK + KST * T64;
-  uint64_t* bars = (uint64_t*)(sV + VST * T64);
+  uint32_t* sTab = (uint32_t*)(sV + VST * T64);      // dropout: one word per key of this (item, head)
+  uint64_t* bars = (uint64_t*)(sTab + FA_MAXT);
   uint64_t* qfull = bars;
   uint64_t* kfull = qfull + 1;
   uint64_t* kempty = kfull + KST;
@@ -605,7 +626,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
     const bool row_valid = t < p.T;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const ADrop dr = adrop_make(p.drop_p, p.seed, p.seed_dev, bh);
-    const uint32_t tpart = dr.s ^ ((uint32_t)t * ADROP_KT);
+    const uint32_t tpart = adrop_row(dr, t);
+    if (dr.thr != 0u)          // visible to every softmax thread after the bar.sync of the row-term exchange below
+      for (int c = (warp - 2) * 32 + lane; c < nkb * AK; c += 128 * NCH) sTab[c] = adrop_col(dr, c);
     const float sc2 = p.scale * LOG2E;
     const float scale = p.scale;
     // D_i = sum_c dO[t,c] * O[t,c]  (== sum_k Pd * dPd, the softmax-backward row term); each thread takes 48 of the 192 dims
@@ -655,11 +678,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
       float v[CW];
       const bool full = (c0 + CW <= kv), drop = dr.thr != 0u;
       if (full) {
-        if (drop) dq_ds<CW, true, true>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, dr.thr);
-        else dq_ds<CW, true, false>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, dr.thr);
+        if (drop) dq_ds<CW, true, true>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, sTab, dr.thr);
+        else dq_ds<CW, true, false>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, sTab, dr.thr);
       } else {
-        if (drop) dq_ds<CW, false, true>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, dr.thr);
-        else dq_ds<CW, false, false>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, dr.thr);
+        if (drop) dq_ds<CW, false, true>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, sTab, dr.thr);
+        else dq_ds<CW, false, false>(r, g, v, sc2, lse, ks_s, ds_s, c0, kv, tpart, sTab, dr.thr);
       }
       uint32_t pk[CW / 2];
 #pragma unroll
@@ -709,7 +732,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
 // ===================================================================================================== backward: dK, dV
 constexpr int KV_QST = 4;
 constexpr int KV_STAGE = 2 * T32 + 256;                          // Q block, dO block, 32 x (lse, D)
-constexpr int KV_SMEM = 2 * T128 + KV_QST * 2 * T32 + KV_QST * 256 + 1024 + 512;
+constexpr int KV_SMEM = 2 * T128 + KV_QST * 2 * T32 + KV_QST * 256 + FA_TAB + 1024 + 512;
 constexpr int B_TMEM_ST = 0, B_TMEM_DPT = 64, B_TMEM_DV = 128, B_TMEM_DK = 320;   // 2 x 32, 2 x 32, 192, 192 columns
 
 __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,
@@ -724,7 +747,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
   uint8_t* sQ = sV + T128;                         // QST x [32 x 192]
   uint8_t* sdO = sQ + QST * T32;
   float* sStat = (float*)(sdO + QST * T32);        // QST x (32 lse, 32 D)
-  uint64_t* bars = (uint64_t*)(sStat + QST * 64);
+  uint32_t* sTab = (uint32_t*)(sStat + QST * 64);  // dropout: one word per query of this (item, head)
+  uint64_t* bars = (uint64_t*)(sTab + FA_MAXT);
   uint64_t* kvfull = bars;
   uint64_t* qfull = kvfull + 1;                    // [QST]
   uint64_t* qempty = qfull + QST;
@@ -853,7 +877,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
     const bool key_valid = c < kv;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const ADrop dr = adrop_make(p.drop_p, p.seed, p.seed_dev, bh);
-    const uint32_t cpart = dr.s ^ ((uint32_t)c * ADROP_KC);
+    const uint32_t cpart = adrop_col(dr, c);
+    if (dr.thr != 0u && nq > 0) {
+      for (int t = (warp - 2) * 32 + lane; t < nq * BQ; t += 512) sTab[t] = adrop_row(dr, t);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
     const float sc2 = p.scale * LOG2E;
     const float ks_s = (dr.thr != 0u ? dr.ks : 1.0f) * p.scale;
     const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
@@ -877,11 +905,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
       uint32_t pp[8], ps[8];
       if (key_valid) {
         if (full) {
-          if (drop) dkv_pt<true, true>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, dr.thr);
-          else dkv_pt<true, false>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, dr.thr);
+          if (drop) dkv_pt<true, true>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, sTab, dr.thr);
+          else dkv_pt<true, false>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, sTab, dr.thr);
         } else {
-          if (drop) dkv_pt<false, true>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, dr.thr);
-          else dkv_pt<false, false>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, dr.thr);
+          if (drop) dkv_pt<false, true>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, sTab, dr.thr);
+          else dkv_pt<false, false>(r, d, st_l, st_d, pp, ps, sc2, ks_s, t0, p.T, cpart, sTab, dr.thr);
         }
       } else {
 #pragma unroll
@@ -940,7 +968,7 @@ __global__ void fa_mask_kernel(int BH, int T, float drop_p, unsigned long long s
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % T), t = (int)((i / T) % T), bh = (int)(i / ((long long)T * T));
     const ADrop dr = adrop_make(drop_p, seed, seed_dev, bh);
-    keep[i] = (dr.thr == 0u || adrop_keep(dr.s ^ ((uint32_t)t * ADROP_KT) ^ ((uint32_t)c * ADROP_KC), dr.thr)) ? 1 : 0;
+    keep[i] = (dr.thr == 0u || adrop_keep(adrop_row(dr, t), adrop_col(dr, c), dr.thr)) ? 1 : 0;
   }
 }
 
@@ -992,6 +1020,10 @@ extern "C" int fs2_flash_attn_fwd(const void* qkv, const int* lens, int B, int H
   if (rc) return rc;
   rc = fs2_tc_make_map_2d(qkv, 3LL * D, (long long)B * p.TP, 3LL * D, 64, AK, &tkv);
   if (rc) return rc;
+  if (drop_p > 0.f && T > FA_MAXT - AQ) {
+    fs2_set_error("fs2_flash_attn: attention dropout is supported up to 1408 rows per item");
+    return FS2_ERR_UNSUPPORTED;
+  }
   p.scale = scale; p.drop_p = drop_p; p.seed = seed; p.seed_dev = seed_dev;
   p.lse = lse;
   p.out = (bf16*)O;
@@ -1024,6 +1056,10 @@ extern "C" int fs2_flash_attn_bwd(const void* dO, const void* O, const void* qkv
   if ((rc = fs2_tc_make_map_2d(qkv, 3LL * D, rows, 3LL * D, 64, BQ, &tq32))) return rc;
   if ((rc = fs2_tc_make_map_2d(dO, D, rows, D, 64, BQ, &tdo32))) return rc;
   tkv128 = tq128;
+  if (drop_p > 0.f && T > FA_MAXT - AQ) {
+    fs2_set_error("fs2_flash_attn: attention dropout is supported up to 1408 rows per item");
+    return FS2_ERR_UNSUPPORTED;
+  }
   p.scale = scale; p.drop_p = drop_p; p.seed = seed; p.seed_dev = seed_dev;
   p.lse = const_cast<float*>(lse);
   p.dvec = dvec;

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(THREADS) softmax_fwd_kernel(const float* S, co
     const int kv = quirk_kv(lens, B, H, bh);
     // the same per-element dropout hash as the flash-style kernels (flash_attention.cu), so both paths draw one mask
     const ADrop dr = adrop_make(dc.p, dc.seed, seed_dev, bh);
-    const uint32_t tpart = dr.s ^ ((uint32_t)(r - (long long)bh * T) * ADROP_KT);
+    const uint32_t tpart = adrop_row(dr, (int)(r - (long long)bh * T));
     const float* s = S + r * ldk;
     float mx = -INFINITY;
     for (int c = lane * 4; c < kv; c += 128) {
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(THREADS) softmax_bwd_kernel(const TA* P, const
     const int bh = (int)(r / T);
     const int kv = quirk_kv(lens, B, H, bh);
     const ADrop dr = adrop_make(dc.p, dc.seed, seed_dev, bh);
-    const uint32_t tpart = dr.s ^ ((uint32_t)(r - (long long)bh * T) * ADROP_KT);
+    const uint32_t tpart = adrop_row(dr, (int)(r - (long long)bh * T));
     const long long ro = r * ldk;
     float dot = 0.f;
     for (int c = lane * 4; c < kv; c += 128) {
