@@ -500,8 +500,8 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "FastSpeech2 full training step (BASELINE configs[2]: fwd + 5xMSE + SSIM + bwd + AdamW"
-                               + (", + NCCL all-reduce of the flat fp32 gradient in 2 pieces, the decoder/PostNet piece overlapped with "
-                                  "the rest of the backward" if world > 1 else "") + ")",
+                               + (", + NCCL all-reduce of the flat fp32 gradient in 3 pieces, each followed by its AdamW update on a side "
+                                  "stream; all but the last piece overlap the rest of the backward" if world > 1 else "") + ")",
                    "batch_per_gpu": BATCH, "global_batch": BATCH * world, "max_phonemes": 128, "max_frames": 800,
                    "n_mels": 80, "params": 85295299, "distinct_batches": N_DISTINCT,
                    "padded_shapes_Tp_Tm": shapes, "parallelism": f"dp{world}",

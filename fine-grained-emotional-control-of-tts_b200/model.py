@@ -168,6 +168,7 @@ class FastSpeech2(nn.Module):
         self._anchor = torch.zeros(1, requires_grad=True)   # lets autograd reach our backward; never a parameter
         self._arenas = None
         self._seed_base = 0x1234
+        self.enc_grad_split = 2      # encoder layers >= 2 finish in part B of the backward, layers 0-1 + embedding in part C
         self._generation = 0
         self._ctr = None              # device-side dropout step counter (uint64 in an int64 tensor)
         self.use_cuda_graphs = False  # opt-in: replay the captured step per (B, Tp, Tm) -- see _graph_forward
@@ -501,9 +502,10 @@ class FastSpeech2(nn.Module):
         fin.p = p
         return out_f32, out_act, saves, fin
 
-    def _stack_bwd(self, cfg, saves, fin, dout, dout2, B, T, lens, final_lens):
+    def _stack_bwd(self, cfg, saves, fin, dout, dout2, B, T, lens, final_lens, upto=0, st=None):
         """dout (+dout2): fp32 padded-row gradient wrt the stack output.  Returns (dx_a, dx_b): the gradient wrt
-        the stack input is their sum."""
+        the stack input is their sum.  `upto` > 0 stops after layer `upto` and returns the resumable state instead
+        (pass it back as `st` to continue): the data-parallel step reduces the finished layers' gradients meanwhile."""
         D, F, H, nl = self.D, cfg["F"], cfg["H"], cfg["nl"]
         name = cfg["name"]
         hd = D // H
@@ -515,23 +517,29 @@ class FastSpeech2(nn.Module):
         ld = 3 * D
         h1, h2 = (self.k0 - 1) // 2, (self.k1 - 1) // 2
         scale = 1.0 / math.sqrt(hd)
-        # scratch shared by all layers
         fused = self._fused_attn(H)
-        dPd = None if fused else self._f32(B * H, T, ldk)
-        dS = self._f32(B * H, _rup(T, 128)) if fused else self._act(B * H, T, ldk)    # fused: rowsum(dO * O) scratch
-        dqkv = self._act(rows, ld)
-        dF_act, dH_act = self._act(rows, D), self._act(rows, F)
-        dHc = self._f32(rows, F) if h2 > 0 else None
-        dz2, dz1, dXa = self._f32(rows, D), self._f32(rows, D), self._f32(rows, D)
-        ksplit = self._dgrad_split(rows, D) if h1 > 0 else 1
-        dX1c = self._f32(ksplit, rows, D)
-        dProj_act, dO_act = self._act(rows, D), self._act(rows, D)
-        dy_a, dy_b = self._f32(rows, D), None
         fuse_bias = D <= 384           # bias gradients of the out-proj / FFN-2 convs come out of the LN backward kernels
-        self._ln_bwd(B, T, D, fin.x_f32, self._P(f"{name}.norm.norm.weight"), self._P(f"{name}.norm.norm.bias"), 1e-6,
-                     fin.mean, fin.rstd, dy=dout, dy2=dout2, lens=final_lens, dx_f32=dy_a,
-                     dgamma=self._G(f"{name}.norm.norm.weight"), dbeta=self._G(f"{name}.norm.norm.bias"))
-        for l in reversed(range(nl)):
+        if st is None:
+            # scratch shared by all layers
+            st = _Saved()
+            st.dPd = None if fused else self._f32(B * H, T, ldk)
+            st.dS = self._f32(B * H, _rup(T, 128)) if fused else self._act(B * H, T, ldk)    # fused: rowsum(dO * O) scratch
+            st.dqkv = self._act(rows, ld)
+            st.dF_act, st.dH_act = self._act(rows, D), self._act(rows, F)
+            st.dHc = self._f32(rows, F) if h2 > 0 else None
+            st.dz2, st.dz1, st.dXa = self._f32(rows, D), self._f32(rows, D), self._f32(rows, D)
+            st.ksplit = self._dgrad_split(rows, D) if h1 > 0 else 1
+            st.dX1c = self._f32(st.ksplit, rows, D)
+            st.dProj_act, st.dO_act = self._act(rows, D), self._act(rows, D)
+            st.dy_a, st.dy_b = self._f32(rows, D), None
+            st.next = nl - 1
+            self._ln_bwd(B, T, D, fin.x_f32, self._P(f"{name}.norm.norm.weight"), self._P(f"{name}.norm.norm.bias"), 1e-6,
+                         fin.mean, fin.rstd, dy=dout, dy2=dout2, lens=final_lens, dx_f32=st.dy_a,
+                         dgamma=self._G(f"{name}.norm.norm.weight"), dbeta=self._G(f"{name}.norm.norm.bias"))
+        dPd, dS, dqkv, dF_act, dH_act, dHc = st.dPd, st.dS, st.dqkv, st.dF_act, st.dH_act, st.dHc
+        dz2, dz1, dXa, ksplit, dX1c, dProj_act, dO_act = st.dz2, st.dz1, st.dXa, st.ksplit, st.dX1c, st.dProj_act, st.dO_act
+        dy_a, dy_b = st.dy_a, st.dy_b
+        for l in reversed(range(upto, st.next + 1)):
             pre = f"{name}.layers.{l}"
             sv = saves[l]
             # ---- LN2 + FFN
@@ -592,6 +600,9 @@ class FastSpeech2(nn.Module):
             if dy_b is None:
                 dy_b = self._f32(rows, D)
             dy_b, dXa = dXa, dy_b
+        if upto > 0:
+            st.dz1, st.dXa, st.dy_a, st.dy_b, st.next = dz1, dXa, dy_a, dy_b, upto - 1
+            return st
         return dy_a, dy_b
 
     # ---------------------------------------------------------------- variance predictor
@@ -904,7 +915,10 @@ class FastSpeech2(nn.Module):
         mid = self._backward_a(ctx, dmel, dpost, capturing)
         if not capturing:
             self._grad_ready()
-        self._backward_b(ctx, mid, dpd, dpp, dpe)
+        mid2 = self._backward_b(ctx, mid, dpd, dpp, dpe)
+        if not capturing:
+            self._grad_ready_mid()
+        self._backward_c(ctx, mid2)
 
     @property
     def grad_split_lo(self):
@@ -921,6 +935,10 @@ class FastSpeech2(nn.Module):
     def _grad_ready(self):
         if self.grad_ready_hook is not None:
             self.grad_ready_hook(self.grad_split_lo, self.store.flat.numel())
+
+    def _grad_ready_mid(self):
+        if self.grad_ready_hook is not None and self.grad_split_mid < self.grad_split_lo:
+            self.grad_ready_hook(self.grad_split_mid, self.grad_split_lo)
 
     def _backward_a(self, ctx, dmel, dpost, capturing=False):
         if not capturing and ctx.generation != self._generation:
@@ -1026,13 +1044,44 @@ class FastSpeech2(nn.Module):
         self._conv_wgrad(dC_act, ctx.enc_act, B, Tp, "concat_proj.tok", "concat_proj.w.weight", None)
         denc = self._f32(rowsP, D)
         self._conv_dgrad(dC_act, B, Tp, "concat_proj.tok", denc)
-        # ---- encoder + embedding
-        ea, eb = self._stack_bwd(self.enc, ctx.enc_saves, ctx.enc_fin, denc, None, B, Tp, ctx.src_lens, ctx.src_lens)
+        # ---- encoder, upper layers: their gradients (and encoder.norm's) are final when this part ends
+        k = self.enc_grad_split_layer
+        est = self._stack_bwd(self.enc, ctx.enc_saves, ctx.enc_fin, denc, None, B, Tp, ctx.src_lens, ctx.src_lens, upto=k) \
+            if k > 0 else None
+        self._side_join()
+        return est, denc
+
+    def _backward_c(self, ctx, mid):
+        """Lower encoder layers + token embedding (part C of the backward; see enc_grad_split)."""
+        est, denc = mid
+        B, Tp, D = ctx.B, ctx.Tp, self.D
+        rowsP = B * (Tp + 2 * PAD)
+        self._side_begin(denc.device)
+        ea, eb = self._stack_bwd(self.enc, ctx.enc_saves, ctx.enc_fin, denc, None, B, Tp, ctx.src_lens, ctx.src_lens, st=est)
         if eb is not None:
             L.call("fs2_add_", ea, eb, rowsP * D)
         L.call("fs2_embedding_bwd", ea, ctx.tokens, B, Tp, D, self.padding_idx,
                self._G("encPreNet.token_embedding.Embedding.weight"))
         self._side_join()
+
+    @property
+    def enc_grad_split_layer(self):
+        """Encoder layers >= this index are back-propagated in part B of the backward, the rest in part C."""
+        return min(max(int(self.enc_grad_split), 0), self.enc["nl"])
+
+    @property
+    def grad_split_mid(self):
+        """First element of the flat buffers that belongs to encoder.layers.{enc_grad_split_layer} (everything from there up
+        to grad_split_lo -- the upper encoder layers and encoder.norm -- is final after part B)."""
+        k = self.enc_grad_split_layer
+        if k <= 0 or k >= self.enc["nl"]:
+            return 0 if k <= 0 else self.grad_split_lo
+        pre = tuple(f"encoder.layers.{l}." for l in range(k, self.enc["nl"])) + ("encoder.norm.",)
+        lo = min(o for key, (o, _) in self.store.offsets.items() if key.startswith(pre))
+        hi = self.grad_split_lo
+        if any(lo <= o < hi and not key.startswith(pre) for key, (o, _) in self.store.offsets.items()):
+            return hi                                # unexpected layout: nothing more is declared ready early
+        return lo
 
 
     # ---------------------------------------------------------------------- CUDA graphs
@@ -1126,8 +1175,11 @@ class FastSpeech2(nn.Module):
             mid = self._backward_a(ctx, entry.grad_in[0], entry.grad_in[1], capturing=True)
         gb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gb):
-            self._backward_b(ctx, mid, *entry.grad_in[2:])
-        entry.bwd_a, entry.bwd_b = ga, gb
+            mid2 = self._backward_b(ctx, mid, *entry.grad_in[2:])
+        gc = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gc):
+            self._backward_c(ctx, mid2)
+        entry.bwd_a, entry.bwd_b, entry.bwd_c = ga, gb, gc
         entry.n_bwd = L.launch_count() - n0
         self._graphs[key] = entry
         return entry
@@ -1171,5 +1223,7 @@ class _FS2Function(torch.autograd.Function):
             entry.bwd_a.replay()
             model._grad_ready()
             entry.bwd_b.replay()
+            model._grad_ready_mid()
+            entry.bwd_c.replay()
             model.replayed_launches += entry.n_bwd
         return (torch.zeros(1, device=dmel.device),) + (None,) * 10
