@@ -6,6 +6,7 @@ from .optim import FusedAdamW  # noqa: F401
 from .intensity import get_intensity_representation, intensity_prototypes, intensity_segment_mean  # noqa: F401
 from .rank_model import IntensityExtractor  # noqa: F401
 from .collate import DeviceCollate  # noqa: F401
+from .npz_io import NpzUtterances, read_npz_utterance, write_npz_utterance  # noqa: F401
 
 DEFAULT_MODEL_CONFIG = dict(
     enc_num_layers=6, enc_num_head=2, enc_d_model=384, enc_ffn_dim=1536, enc_k_dim=384, enc_v_dim=384,

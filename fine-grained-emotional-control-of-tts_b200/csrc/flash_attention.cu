@@ -180,11 +180,14 @@ __device__ __forceinline__ void dkv_pt(const uint32_t* r, const uint32_t* d, con
 }
 
 // ===================================================================================================== forward
-constexpr int FWD_NCH = 2;                       // threads per query row (column halves of a key block)
+#ifndef FS2_FWD_NCH
+#define FS2_FWD_NCH 2
+#endif
+constexpr int FWD_NCH = FS2_FWD_NCH;             // threads per query row (column slices of a key block)
 constexpr int FWD_THREADS = 32 * (2 + 4 * FWD_NCH);
 template <bool PT> struct FwdCfg {
   static constexpr int KST = PT ? 4 : 3, VST = PT ? 3 : 2;
-  static constexpr int SMEM = T128 + (KST + VST) * T64 + (PT ? 0 : 2 * AQ * 128) + FA_TAB + 1024 + 512 + FWD_NCH * AQ * 8;
+  static constexpr int SMEM = T128 + (KST + VST) * T64 + (PT ? 0 : 2 * AQ * 128) + FA_TAB + 1024 + 512 + FWD_NCH * AQ * 4;
 };
 constexpr int F_TMEM_S = 0, F_TMEM_O = 128, F_TMEM_P = 320;      // S: 2 x 64 columns, O: 192, P: 2 x 32 (bf16 pairs)
 
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
   uint64_t* pempty = pfull + 2;
   uint64_t* ofull = pempty + 2;
   uint32_t* tmem_slot = (uint32_t*)(ofull + 1);
-  float2* xch = (float2*)(tmem_slot + 2);
+  float* xch = (float*)(tmem_slot + 2);      // [NCH][AQ] exchange between the threads of a row
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = p.err;
@@ -361,11 +364,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
       const bool full = (c0 + CW <= kv);
       if (job == nkb) {
         // row maximum over both column halves, in the log2 domain
-        xch[ch * AQ + row] = make_float2(mx, 0.f);
+        xch[ch * AQ + row] = mx;
         asm volatile("bar.sync 1, %0;" ::"n"(128 * NCH) : "memory");
         float m = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) m = fmaxf(m, xch[c * AQ + row].x);
+        for (int c = 0; c < NCH; ++c) m = fmaxf(m, xch[c * AQ + row]);
         mx = m * sc2;
         asm volatile("bar.sync 1, %0;" ::"n"(128 * NCH) : "memory");     // xch is reused for the sums
       }
@@ -374,7 +377,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
       if (main_pass) PROBE_T(w2_sf); else PROBE_T(w1_sf);
       tc_fence_after();
       uint32_t r[CW];
-      tmem_ld32(lane_addr + (uint32_t)(F_TMEM_S + sb * AK + ch * CW), r);
+      if constexpr (CW == 32) tmem_ld32(lane_addr + (uint32_t)(F_TMEM_S + sb * AK + ch * CW), r);
+      else tmem_ld16(lane_addr + (uint32_t)(F_TMEM_S + sb * AK + ch * CW), r);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&sempty[sb]));
@@ -413,7 +417,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
       PROBE_T(w2_pe);
       if constexpr (PT) {
         tc_fence_after();
-        tmem_st16(lane_addr + (uint32_t)(F_TMEM_P + pb * 32 + ch * (CW / 2)), pk);
+        if constexpr (CW == 32) tmem_st16(lane_addr + (uint32_t)(F_TMEM_P + pb * 32 + ch * (CW / 2)), pk);
+        else tmem_st8(lane_addr + (uint32_t)(F_TMEM_P + pb * 32 + ch * (CW / 2)), pk);
         tmem_wait_st();
         tc_fence_before();
       } else {
@@ -435,11 +440,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) fa_fwd_kernel(const __grid_con
     // row sum over both column halves; O = acc / sum; lse = max + log2(sum)
     bf16* orow = p.out + (long long)(row_base + t) * p.D + h * HD + ch * (HD / NCH);
     if (nkb > 0) {
-      xch[ch * AQ + row] = make_float2(sum, 0.f);
+      xch[ch * AQ + row] = sum;
       asm volatile("bar.sync 1, %0;" ::"n"(128 * NCH) : "memory");
       float tot = 0.f;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) tot += xch[c * AQ + row].x;
+      for (int c = 0; c < NCH; ++c) tot += xch[c * AQ + row];
       const float inv = (dr.thr != 0u ? dr.ks : 1.0f) / tot;
       if (p.lse && ch == 0 && row_valid) p.lse[(long long)bh * p.Tl + t] = mx + log2f(tot);
       if (mbar_wait(smem_u32(ofull), 0, err)) {

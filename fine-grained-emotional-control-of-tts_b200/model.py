@@ -698,6 +698,22 @@ class FastSpeech2(nn.Module):
         has_p, has_e = pitch is not None, energy is not None
         return (mel, post, pd, pp, ap if has_p else None, pe, ae if has_e else None, self._last_mel_lens_cpu)
 
+    def forward_batch(self, texts, src_lens, mels, durations, pitches, energies, intensity, speakers=None, **control):
+        """The call as BASELINE.json's north_star spells it -- forward(texts, src_lens, mels, durations, pitches, energies,
+        intensity) -- mapped onto the reference's real signature: `texts` are the padded token ids (positions
+        >= src_lens[b] are forced to the padding id, which is what the reference's collate guarantees, dataset.py:78-81),
+        `mels` only fixes the frame count the targets were padded to (the model never reads target mels, model.py:279-290),
+        `speakers` defaults to speaker 0.  Same return tuple as forward()."""
+        tokens = texts.long()
+        if src_lens is not None:
+            pos = torch.arange(tokens.shape[1], device=tokens.device)[None]
+            tokens = torch.where(pos < src_lens.to(tokens.device)[:, None], tokens, torch.full_like(tokens, self.padding_idx))
+        if speakers is None:
+            speakers = torch.zeros(tokens.shape[0], dtype=torch.long, device=tokens.device)
+        if mels is not None and pitches is not None and mels.shape[1] != pitches.shape[1]:
+            raise ValueError("forward_batch: mels and pitches are padded to different frame counts")
+        return self.forward(tokens, speakers, durations, pitches, energies, intensity=intensity, **control)
+
     def _forward_impl(self, tokens, speakers, durations, pitch, energy, pace, pitch_rate, energy_rate, intensity,
                       Tm_known=None):
         st = self.store

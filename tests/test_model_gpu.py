@@ -301,3 +301,22 @@ def test_full_size_batch_properties(pkg):
     assert abs(outs["bf16"][1] - outs["fp32"][1]) <= 5e-3 * abs(outs["fp32"][1])
     ga, gb = outs["bf16"][2].double(), outs["fp32"][2].double()
     assert ((ga - gb).norm() / gb.norm()).item() <= 0.1
+
+
+def test_north_star_spelled_call_equals_the_reference_call(pkg):
+    """forward_batch(texts, src_lens, mels, durations, pitches, energies, intensity) is the reference call in the
+    north_star's argument order: identical outputs, and garbage behind src_lens is ignored."""
+    import importlib
+    data = importlib.import_module("fine-grained-emotional-control-of-tts_b200.data")
+    torch.manual_seed(0)
+    m = pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4, precision="bf16").cuda().eval()
+    (batch, intensity), = data.synthetic_batches(4, 1, seed=3, min_tp=8, max_tp=20, max_frames=120, pool_factor=2)
+    tokens, speakers, in_lens, mel, pitch, energy, dur, out_lens = [t.cuda() for t in batch[:8]]
+    with torch.no_grad():
+        a = m(tokens, speakers, dur, pitch, energy, intensity=intensity.cuda())
+        dirty = tokens.clone()
+        dirty[torch.arange(tokens.shape[1], device="cuda")[None] >= in_lens[:, None]] = 7
+        b = m.forward_batch(dirty, in_lens, mel, dur, pitch, energy, intensity.cuda(), speakers=speakers)
+    for x, y in zip(a[:7], b[:7]):
+        assert torch.equal(x, y)
+    assert torch.equal(a[7], b[7])
