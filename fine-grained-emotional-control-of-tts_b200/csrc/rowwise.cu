@@ -1057,6 +1057,81 @@ __global__ void __launch_bounds__(THREADS) lr_bwd_kernel(const float* __restrict
   }
 }
 
+// Segment-sum form: one CTA owns 8 consecutive rows of the padded output (= 8 phonemes) and therefore one contiguous
+// run of frames.  A warp owns a 128-column block of the rows and every P-th frame of the run (D = 384: 3 column blocks
+// x 2 frame phases = 6 warps), so a long phoneme -- a 200-frame silence -- is shared by all warps instead of stalling
+// one, every (phoneme, column) sum has exactly one writer per phase, and the phases are combined in a fixed order:
+// no atomics, no memset of the output (halo rows and zero-duration phonemes come out as zeros), bit-reproducible.
+constexpr int LRB_MAXD = 512;
+__global__ void __launch_bounds__(THREADS) lr_bwd_seg_kernel(const float* __restrict__ df, const float* __restrict__ df2,
+                                                             int f_pitch, int f_off, const int* __restrict__ ends, int B,
+                                                             int Tp, int Tm, int D, float* __restrict__ dphon, int p_pitch,
+                                                             int p_off) {
+  pdl_wait();
+  __shared__ float part[2 * WARPS * LRB_MAXD];     // [phase][local row][D], phases <= 2 * (512 / D) fit for D >= 256 ...
+  __shared__ int s_end[WARPS + 1];                 // s_end[i] = first frame of local row i (s_end[8] = end of the run)
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * WARPS;             // first row of the padded (p_pitch-row) output of item b
+  const int ncb = D / 128;                         // column blocks (host guarantees D % 128 == 0, D <= 512)
+  const int P = min(WARPS / ncb, (2 * WARPS * LRB_MAXD) / (WARPS * D));      // frame phases
+  if (threadIdx.x <= WARPS) {
+    const int p = row0 - p_off + threadIdx.x;      // phoneme that STARTS at this boundary; rows outside [0, Tp) are empty
+    const int* e = ends + (long long)b * Tp;
+    s_end[threadIdx.x] = p <= 0 ? 0 : min(e[min(p, Tp) - 1], Tm);
+  }
+  __syncthreads();
+  const int fa = s_end[0], fb = s_end[WARPS];
+  const int cb = warp % ncb, phase = warp / ncb;
+  const int c = cb * 128 + lane * 4;
+  if (phase < P) {
+    const float* src = df + ((long long)b * f_pitch + f_off) * D + c;
+    const float* src2 = df2 ? df2 + ((long long)b * f_pitch + f_off) * D + c : nullptr;
+    float* mine = part + (long long)phase * WARPS * D + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur = 0;                                   // local row of the running sum
+    for (int q = 0; q < WARPS; ++q) st4(mine + q * D, acc);
+    for (int f = fa + phase; f < fb; f += 4 * P) {
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ff = f + j * P;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ff < fb) {
+          v[j] = ld4(src + (long long)ff * D);
+          if (src2) { const float4 w = ld4(src2 + (long long)ff * D); v[j].x += w.x; v[j].y += w.y; v[j].z += w.z; v[j].w += w.w; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ff = f + j * P;
+        if (ff >= fb) break;
+        int q = cur;
+        while (ff >= s_end[q + 1]) ++q;            // frames are visited in increasing order: q only grows
+        if (q != cur) { st4(mine + cur * D, acc); acc = make_float4(0.f, 0.f, 0.f, 0.f); cur = q; }
+        acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+      }
+    }
+    st4(mine + cur * D, acc);
+  }
+  __syncthreads();
+  // row `warp` of the tile: phases added in order, stored once
+  const int row = row0 + warp;
+  if (row < p_pitch) {
+    float* dst = dphon + ((long long)b * p_pitch + row) * D;
+    for (int cc = lane * 4; cc < D; cc += 128) {
+      float4 t = ld4(part + warp * D + cc);
+      for (int ph = 1; ph < P; ++ph) {
+        const float4 u = ld4(part + ((long long)ph * WARPS + warp) * D + cc);
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      st4(dst + cc, t);
+    }
+  }
+}
+
+int g_lr_bwd_seg = 0; // 0: frame-parallel form with vector atomics (default: 23.5 us at B = 64), 1: segment-sum form (no memset, no
+                      // atomics, bit-reproducible; 31.5 us) -- fs2_lr_tune_bwd
 int g_lr_rb = 4;      // rows in flight per warp in lr_expand / lr_bwd: 2, 4 or 8 (fs2_lr_tune)
 int g_lr_bulk = 8;    // rows per CTA of lr_expand_bulk_kernel: 8 ... 128 (8 measured best on B200: 82 % of the HBM peak); 0 = SIMT kernel (fs2_lr_bulk_rows)
 
@@ -1694,6 +1769,12 @@ extern "C" int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pit
   REQUIRE(dframes && ends && dphon && D % 4 == 0, "fs2_lr_bwd: bad arguments");
   REQUIRE(B > 0 && B <= 65535 && Tp > 0 && Tp <= 12000 && Tm > 0, "fs2_lr_bwd: B <= 65535 and 0 < Tp <= 12000 (prefix sums are staged in shared memory)");
   (void)mel_lens;
+  if (g_lr_bwd_seg && D % 128 == 0 && D <= LRB_MAXD) {
+    REQUIRE(p_off >= 0 && p_pitch >= p_off + Tp, "fs2_lr_bwd: bad output pitch");
+    FS2_LAUNCH((lr_bwd_seg_kernel), dim3((p_pitch + WARPS - 1) / WARPS, B), THREADS, 0, ST, dframes, dframes2, f_pitch, f_off, ends,
+               B, Tp, Tm, D, dphon, p_pitch, p_off);
+    return fs2_check_launch();
+  }
   CUDA_CHECK_RET(cudaMemsetAsync(dphon, 0, (size_t)B * p_pitch * D * sizeof(float), ST));
   const dim3 grid((Tm + LR_ROWS - 1) / LR_ROWS, B);
 #define LR_BWD(RB) FS2_LAUNCH((lr_bwd_kernel<RB>), grid, THREADS, (size_t)Tp * sizeof(int), ST, dframes, dframes2, f_pitch, f_off, ends, B, Tp, Tm, D, dphon, p_pitch, p_off)
@@ -1706,6 +1787,13 @@ extern "C" int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pit
 extern "C" int fs2_lr_tune(int rows_in_flight) {
   REQUIRE(rows_in_flight == 2 || rows_in_flight == 4 || rows_in_flight == 8, "fs2_lr_tune: 2, 4 or 8");
   g_lr_rb = rows_in_flight;
+  return FS2_OK;
+}
+
+/* 1 = segment-sum form of fs2_lr_bwd (plain stores, no memset, bit-reproducible), 0 (default) = frame-parallel form
+ * (memset + 16-byte vector atomics; faster on B200: 23.5 vs 31.5 us at B = 64) */
+extern "C" int fs2_lr_tune_bwd(int segment_sum) {
+  g_lr_bwd_seg = segment_sum ? 1 : 0;
   return FS2_OK;
 }
 

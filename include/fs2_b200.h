@@ -208,9 +208,10 @@ int fs2_lr_finalize(const int* mel_lens, int B, int Tm_expected, long long* out_
 int fs2_lr_expand(const float* in, int in_pitch, int in_off, const int* ends, const int* mel_lens, const float* pe,
                   int B, int Tp, int Tm, int D, float* out_f32, void* out_act, int act_bf16,
                   int out_pitch, int out_off, int* frame2ph, void* stream);
-/* backward: dphon[b,p,:] = sum over the phoneme's frames of (dframes + dframes2).  Frame-parallel segment sum: the
- * whole dphon buffer (B * p_pitch rows) is zeroed by the call, runs of frames are flushed with 16-byte vector atomics
- * (fp32 sums of <= max-duration terms; the order of the partial sums is not fixed). */
+/* backward: dphon[b,p,:] = sum over the phoneme's frames of (dframes + dframes2).  Default: frame-parallel segment sum
+ * (the whole dphon buffer, B * p_pitch rows, is zeroed by the call; runs of frames are flushed with 16-byte vector atomics,
+ * so the order of the partial sums is not fixed).  fs2_lr_tune_bwd(1) selects the reproducible form: one CTA per 8 output
+ * rows, every row written exactly once with a plain store (no memset, no atomics, fixed summation order). */
 int fs2_lr_bwd(const float* dframes, const float* dframes2, int f_pitch, int f_off, const int* ends,
                const int* mel_lens, int B, int Tp, int Tm, int D, float* dphon, int p_pitch, int p_off, void* stream);
 /* measurement hook: rows in flight per warp (2, 4 or 8) in fs2_lr_expand / fs2_lr_bwd (default 4, chosen on B200) */
@@ -219,6 +220,9 @@ int fs2_lr_tune(int rows_in_flight);
  * fs2_lr_expand runs on the bulk-copy engine: cp.async.bulk global -> shared once per phoneme run, shared -> global
  * once per frame, no register staging.  Measurement hook: rows per CTA of that form (8 ... 128, default 8; 0 = never use it). */
 int fs2_lr_bulk_rows(int rows);
+/* 1 = reproducible segment-sum form of fs2_lr_bwd, 0 (default) = frame-parallel form (faster on B200: 23.5 vs 31.5 us at
+ * BASELINE configs[1]'s size) */
+int fs2_lr_tune_bwd(int segment_sum);
 
 /* misc row-space utilities */
 /* out = (src + reflect-fold_p(src) + add + add2) * rowmask, zero halo */

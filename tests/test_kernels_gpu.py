@@ -92,6 +92,26 @@ def test_length_regulator_bit_exact(lib, lr_bulk_rows, B, Tp, pace):
         m = torch.repeat_interleave(torch.arange(Tp), frames[b])
         ref_b[b].index_add_(0, m, df[b, : m.numel()].double().cpu())
     assert (dph.double().cpu() - ref_b).abs().max() <= 1e-4       # fp32 sums of <= 48 terms
+    # the model's call: padded row space on both sides, two gradient inputs, an output buffer full of garbage --
+    # every row (halo rows included) is written, deterministically, by both forms of the kernel
+    PAD = 4
+    dfp = torch.full((B, Tm + 2 * PAD, D), float("nan"), device="cuda")
+    dfp2 = torch.full((B, Tm + 2 * PAD, D), float("nan"), device="cuda")
+    dfp[:, PAD:PAD + Tm] = df
+    dfp2[:, PAD:PAD + Tm] = 0.5 * df
+    outs = []
+    raw = lib.load()
+    raw.fs2_lr_tune_bwd.argtypes = [lib.C.c_int]
+    for form in (1, 0, 1):
+        raw.fs2_lr_tune_bwd(form)
+        dpp = torch.full((B, Tp + 2 * PAD, D), float("nan"), device="cuda")
+        lib.call("fs2_lr_bwd", dfp, dfp2, Tm + 2 * PAD, PAD, ends, mel_lens, B, Tp, Tm, D, dpp, Tp + 2 * PAD, PAD)
+        torch.cuda.synchronize()
+        assert (dpp[:, :PAD] == 0).all() and (dpp[:, PAD + Tp:] == 0).all()
+        assert (dpp[:, PAD:PAD + Tp].double().cpu() - 1.5 * ref_b).abs().max() <= 2e-4
+        outs.append(dpp)
+    raw.fs2_lr_tune_bwd(0)
+    assert torch.equal(outs[0], outs[2])                          # segment-sum form: bit-reproducible
 
 
 @pytest.mark.parametrize("B,Tp,maxd", [(4, 9, 6), (6, 61, 24)])

@@ -116,8 +116,15 @@ def main():
                B * Tp * D * 4 + B * (Tm + 8) * D * 6 + Tm * D * 4, us,
                "model form: writes the fp32 stream and the bf16 GEMM operand in one pass")
         us = timeit(lambda i: L.call("fs2_lr_bwd", df[i], None, Tm + 8, PAD, ends, mel_lens, B, Tp, Tm, D, dph[i], Tp + 8, PAD), R)
-        report("lr_bwd (segment sums, B=64)" + tag, B * Tm * D * 4 + B * Tp * D * 4, us,
+        report("lr_bwd (frame-parallel segment sums: memset + vector atomics, B=64)" + tag, B * Tm * D * 4 + B * Tp * D * 4, us,
                "read B*Tm*D*4, write B*Tp*D*4 (+ the 13 MB memset of dphon inside the call)")
+        if hasattr(lib, "fs2_lr_tune_bwd"):
+            lib.fs2_lr_tune_bwd.argtypes = [L.C.c_int]
+            lib.fs2_lr_tune_bwd(1)
+            us = timeit(lambda i: L.call("fs2_lr_bwd", df[i], None, Tm + 8, PAD, ends, mel_lens, B, Tp, Tm, D, dph[i], Tp + 8, PAD), R)
+            report("lr_bwd (reproducible form: one CTA per 8 phonemes, plain stores, B=64)" + tag, B * Tm * D * 4 + B * Tp * D * 4, us,
+                   "opt-in (fs2_lr_tune_bwd(1)): no memset, no atomics, fixed summation order")
+            lib.fs2_lr_tune_bwd(0)
     lib.fs2_lr_tune(4)
     # plain fp32 expansion on the bulk-copy engine (cp.async.bulk in and out of shared memory), rows per CTA swept;
     # 0 = the SIMT kernel measured above
