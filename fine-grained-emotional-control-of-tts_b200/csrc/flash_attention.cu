@@ -9,9 +9,10 @@
 //       warps 2+ softmax: tcgen05.ld of the score tile, pass 1 = row maximum only (no exponentials), pass 2 = recompute
 //                the scores, p = 2^(s - max) (un-normalised), dropout, P -> TENSOR MEMORY (bf16 pairs, the A operand
 //                of the second contraction, tcgen05.st) ; O is scaled by 1 / sum in the epilogue
-//   fa_bwd_dq_kernel  same tiling: S = Q.K^T and dPd = dO.V^T per key block (TMEM), P = 2^(s - lse),
+//   fa_bwd_kernel     ONE launch for the backward, two kinds of CTA (after fa_rowdot_kernel: D = scale * rowsum(dO * O)):
+//     dQ tiles   same tiling as the forward: S = Q.K^T and dPd = dO.V^T per key block (TMEM), P = 2^(s - lse),
 //                dS = scale * P * (dPd * keep - rowsum(dO * O)) -> tensor memory -> dQ += dS.K (TMEM accumulator)
-//   fa_bwd_dkv_kernel one CTA = 128 KEY rows of one (item, head), queries in blocks of 32: S^T = K.Q^T and
+//     dK/dV tiles one CTA = 128 KEY rows of one (item, head), queries in blocks of 32: S^T = K.Q^T and
 //                dPd^T = V.dO^T (TMEM, two buffers worked by two warp groups in ping-pong), P^T / dS^T overwrite their own
 //                score columns in tensor memory, dV += Pd^T.dO and dK += dS^T.Q (two 192-column TMEM accumulators)
 #include <cuda.h>
@@ -483,10 +484,8 @@ constexpr int DQ_KST = 3, DQ_VST = 2;
 constexpr int DQ_SMEM = 2 * T128 + (DQ_KST + DQ_VST) * T64 + FA_TAB + 1024 + 512 + BWD_NCH * AQ * 4;
 constexpr int A_TMEM_S = 0, A_TMEM_DP = 128, A_TMEM_DQ = 256, A_TMEM_DS = 448;   // 2 x 64, 2 x 64, 192, 2 x 32 columns
 
-__global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                   const __grid_constant__ CUtensorMap tmdO,
-                                                                   const __grid_constant__ CUtensorMap tmKV,
-                                                                   const FaParams p) {
+__device__ __forceinline__ void fa_dq_body(const CUtensorMap& tmQ, const CUtensorMap& tmdO, const CUtensorMap& tmKV,
+                                           const FaParams& p, const int tile) {
   constexpr int NCH = BWD_NCH, KST = DQ_KST, VST = DQ_VST, CW = AK / NCH;      // 16 score columns per thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -507,13 +506,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
   uint64_t* pempty = pfull + 2;
   uint64_t* ofull = pempty + 2;
   uint32_t* tmem_slot = (uint32_t*)(ofull + 1);
-  float* xch = (float*)(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = p.err;
   const int nqb = (p.T + AQ - 1) / AQ;
-  const int qb = blockIdx.x % nqb;
-  const int bh = blockIdx.x / nqb;
+  const int qb = tile % nqb;
+  const int bh = tile / nqb;
   const int b = bh / p.H, h = bh % p.H;
   const int kv = fa_kv(p.lens, p.B, p.H, bh, p.plain_mask);
   const int nkb = (kv + AK - 1) / AK;
@@ -579,7 +577,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
       bool ok = mbar_wait(smem_u32(qfull), 0, err);
       int s = 0, sv = 0, sd = 0;                   // K stage of the score MMA, V stage, K stage of the dQ MMA
       uint32_t ph = 0, phv = 0;
-      const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0;
+      const bool prof = kProbe && p.dbg != nullptr && tile == 0;
       long long w_k = 0, w_v = 0, w_se = 0, w_pf = 0, t_all = clock64(), tt = t_all;
       for (int job = 0; job <= nkb && ok; ++job) {
         if (job < nkb) {
@@ -636,34 +634,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dq_kernel(const __grid_
       for (int c = (warp - 2) * 32 + lane; c < nkb * AK; c += 128 * NCH) sTab[c] = adrop_col(dr, c);
     const float sc2 = p.scale * LOG2E;
     const float scale = p.scale;
-    // D_i = sum_c dO[t,c] * O[t,c]  (== sum_k Pd * dPd, the softmax-backward row term); each thread takes 48 of the 192 dims
-    float dsum = 0.f;
-    if (row_valid) {
-      const uint4* a = reinterpret_cast<const uint4*>(p.dO + (long long)(row_base + t) * p.D + h * HD + ch * (HD / NCH));
-      const uint4* o = reinterpret_cast<const uint4*>(p.O + (long long)(row_base + t) * p.D + h * HD + ch * (HD / NCH));
-#pragma unroll
-      for (int i = 0; i < HD / NCH / 8; ++i) {
-        const uint4 x = a[i], y = o[i];
-        const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 fx = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[k]));
-          const float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[k]));
-          dsum += fx.x * fy.x + fx.y * fy.y;
-        }
-      }
-    }
-    xch[ch * AQ + row] = dsum;
-    asm volatile("bar.sync 1, %0;" ::"n"(128 * NCH) : "memory");
-    dsum = 0.f;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) dsum += xch[c * AQ + row];
-    const float ds_s = dsum * scale;               // the dK/dV kernel reads the row term pre-multiplied by the softmax scale
-    if (ch == 0 && row_valid) p.dvec[(long long)bh * p.Tl + t] = ds_s;
+    // scale * rowsum(dO * O) of this row (the softmax-backward row term) comes from fa_rowdot_kernel
+    const float ds_s = row_valid ? p.dvec[(long long)bh * p.Tl + t] : 0.f;
+    if (dr.thr != 0u) asm volatile("bar.sync 1, %0;" ::"n"(128 * NCH) : "memory");       // the dropout word table is complete
     const float ks_s = (dr.thr != 0u ? dr.ks : 1.0f) * scale;
     // rows past T: lse = +inf makes every probability 2^-inf = 0 without a per-element test
     const float lse = row_valid ? p.lse[(long long)bh * p.Tl + t] : INFINITY;
-    const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
+    const bool prof = kProbe && p.dbg != nullptr && tile == 0 && warp == 2 && lane == 0;
     long long w_sf = 0, w_ld = 0, w_m = 0, w_pe = 0, w_st = 0, t_all = clock64(), tt = t_all;
     for (int j = 0; j < nkb; ++j) {
       const int sb = j & 1, pb = j & 1;
@@ -740,10 +717,8 @@ constexpr int KV_STAGE = 2 * T32 + 256;                          // Q block, dO 
 constexpr int KV_SMEM = 2 * T128 + KV_QST * 2 * T32 + KV_QST * 256 + FA_TAB + 1024 + 512;
 constexpr int B_TMEM_ST = 0, B_TMEM_DPT = 64, B_TMEM_DV = 128, B_TMEM_DK = 320;   // 2 x 32, 2 x 32, 192, 192 columns
 
-__global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,
-                                                                    const __grid_constant__ CUtensorMap tmQ,
-                                                                    const __grid_constant__ CUtensorMap tmdO,
-                                                                    const FaParams p) {
+__device__ __forceinline__ void fa_dkv_body(const CUtensorMap& tmKV, const CUtensorMap& tmQ, const CUtensorMap& tmdO,
+                                            const FaParams& p, const int tile) {
   constexpr int QST = KV_QST;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -766,8 +741,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* err = p.err;
   const int nkt = (p.T + AQ - 1) / AQ;
-  const int kt = blockIdx.x % nkt;
-  const int bh = blockIdx.x / nkt;
+  const int kt = tile % nkt;
+  const int bh = tile / nkt;
   const int b = bh / p.H, h = bh % p.H;
   const int kv = fa_kv(p.lens, p.B, p.H, bh, p.plain_mask);
   const int k0 = kt * AQ;
@@ -829,7 +804,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
       bool ok = mbar_wait(smem_u32(kvfull), 0, err);
       int s = 0, sd = 0;
       uint32_t ph = 0;
-      const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0;
+      const bool prof = kProbe && p.dbg != nullptr && tile == 0;
       long long w_q = 0, w_bf = 0, w_pf = 0, t_all = clock64(), tt = t_all;
       for (int job = 0; job <= nq && ok; ++job) {
         if (job < nq) {
@@ -889,7 +864,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
     }
     const float sc2 = p.scale * LOG2E;
     const float ks_s = (dr.thr != 0u ? dr.ks : 1.0f) * p.scale;
-    const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
+    const bool prof = kProbe && p.dbg != nullptr && tile == 0 && warp == 2 && lane == 0;
     long long w_sf = 0, w_ld = 0, w_m = 0, w_st = 0, t_all = clock64(), tt = t_all;
     for (int i = g; i < nq; i += 2) {
       const int s = i % QST;
@@ -964,6 +939,42 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_dkv_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_free512(tmem_base);
+}
+
+// One launch for the whole attention backward: the first half of the grid are dK/dV tiles (the longer ones first), the second
+// half dQ tiles.  Two separate launches of 448 CTAs each end in two nearly empty fourth waves on 148 SMs (3.03 waves at
+// B = 32, T = 800); 896 CTAs of one launch fill the machine until the very end.  The row term D = scale * rowsum(dO * O) both
+// kinds of tile need comes from a small pre-pass (fa_rowdot_kernel), so the tiles are independent of each other.
+__global__ void __launch_bounds__(BWD_THREADS, 1) fa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ128,
+                                                                const __grid_constant__ CUtensorMap tmdO128,
+                                                                const __grid_constant__ CUtensorMap tmKV64,
+                                                                const __grid_constant__ CUtensorMap tmQ32,
+                                                                const __grid_constant__ CUtensorMap tmdO32, const FaParams p) {
+  const int n_tiles = (p.T + AQ - 1) / AQ * p.B * p.H;
+  if ((int)blockIdx.x < n_tiles) fa_dkv_body(tmQ128, tmQ32, tmdO32, p, (int)blockIdx.x);
+  else fa_dq_body(tmQ128, tmdO128, tmKV64, p, (int)blockIdx.x - n_tiles);
+}
+
+// dvec[bh][t] = scale * sum_c dO[t, c] * O[t, c] over the head's 192 columns: one warp per (row, head)
+__global__ void __launch_bounds__(256) fa_rowdot_kernel(const FaParams p) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long n = (long long)p.B * p.H * p.T;
+  for (long long i = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += (long long)gridDim.x * 8) {
+    const int t = (int)(i % p.T);
+    const int bh = (int)(i / p.T);
+    const int b = bh / p.H, h = bh % p.H;
+    const long long o = ((long long)b * p.TP + FS2_PAD + t) * p.D + h * HD + lane * 2;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < HD / 64; ++k) {
+      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.dO + o + 64 * k));
+      const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p.O + o + 64 * k));
+      acc += x.x * y.x + x.y * y.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) p.dvec[(long long)bh * p.Tl + t] = acc * p.scale;
+  }
 }
 
 // the keep mask of the attention dropout, for tests (uint8 [B*H, T, T])
@@ -1053,14 +1064,13 @@ extern "C" int fs2_flash_attn_bwd(const void* dO, const void* O, const void* qkv
   int rc = fa_common(qkv, lens, B, H, T, D, p);
   if (rc) return rc;
   if (!dO || !O || !lse || !dvec || !dqkv) { fs2_set_error("fs2_flash_attn_bwd: null pointer"); return FS2_ERR_ARG; }
-  const long long rows = (long long)B * p.TP;
-  CUtensorMap tq128, tdo128, tkv64, tkv128, tq32, tdo32;
-  if ((rc = fs2_tc_make_map_2d(qkv, 3LL * D, rows, 3LL * D, 64, AQ, &tq128))) return rc;
-  if ((rc = fs2_tc_make_map_2d(dO, D, rows, D, 64, AQ, &tdo128))) return rc;
-  if ((rc = fs2_tc_make_map_2d(qkv, 3LL * D, rows, 3LL * D, 64, AK, &tkv64))) return rc;
-  if ((rc = fs2_tc_make_map_2d(qkv, 3LL * D, rows, 3LL * D, 64, BQ, &tq32))) return rc;
-  if ((rc = fs2_tc_make_map_2d(dO, D, rows, D, 64, BQ, &tdo32))) return rc;
-  tkv128 = tq128;
+  const long long prow = (long long)B * p.TP;
+  CUtensorMap tq128, tdo128, tkv64, tq32, tdo32;
+  if ((rc = fs2_tc_make_map_2d(qkv, 3LL * D, prow, 3LL * D, 64, AQ, &tq128))) return rc;
+  if ((rc = fs2_tc_make_map_2d(dO, D, prow, D, 64, AQ, &tdo128))) return rc;
+  if ((rc = fs2_tc_make_map_2d(qkv, 3LL * D, prow, 3LL * D, 64, AK, &tkv64))) return rc;
+  if ((rc = fs2_tc_make_map_2d(qkv, 3LL * D, prow, 3LL * D, 64, BQ, &tq32))) return rc;
+  if ((rc = fs2_tc_make_map_2d(dO, D, prow, D, 64, BQ, &tdo32))) return rc;
   if (drop_p > 0.f && T > FA_MAXT - AQ) {
     fs2_set_error("fs2_flash_attn: attention dropout is supported up to 1408 rows per item");
     return FS2_ERR_UNSUPPORTED;
@@ -1072,17 +1082,18 @@ extern "C" int fs2_flash_attn_bwd(const void* dO, const void* O, const void* qkv
   p.O = (const bf16*)O;
   p.dO = (const bf16*)dO;
   p.plain_mask = plain_mask;
+  constexpr int BWD_SMEM = DQ_SMEM > KV_SMEM ? DQ_SMEM : KV_SMEM;
   static bool cfg = false;
   if (!cfg) {
-    if ((rc = fa_smem_attr(fa_bwd_dq_kernel, DQ_SMEM))) return rc;
-    if ((rc = fa_smem_attr(fa_bwd_dkv_kernel, KV_SMEM))) return rc;
+    if ((rc = fa_smem_attr(fa_bwd_kernel, BWD_SMEM))) return rc;
     cfg = true;
   }
-  const int grid = (T + AQ - 1) / AQ * B * H;
-  FS2_LAUNCH(fa_bwd_dq_kernel, grid, BWD_THREADS, DQ_SMEM, (cudaStream_t)stream, tq128, tdo128, tkv64, p);
+  const int tiles = (T + AQ - 1) / AQ * B * H;
+  const long long rows = (long long)B * H * T;
+  FS2_LAUNCH(fa_rowdot_kernel, (unsigned)((rows + 7) / 8 < 4096 ? (rows + 7) / 8 : 4096), 256, 0, (cudaStream_t)stream, p);
   rc = fs2_check_launch();
   if (rc) return rc;
-  FS2_LAUNCH(fa_bwd_dkv_kernel, grid, BWD_THREADS, KV_SMEM, (cudaStream_t)stream, tkv128, tq32, tdo32, p);
+  FS2_LAUNCH(fa_bwd_kernel, 2 * tiles, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream, tq128, tdo128, tkv64, tq32, tdo32, p);
   return fs2_check_launch();
 }
 

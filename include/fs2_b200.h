@@ -150,7 +150,8 @@ int fs2_softmax_bwd(const void* P, const float* dPd, const int* lens, int B, int
  * key-padding mask (keys [0, lens[b]) for every head) as nn.MultiheadAttention(key_padding_mask=...) in the intensity
  * extractor (rank_model/model.py:34, 103); 0: FastSpeech2's attn_mask quirk, keys [0, min(len[b], len[(b*H+h) % B])).
  * backward: dQ, dK, dV into columns [0,D), [D,2D), [2D,3D) of dqkv (B*(T+8), 3D) bf16, rows t < T written;
- * two launches: the dQ kernel (also writes dvec = rowsum(dO*O), same shape as lse, scratch) and the dK/dV kernel. */
+ * a row-dot pre-pass (dvec = scale * rowsum(dO*O), same shape as lse, scratch) and ONE launch whose grid holds the dK/dV
+ * tiles followed by the dQ tiles (two separate launches would each end in a nearly empty last wave). */
 int fs2_flash_attn_lse_len(int T);
 int fs2_flash_attn_fwd(const void* qkv, const int* lens, int B, int H, int T, int D, float scale, float drop_p,
                        unsigned long long seed, const unsigned long long* seed_dev, float* lse, void* O, int plain_mask,
