@@ -508,7 +508,8 @@ def main():
                    "l2_policy": "per-step working set (several GB of activations) exceeds the 126 MB L2; no flush needed",
                    "dropout": "on (train mode, counter-based masks)",
                    "mel_lens": "async (pinned, Tm = pitch.shape[1], device-side check)" if model.async_mel_lens else "synchronous read-back",
-                   "launch": "CUDA-graph replay per (B,Tp,Tm) shape" if model.use_cuda_graphs else "eager launches from Python"},
+                   "launch": "CUDA-graph replay per (B,Tp,Tm) shape" if model.use_cuda_graphs else "eager launches from Python",
+                   "optimizer": "FusedAdamW per gradient piece on an optimizer stream (DataParallelStep)"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 4 * BATCH,
                 "ms_per_step": ms_e / args.steps,
                 "note": "FastSpeech2()/Loss()/FusedAdamW public API; every step: pinned host batch -> device copy (copy stream, "

@@ -640,19 +640,22 @@ class FastSpeech2(nn.Module):
         p = sv.p
         d2_act, d1_act = self._act(rows, D), self._act(rows, D)
         dA1c = self._f32(rows, D)
+        fuse_bias = D <= 384           # the conv bias gradients (column sums of dact) come out of the LN backward kernels
         self._ln_bwd(B, T, D, sv.h2, self._P(f"{pname}.ln2.norm.weight"), self._P(f"{pname}.ln2.norm.bias"), 1e-5,
                      sv.mean2, sv.rstd2, dhead=dpred, head_w=self._P(f"{pname}.linear.w.weight"), head_scale=sv.scale,
                      drop_a=(p, sv.seeds[1]), lens=lens, relu_x=1, dact=d2_act,
                      dgamma=self._G(f"{pname}.ln2.norm.weight"), dbeta=self._G(f"{pname}.ln2.norm.bias"),
-                     dhead_w=self._G(f"{pname}.linear.w.weight"), dhead_b=self._G(f"{pname}.linear.w.bias"))
+                     dhead_w=self._G(f"{pname}.linear.w.weight"), dhead_b=self._G(f"{pname}.linear.w.bias"),
+                     dact_colsum=self._G(f"{pname}.conv2.conv.bias") if fuse_bias else None)
         self._conv_wgrad(d2_act, sv.a1, B, T, f"{pname}.conv2.conv.weight", f"{pname}.conv2.conv.weight",
-                         f"{pname}.conv2.conv.bias")
+                         None if fuse_bias else f"{pname}.conv2.conv.bias")
         self._conv_dgrad(d2_act, B, T, f"{pname}.conv2.conv.weight", dA1c)
         self._ln_bwd(B, T, D, sv.h1, self._P(f"{pname}.ln1.norm.weight"), self._P(f"{pname}.ln1.norm.bias"), 1e-5,
                      sv.mean1, sv.rstd1, dy2=dA1c, dy2_fold=h, drop_a=(p, sv.seeds[0]), lens=lens, relu_x=1,
-                     dact=d1_act, dgamma=self._G(f"{pname}.ln1.norm.weight"), dbeta=self._G(f"{pname}.ln1.norm.bias"))
+                     dact=d1_act, dgamma=self._G(f"{pname}.ln1.norm.weight"), dbeta=self._G(f"{pname}.ln1.norm.bias"),
+                     dact_colsum=self._G(f"{pname}.conv1.conv.bias") if fuse_bias else None)
         self._conv_wgrad(d1_act, sv.x_act, B, T, f"{pname}.conv1.conv.weight", f"{pname}.conv1.conv.weight",
-                         f"{pname}.conv1.conv.bias")
+                         None if fuse_bias else f"{pname}.conv1.conv.bias")
         self._conv_dgrad(d1_act, B, T, f"{pname}.conv1.conv.weight", dx_out)
 
     def _exact_log_durations(self, tokens, speakers, intensity, out):
