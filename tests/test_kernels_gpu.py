@@ -456,6 +456,13 @@ def test_fold_halo_colsum_pad_unpad(lib):
     cs = torch.zeros(C, device="cuda")
     lib.call("fs2_colsum", src, 0, src.shape[0], C, C, cs)
     assert (cs - src.sum(0)).abs().max() <= 1e-4
+    # bf16 inputs: the 16-byte-load kernel (C % 8 == 0), ragged column tails and a leading dimension wider than C
+    for rows_b, Cb, ldb in ((1000, 1536, 1536), (777, 1152, 1152), (300, 384, 1152), (50, 80, 80), (33, 52, 64)):
+        xb = randn(rows_b, ldb, seed=5).to(torch.bfloat16)
+        csb = torch.zeros(Cb, device="cuda")
+        lib.call("fs2_colsum", xb, 1, rows_b, Cb, ldb, csb)
+        refb = xb[:, :Cb].double().sum(0)
+        assert (csb.double() - refb).abs().max() <= 1e-3 * max(1.0, refb.abs().max().item()), (rows_b, Cb, ldb)
     plain = torch.full((B, T, C), float("nan"), device="cuda")
     lib.call("fs2_unpad_mask", src, lens, B, T, C, plain, None, 0, 0)
     assert torch.equal(plain, s[:, PAD:PAD + T] * (torch.arange(T, device="cuda")[None, :] < lens[:, None]).unsqueeze(-1))
