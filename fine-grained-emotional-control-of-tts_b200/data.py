@@ -89,10 +89,12 @@ def synthetic_batches(batch_size, n_batches, seed=1234, rank=0, min_tp=24, max_t
 
     world == 1 (default): one rank's private stream of batches, seeded by (seed, rank, step).
     world > 1 (data parallel): ONE pool of pool_factor*B*world utterances per draw, shared by all
-    ranks (same seed everywhere); the sorted pool is cut into pool_factor "length classes" of `world` consecutive
-    groups and rank r takes group r of a class, so the ranks of one step pad to (nearly) the same rectangle and
-    nobody waits at the gradient all-reduce.  The classes are visited in the order the single-GPU stream visits
-    its groups, so the mix of short and long batches per rank is the same at every world size."""
+    ranks (same seed everywhere); the sorted pool is cut into pool_factor "length classes" of `world * B` consecutive
+    utterances which are dealt to the ranks round-robin (rank r takes utterances r, r + world, ... of its class), so the
+    ranks of one step pad to the same rectangle to within a frame or two and nobody waits at the gradient all-reduce
+    (taking `world` neighbouring groups instead left the slowest rank ~3 % behind the mean: 0.25 ms of an 8.4 ms step).
+    The classes are visited in the order the single-GPU stream visits its groups, so the mix of short and long batches
+    per rank is the same at every world size."""
     out = []
     step = 0
     while len(out) < n_batches:
@@ -111,7 +113,11 @@ def synthetic_batches(batch_size, n_batches, seed=1234, rank=0, min_tp=24, max_t
         groups = [pool[i:i + batch_size] for i in range(0, len(pool), batch_size)]
         for k in perm:
             # length class k of the single-GPU stream = super-groups k*fine .. k*fine+fine-1; take the middle one
-            out.append(collate(groups[(k * fine + fine // 2) * world + rank] if world > 1 else groups[k]))
+            if world > 1:
+                g0 = (k * fine + fine // 2) * world * batch_size
+                out.append(collate(pool[g0:g0 + world * batch_size][rank::world]))
+            else:
+                out.append(collate(groups[k]))
             if len(out) == n_batches:
                 break
         step += 1

@@ -168,7 +168,9 @@ class FastSpeech2(nn.Module):
         self._anchor = torch.zeros(1, requires_grad=True)   # lets autograd reach our backward; never a parameter
         self._arenas = None
         self._seed_base = 0x1234
-        self.enc_grad_split = 2      # encoder layers >= 2 finish in part B of the backward, layers 0-1 + embedding in part C
+        # encoder layers at which the backward is cut into separately launched parts (descending): after each part the
+        # gradients of the layers it covered are final and are reported through grad_ready_hook (parallel.py)
+        self.enc_grad_splits = (4, 2, 1)
         self._generation = 0
         self._ctr = None              # device-side dropout step counter (uint64 in an int64 tensor)
         self.use_cuda_graphs = False  # opt-in: replay the captured step per (B, Tp, Tm) -- see _graph_forward
@@ -193,6 +195,7 @@ class FastSpeech2(nn.Module):
         # dgrad chain leaves idle (short grids, wave tails, memory-bound LN kernels)
         self.overlap_wgrad = True
         self._split_lo = None
+        self._split_ok = None
         self.grad_ready_hook = None   # callable(lo, hi): flat-gradient range [lo, hi) is final (set by DataParallelStep)
         self._side = None
         self._side_stream = None
@@ -935,9 +938,10 @@ class FastSpeech2(nn.Module):
         if not capturing:
             self._grad_ready()
         mid2 = self._backward_b(ctx, mid, dpd, dpp, dpe)
-        if not capturing:
-            self._grad_ready_mid()
-        self._backward_c(ctx, mid2)
+        for i in range(len(self._enc_cuts())):
+            if not capturing:
+                self._grad_ready_part(i)
+            mid2 = self._backward_c(ctx, mid2, i)
 
     @property
     def grad_split_lo(self):
@@ -955,9 +959,33 @@ class FastSpeech2(nn.Module):
         if self.grad_ready_hook is not None:
             self.grad_ready_hook(self.grad_split_lo, self.store.flat.numel())
 
-    def _grad_ready_mid(self):
-        if self.grad_ready_hook is not None and self.grad_split_mid < self.grad_split_lo:
-            self.grad_ready_hook(self.grad_split_mid, self.grad_split_lo)
+    def _enc_cuts(self):
+        """Validated cut layers, descending, inside (0, n_layers): part B covers layers >= cuts[0], part C_i the layers
+        [cuts[i+1], cuts[i]) and the last one [0, cuts[-1]) + the token embedding.  () = one part C with every layer."""
+        nl = self.enc["nl"]
+        cuts = sorted({int(c) for c in self.enc_grad_splits if 0 < int(c) < nl}, reverse=True)
+        return cuts if cuts else [nl]
+
+    def _layer_offset(self, l):
+        """First flat-buffer element of encoder.layers.{l} (l == n_layers: of encoder.norm)."""
+        pre = f"encoder.layers.{l}." if l < self.enc["nl"] else "encoder.norm."
+        return min(o for key, (o, _) in self.store.offsets.items() if key.startswith(pre))
+
+    def _grad_ready_part(self, i):
+        """Called before part C_i starts: the layers >= cuts[i] (down to the previous cut) have final gradients."""
+        if self.grad_ready_hook is None:
+            return
+        cuts = self._enc_cuts()
+        if cuts[i] >= self.enc["nl"]:
+            return
+        hi = self.grad_split_lo if i == 0 else self._layer_offset(cuts[i - 1])
+        lo = self._layer_offset(cuts[i])
+        # the flat order is the state_dict order: encoder.layers.0 ... 5, encoder.norm, then decoder.* (checked once)
+        if self._split_ok is None:
+            offs = [self._layer_offset(l) for l in range(self.enc["nl"] + 1)]
+            self._split_ok = offs == sorted(offs) and offs[-1] < self.grad_split_lo
+        if self._split_ok and lo < hi:
+            self.grad_ready_hook(lo, hi)
 
     def _backward_a(self, ctx, dmel, dpost, capturing=False):
         if not capturing and ctx.generation != self._generation:
@@ -1064,44 +1092,30 @@ class FastSpeech2(nn.Module):
         denc = self._f32(rowsP, D)
         self._conv_dgrad(dC_act, B, Tp, "concat_proj.tok", denc)
         # ---- encoder, upper layers: their gradients (and encoder.norm's) are final when this part ends
-        k = self.enc_grad_split_layer
+        k = self._enc_cuts()[0]
         est = self._stack_bwd(self.enc, ctx.enc_saves, ctx.enc_fin, denc, None, B, Tp, ctx.src_lens, ctx.src_lens, upto=k) \
-            if k > 0 else None
+            if k < self.enc["nl"] else None
         self._side_join()
         return est, denc
 
-    def _backward_c(self, ctx, mid):
-        """Lower encoder layers + token embedding (part C of the backward; see enc_grad_split)."""
+    def _backward_c(self, ctx, mid, i):
+        """Part C_i of the backward: the next group of encoder layers; the last one ends with the token embedding."""
         est, denc = mid
+        cuts = self._enc_cuts()
         B, Tp, D = ctx.B, ctx.Tp, self.D
         rowsP = B * (Tp + 2 * PAD)
+        last = i == len(cuts) - 1
+        upto = 0 if last else cuts[i + 1]
         self._side_begin(denc.device)
-        ea, eb = self._stack_bwd(self.enc, ctx.enc_saves, ctx.enc_fin, denc, None, B, Tp, ctx.src_lens, ctx.src_lens, st=est)
-        if eb is not None:
-            L.call("fs2_add_", ea, eb, rowsP * D)
-        L.call("fs2_embedding_bwd", ea, ctx.tokens, B, Tp, D, self.padding_idx,
-               self._G("encPreNet.token_embedding.Embedding.weight"))
+        out = self._stack_bwd(self.enc, ctx.enc_saves, ctx.enc_fin, denc, None, B, Tp, ctx.src_lens, ctx.src_lens, upto=upto, st=est)
+        if last:
+            ea, eb = out
+            if eb is not None:
+                L.call("fs2_add_", ea, eb, rowsP * D)
+            L.call("fs2_embedding_bwd", ea, ctx.tokens, B, Tp, D, self.padding_idx,
+                   self._G("encPreNet.token_embedding.Embedding.weight"))
         self._side_join()
-
-    @property
-    def enc_grad_split_layer(self):
-        """Encoder layers >= this index are back-propagated in part B of the backward, the rest in part C."""
-        return min(max(int(self.enc_grad_split), 0), self.enc["nl"])
-
-    @property
-    def grad_split_mid(self):
-        """First element of the flat buffers that belongs to encoder.layers.{enc_grad_split_layer} (everything from there up
-        to grad_split_lo -- the upper encoder layers and encoder.norm -- is final after part B)."""
-        k = self.enc_grad_split_layer
-        if k <= 0 or k >= self.enc["nl"]:
-            return 0 if k <= 0 else self.grad_split_lo
-        pre = tuple(f"encoder.layers.{l}." for l in range(k, self.enc["nl"])) + ("encoder.norm.",)
-        lo = min(o for key, (o, _) in self.store.offsets.items() if key.startswith(pre))
-        hi = self.grad_split_lo
-        if any(lo <= o < hi and not key.startswith(pre) for key, (o, _) in self.store.offsets.items()):
-            return hi                                # unexpected layout: nothing more is declared ready early
-        return lo
-
+        return (out, denc) if not last else None
 
     # ---------------------------------------------------------------------- CUDA graphs
     def _graph_eligible(self, durations, pitch, energy):
@@ -1195,10 +1209,13 @@ class FastSpeech2(nn.Module):
         gb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gb):
             mid2 = self._backward_b(ctx, mid, *entry.grad_in[2:])
-        gc = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gc):
-            self._backward_c(ctx, mid2)
-        entry.bwd_a, entry.bwd_b, entry.bwd_c = ga, gb, gc
+        entry.bwd_c = []
+        for i in range(len(self._enc_cuts())):
+            gc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gc):
+                mid2 = self._backward_c(ctx, mid2, i)
+            entry.bwd_c.append(gc)
+        entry.bwd_a, entry.bwd_b = ga, gb
         entry.n_bwd = L.launch_count() - n0
         self._graphs[key] = entry
         return entry
@@ -1242,7 +1259,8 @@ class _FS2Function(torch.autograd.Function):
             entry.bwd_a.replay()
             model._grad_ready()
             entry.bwd_b.replay()
-            model._grad_ready_mid()
-            entry.bwd_c.replay()
+            for i, gc in enumerate(entry.bwd_c):
+                model._grad_ready_part(i)
+                gc.replay()
             model.replayed_launches += entry.n_bwd
         return (torch.zeros(1, device=dmel.device),) + (None,) * 10
