@@ -33,7 +33,12 @@ def get_intensity_representation(intensity_extractor, batch, device):
     """Drop-in for train.py:16-51: same arguments, same (B, T_phon_max, D) result."""
     (phoneme, _, phon_len, _, _, _, duration_tgt, mel_len, _, _, rank_X, emo_ids) = batch
     with torch.no_grad():
-        I = intensity_extractor(rank_X, mel_len, emo_ids)
+        # the collate hands rank_X over channels-first (B, n_mels + 2, Tm) (dataset.py:116-117): say so instead of letting
+        # the extractor infer the layout from the shape (a batch padded to exactly n_mels + 2 frames would be ambiguous)
+        try:
+            I = intensity_extractor(rank_X, mel_len, emo_ids, channels_first=True)
+        except TypeError:                      # the reference's own IntensityExtractor has no such argument
+            I = intensity_extractor(rank_X, mel_len, emo_ids)
         return intensity_segment_mean(I.to(device), duration_tgt, phon_len, phoneme.shape[1])
 
 

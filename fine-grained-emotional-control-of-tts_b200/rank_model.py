@@ -125,14 +125,21 @@ class IntensityExtractor(nn.Module):
 
     # ------------------------------------------------------------------ forward (rank_model/model.py:97-109)
     @torch.no_grad()
-    def forward(self, x, length, emotions):
+    def forward(self, x, length, emotions, channels_first=None):
+        """channels_first: True for the collate's rank_X layout (B, n_mels + 2, T) (dataset.py:116-117), False for
+        (B, T, n_mels + 2) as rank_model/model.py:97 documents it; None infers it from the shape and refuses the one
+        ambiguous case (both axes equal n_mels + 2, i.e. a batch padded to exactly 82 frames) instead of guessing."""
         if not x.is_cuda:
             raise RuntimeError("fs2_b200: IntensityExtractor inputs must be CUDA tensors (there is no CPU fallback)")
         if x.dim() != 3:
             raise ValueError("x must be (B, T, n_mels + 2) or (B, n_mels + 2, T)")
-        channels_first = x.shape[-1] != self.n_in
-        if channels_first and x.shape[1] != self.n_in:
-            raise ValueError(f"no axis of x has size n_mels + 2 = {self.n_in}")
+        if channels_first is None:
+            if x.shape[1] == self.n_in and x.shape[2] == self.n_in:
+                raise ValueError(f"x is (B, {self.n_in}, {self.n_in}): the layout cannot be inferred, pass channels_first=")
+            channels_first = x.shape[-1] != self.n_in
+        channels_first = bool(channels_first)
+        if x.shape[1 if channels_first else 2] != self.n_in:
+            raise ValueError(f"the feature axis of x must have size n_mels + 2 = {self.n_in}")
         B = x.shape[0]
         T = x.shape[2] if channels_first else x.shape[1]
         if T <= PAD:

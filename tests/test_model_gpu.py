@@ -320,3 +320,46 @@ def test_north_star_spelled_call_equals_the_reference_call(pkg):
     for x, y in zip(a[:7], b[:7]):
         assert torch.equal(x, y)
     assert torch.equal(a[7], b[7])
+
+
+def test_piecewise_adamw_and_multi_part_backward_equal_the_plain_step(pkg):
+    """DataParallelStep's schedule on one GPU -- gradients reported piece by piece (grad_ready_hook after every part of the
+    backward), each piece updated by its own FusedAdamW.step(ranges=..., advance=...) on an optimizer stream -- must leave
+    exactly the parameters of `loss.backward(); opt.step()`; and any choice of encoder cut points gives the same gradient."""
+    import importlib
+    data = importlib.import_module("fine-grained-emotional-control-of-tts_b200.data")
+    par = importlib.import_module("fine-grained-emotional-control-of-tts_b200.parallel")
+    (batch, intensity), = data.synthetic_batches(4, 1, seed=3, min_tp=8, max_tp=20, max_frames=120, pool_factor=2)
+    dev_batch = [t.cuda() for t in batch[:8]]
+    tokens, speakers, in_lens, mel, pitch, energy, dur, out_lens = dev_batch
+    crit = pkg.Loss(**pkg.DEFAULT_LOSS_CONFIG)
+    flats, grads = [], []
+    for mode in ("plain", "trainer", "no_cuts"):
+        torch.manual_seed(0)
+        m = pkg.FastSpeech2(**pkg.DEFAULT_MODEL_CONFIG, n_speakers=4, precision="fp32").cuda().eval()
+        if mode == "no_cuts":
+            m.enc_grad_splits = ()
+        opt = pkg.FusedAdamW(m, lr=1e-3)
+        if mode == "trainer":
+            tr = par.DataParallelStep(m, crit, opt)
+            pieces = []
+            orig = tr._piece_ready
+            tr._piece_ready = lambda lo, hi: (pieces.append((lo, hi)), orig(lo, hi))[1]
+            tr(dev_batch, intensity.cuda())
+            assert len(pieces) == 5 and pieces[0][1] == m.store.flat.numel() and pieces[4][0] == 0      # five pieces per step
+        else:
+            opt.zero_grad()
+            preds = m(tokens, speakers, dur, pitch, energy, intensity=intensity.cuda())
+            crit(preds, (mel, dur, pitch, energy, out_lens, in_lens), 0)["total_loss"].backward()
+            opt.step()
+        torch.cuda.synchronize()
+        flats.append(m.store.flat.clone())
+        grads.append(m.store.flat_grad.clone())
+    # same kernels in the same order; only the atomics of the segment sums may order their partial sums differently, and
+    # Adam's first step (update = lr * sign(g)) turns a last-ulp difference of a near-zero gradient into a visible one:
+    # compare the gradients tightly and the parameters robustly
+    gmax = grads[0].abs().max()
+    for other in (1, 2):
+        assert (grads[0] - grads[other]).abs().max() <= 1e-5 * gmax, other
+        bad = ((flats[0] - flats[other]).abs() > 1e-5).float().mean().item()
+        assert bad <= 1e-4, (other, bad)

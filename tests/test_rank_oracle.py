@@ -80,6 +80,27 @@ def test_b200_forward_matches_reference_golden(channels_first):
 
 
 @pytest.mark.gpu
+def test_b200_forward_layout_is_explicit_when_ambiguous():
+    """A batch padded to exactly n_mels + 2 = 82 frames: both axes have the feature size.  The layout is then taken from
+    `channels_first`, never guessed (get_intensity_representation passes True for the collate's rank_X)."""
+    pkg = importlib.import_module("fine-grained-emotional-control-of-tts_b200.rank_model")
+    cfg = dict(RW.CFG, n_encoder_layers=1)
+    m = pkg.IntensityExtractor(**cfg)
+    m.load_state_dict(RW.state_dict(cfg), strict=True)
+    m = m.cuda().eval()
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 82, 82, generator=gen).cuda()                 # (B, T, C) with T == C
+    length, emo = torch.tensor([82, 40]).cuda(), torch.tensor([1, 3]).cuda()
+    with pytest.raises(ValueError, match="channels_first"):
+        m(x, length, emo)
+    a = m(x, length, emo, channels_first=False)
+    b = m(x.transpose(1, 2).contiguous(), length, emo, channels_first=True)
+    assert torch.equal(a, b)
+    c = m(x, length, emo, channels_first=True)                       # the other reading of the same bytes differs
+    assert not torch.allclose(a, c)
+
+
+@pytest.mark.gpu
 def test_b200_forward_ragged_batch_vs_oracle():
     pkg = importlib.import_module("fine-grained-emotional-control-of-tts_b200.rank_model")
     cfg = dict(RW.CFG, n_encoder_layers=2)
