@@ -24,6 +24,7 @@ _lib = None
 SIGNATURES = {
     "fs2_gemm_simt": "pp",
     "fs2_gemm_tc": "pp",
+    "fs2_gemm_ln_tc": "pp",
     "fs2_embed_posenc": "pppiiiippipp",
     "fs2_embedding_bwd": "ppiiiipp",
     "fs2_ln_fwd": "pp",
@@ -116,7 +117,18 @@ class Fs2LnBwd(C.Structure):
         ("relu_x", C.c_int),
         ("dx_f32", C.c_void_p), ("dact", C.c_void_p), ("act_bf16", C.c_int),
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dhead_w", C.c_void_p), ("dhead_b", C.c_void_p),
-        ("seed_dev", C.c_void_p), ("dact_colsum", C.c_void_p), ("dy3", C.c_void_p),
+        ("seed_dev", C.c_void_p), ("dact_colsum", C.c_void_p), ("dy3", C.c_void_p), ("y", C.c_void_p),
+    ]
+
+
+class Fs2GemmLn(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("T", C.c_int), ("K", C.c_int), ("lda", C.c_longlong), ("ldw", C.c_longlong),
+        ("A", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("x", C.c_void_p),
+        ("drop_p", C.c_float), ("drop_seed", C.c_ulonglong), ("seed_dev", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+        ("out_f32", C.c_void_p), ("out_act", C.c_void_p), ("halo", C.c_int),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p),
     ]
 
 

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
       continue;
     }
     const bool live = (p.lens == nullptr) || (t < p.lens[b]);
-    const float mean = p.mean[r], rstd = p.rstd[r];
+    const float mean = p.mean ? p.mean[r] : 0.f, rstd = p.rstd[r];
     const float dh = p.dhead ? p.dhead[(long long)b * T + t] * p.head_scale : 0.f;
     const int f = p.dy2_fold;
     const long long m1 = (f > 0 && t >= 1 && t <= f) ? -2LL * t * C : 0;
@@ -297,13 +297,22 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
       int c = lane * 4 + i * 128;
       xh[i] = gx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < C) {
-        float4 z = ld4(p.x + ro + c);
-        if (p.branch) {
-          float4 br = ld4(p.branch + ro + c);
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!HEAD && p.y) {
+          // the forward never materialised x + branch (fs2_gemm_ln_tc): x_hat comes from its output below; only the
+          // branch-dropout mask is regenerated here
+          z = ld4(p.y + ro + c);
           float4 k = drop_scale4(db, (uint64_t)(ro + c) >> 2);
-          z.x += br.x * k.x; z.y += br.y * k.y; z.z += br.z * k.z; z.w += br.w * k.w;
-          // remember the keep bits: the gradient of the branch needs the same mask again (one RNG evaluation, not two)
           keep_b |= ((k.x != 0.f ? 1u : 0u) | (k.y != 0.f ? 2u : 0u) | (k.z != 0.f ? 4u : 0u) | (k.w != 0.f ? 8u : 0u)) << (4 * i);
+        } else {
+          z = ld4(p.x + ro + c);
+          if (p.branch) {
+            float4 br = ld4(p.branch + ro + c);
+            float4 k = drop_scale4(db, (uint64_t)(ro + c) >> 2);
+            z.x += br.x * k.x; z.y += br.y * k.y; z.z += br.z * k.z; z.w += br.w * k.w;
+            // remember the keep bits: the gradient of the branch needs the same mask again (one RNG evaluation, not two)
+            keep_b |= ((k.x != 0.f ? 1u : 0u) | (k.y != 0.f ? 2u : 0u) | (k.z != 0.f ? 4u : 0u) | (k.w != 0.f ? 8u : 0u)) << (4 * i);
+          }
         }
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.dy) g = ld4(p.dy + ro + c);
@@ -321,7 +330,14 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
         }
         float4 gam = ld4(p.gamma + c), bet = ld4(p.beta + c);
         float4 h;
-        h.x = (z.x - mean) * rstd; h.y = (z.y - mean) * rstd; h.z = (z.z - mean) * rstd; h.w = (z.w - mean) * rstd;
+        if (!HEAD && p.y) {
+          h.x = gam.x != 0.f ? __fdividef(z.x - bet.x, gam.x) : 0.f;
+          h.y = gam.y != 0.f ? __fdividef(z.y - bet.y, gam.y) : 0.f;
+          h.z = gam.z != 0.f ? __fdividef(z.z - bet.z, gam.z) : 0.f;
+          h.w = gam.w != 0.f ? __fdividef(z.w - bet.w, gam.w) : 0.f;
+        } else {
+          h.x = (z.x - mean) * rstd; h.y = (z.y - mean) * rstd; h.z = (z.z - mean) * rstd; h.w = (z.w - mean) * rstd;
+        }
         float4 u = make_float4(h.x * gam.x + bet.x, h.y * gam.y + bet.y, h.z * gam.z + bet.z, h.w * gam.w + bet.w);
         if (HEAD && p.tanh_act) { u.x = tanhf(u.x); u.y = tanhf(u.y); u.z = tanhf(u.z); u.w = tanhf(u.w); }
         float4 k = HEAD ? drop_scale4(da, (uint64_t)(ro + c) >> 2) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -361,6 +377,7 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
         prefetch_row_l2(p.dy, rn * C, C, lane);
         prefetch_row_l2(p.dy2, rn * C, C, lane);
         prefetch_row_l2(p.dy3, rn * C, C, lane);
+        prefetch_row_l2(p.y, rn * C, C, lane);
       }
     }
     pf_first = pf;
@@ -385,7 +402,7 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
         }
         if (p.dx_f32) st4(p.dx_f32 + ro + c, dz);
         if (da_out) {
-          if (p.branch) {
+          if (p.branch || (!HEAD && p.y)) {
             const float sk = db.p > 0.f ? 1.0f / (1.0f - db.p) : 1.0f;
             const unsigned kb = keep_b >> (4 * i);
             dz.x *= (kb & 1u) ? sk : 0.f; dz.y *= (kb & 2u) ? sk : 0.f; dz.z *= (kb & 4u) ? sk : 0.f; dz.w *= (kb & 8u) ? sk : 0.f;
@@ -1612,7 +1629,10 @@ extern "C" int fs2_ln_fwd(const Fs2LnFwd* p, void* stream) {
 }
 
 extern "C" int fs2_ln_bwd(const Fs2LnBwd* p, void* stream) {
-  REQUIRE(p && p->x && p->gamma && p->beta && p->mean && p->rstd, "fs2_ln_bwd: null pointer");
+  REQUIRE(p && (p->x || p->y) && p->gamma && p->beta && (p->mean || p->y) && p->rstd, "fs2_ln_bwd: null pointer");
+  REQUIRE(p->y == nullptr || (p->head_w == nullptr && p->dhead_w == nullptr && p->dhead_b == nullptr && !p->tanh_act && !p->relu_x &&
+                              p->drop_a_p <= 0.f && p->lens == nullptr),
+          "fs2_ln_bwd: y (x_hat from the forward output) needs a plain LayerNorm");
   REQUIRE(p->C % 4 == 0 && p->C <= 128 * MAXV, "fs2_ln_bwd: C must be a multiple of 4 and <= 512");
   REQUIRE(p->dact_colsum == nullptr || (p->C <= 384 && p->dact != nullptr), "fs2_ln_bwd: dact_colsum needs dact and C <= 384");
   const long long rows = (long long)p->B * (p->T + 2 * FS2_PAD);

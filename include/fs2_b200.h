@@ -126,11 +126,35 @@ typedef struct {
   float* dact_colsum;   /* optional [C], accumulated (+=): column sums of `dact` over all rows = the bias gradient of the
                            GEMM that produced `branch` (saves the separate fs2_colsum pass over dact); C <= 384 only */
   const float* dy3;     /* optional second half of dy2 (same layout, same fold): the other partial result of a split-K dgrad */
+  const float* y;       /* optional: the forward's fp32 OUTPUT (padded rows).  When set, the normalised value is taken from it,
+                           x_hat = (y - beta) / gamma (0 where gamma == 0), and x / branch / mean are not read -- for forwards
+                           that never materialise the branch (fs2_gemm_ln_tc).  Plain LayerNorm only: no tanh, dropout-after,
+                           row mask, post_add or head.  drop_b_p still applies to `dact` (the branch gradient). */
 } Fs2LnBwd;
 int fs2_ln_bwd(const Fs2LnBwd* p, void* stream);
 /* measurement hook: the LayerNorm kernels ask L2 for a warp's next row while the current one is reduced; `prefetch` =
  * distance in rows of a warp, 0 (off) .. 4, default 1 (measured best on B200; FS2_LN_PREFETCH sets it at load time) */
 int fs2_ln_tune(int prefetch);
+
+/* GEMM + bias + branch dropout + residual + LayerNorm in ONE tcgen05 kernel (gemm_ln.cu): the two places per FFT block
+ * where speechbrain's TransformerEncoderLayer runs  LN(x + dropout(Linear/Conv1d-k1(a)))  -- out-projection -> norm1 and
+ * FFN conv 2 -> norm2 (reference model.py:344-347, 425-428 through speechbrain's post-norm encoder layer).  Equivalent to
+ * fs2_gemm_tc (mode 0, taps 1, fp32 C = branch) followed by fs2_ln_fwd (x, branch, drop_b, out_f32, out_act bf16, halo,
+ * mean, rstd), but the fp32 branch never reaches HBM: a 128 x 384 tile holds full rows in tensor memory, the epilogue warps
+ * add bias / dropout / residual, take the row statistics in two more passes over tensor memory and store fp32 + bf16.
+ *   A (M, K) bf16, M = B*(T+8) padded rows;  W (384, K) bf16 K-major;  x, out_f32 fp32 (M, 384);  out_act bf16 (M, 384).
+ * N is fixed to 384 (the model width).  Rows outside the rectangle follow the producer rule of the row-wise kernels. */
+typedef struct {
+  int B, T;                 /* row space: M = B * (T + 8) */
+  int K; long long lda, ldw;
+  const void* A; const void* W; const float* bias;
+  const float* x;           /* residual */
+  float drop_p; unsigned long long drop_seed; const unsigned long long* seed_dev;
+  const float* gamma; const float* beta; float eps;
+  float* out_f32; void* out_act; int halo;
+  float* mean; float* rstd; /* optional [M] */
+} Fs2GemmLn;
+int fs2_gemm_ln_tc(const Fs2GemmLn* g, void* stream);
 
 /* softmax over keys with the reference's attn_mask quirk (model.py:338-343, 414-419):
  * keys valid for (b,h) are [0, min(len[b], len[(b*H+h) % B])).  S (B*H, T, ldk) fp32 -> P (and Pd = dropout(P)

@@ -60,13 +60,13 @@ def test_signature_table_matches_header(built):
 def test_struct_sizes_match_c(built, tmp_path):
     """ctypes mirrors of the descriptor structs have the C compiler's size."""
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "fs2_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(Fs2Gemm), '
-                   'sizeof(Fs2LnFwd), sizeof(Fs2LnBwd), sizeof(Fs2PackItem));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "fs2_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(Fs2Gemm), '
+                   'sizeof(Fs2LnFwd), sizeof(Fs2LnBwd), sizeof(Fs2PackItem), sizeof(Fs2GemmLn));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ctypes.sizeof(built.Fs2Gemm), ctypes.sizeof(built.Fs2LnFwd), ctypes.sizeof(built.Fs2LnBwd),
-                     ctypes.sizeof(built.Fs2PackItem)]
+                     ctypes.sizeof(built.Fs2PackItem), ctypes.sizeof(built.Fs2GemmLn)]
 
 
 def test_no_cpu_fallback(built):
