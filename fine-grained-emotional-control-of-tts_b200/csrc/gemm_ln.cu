@@ -3,9 +3,12 @@
 // The post-norm FFT block of the reference (speechbrain TransformerEncoderLayer, reached from model.py:344-347 and
 // 425-428) runs  y = LN(x + dropout(a . W^T + b))  twice per layer: out-projection -> norm1 and FFN conv 2 -> norm2.  As
 // two launches the fp32 branch (a . W^T + b) makes a round trip through HBM: 8 of the 18 bytes per element the pair moves.
-// Here one CTA owns a 128 x 384 tile, i.e. 128 COMPLETE LayerNorm rows, in tensor memory (384 of the 512 columns, fp32):
-//   warp 0   : TMA producer   (A 128 x 64 and W 384 x 64 bf16 boxes, 128B swizzle, 3-stage ring of 64 KB)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (two N = 192 MMAs per K = 16 step)
+// Here a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) owns a 256 x 384 tile; each CTA holds 128 COMPLETE LayerNorm rows
+// in its tensor memory (384 of the 512 columns, fp32):
+//   warp 0   : TMA producer   (own A 128 x 64 box + its HALF of W per k-block: 40 KB per CTA instead of 64 -- the
+//              single-CTA form was bound by the L2 -> SM traffic of re-reading W, 1.9 k cycles per k-block for 0.77 k of MMA)
+//   warp 1   : TMEM allocator; in the leader CTA the single-thread tcgen05.mma issuer (two M = 256, N = 192 MMAs per
+//              K = 16 step, completion multicast to both CTAs)
 //   warps 2-9: epilogue.  Each warp owns 16 rows (its TMEM lane quadrant, upper or lower half) and reads them in the
 //              16x256b register layout: a quad of lanes holds 32 contiguous bytes of a row, so residual loads and output
 //              stores are full-sector accesses straight from / to registers, and row statistics are quad shuffles.
@@ -29,21 +32,36 @@ constexpr int BK = 64;
 constexpr int LN_N = 384;
 constexpr int BNS = 192;                      // UMMA N (<= 256): two MMAs cover the row
 constexpr int STAGES = 3;
+constexpr int NCTA = 2;                       // CTA pair
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NTHREADS = 32 * (2 + NUM_EPI_WARPS);
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-constexpr int BSUB_BYTES = BNS * BK * 2;      // 24 KB
-constexpr int STAGE_BYTES = A_BYTES + 2 * BSUB_BYTES;     // 64 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int BSUB_ROWS = BNS / NCTA;         // W rows (output columns) of a 192-wide sub-tile this CTA stages
+constexpr int BSUB_BYTES = BSUB_ROWS * BK * 2;            // 12 KB
+constexpr int STAGE_BYTES = A_BYTES + 2 * BSUB_BYTES;     // 40 KB per CTA
+// per epilogue warp: a staging tile the bulk-tensor engine stores from -- one step (64 columns) of the warp's 16 rows as
+// two fp32 boxes (16 x 128 B each) and one bf16 box (16 x 128 B), 128B-swizzled
+constexpr int OUT_BOX_BYTES = 16 * 128;
+constexpr int OUT_STAGE_BYTES = 3 * OUT_BOX_BYTES;                 // 6 KB, double-buffered
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * 2 * OUT_STAGE_BYTES + 1024 + 256;
 constexpr int NCHUNK = LN_N / 32;             // 32-column chunks per row
 constexpr int CH = 2;                         // chunks per epilogue step
 static_assert(NCHUNK % CH == 0, "chunks per step");
+static_assert(CH == 2, "the staging tile holds one bf16 box of 64 columns and two fp32 boxes of 32");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+// cycle probes of CTA 0 (tools/gemm_ln_bench.py GEMM_LN_DBG=1) are compiled in with `make probe` only
+#ifdef FS2_TC_PROBE
+constexpr bool kProbe = true;
+#else
+constexpr bool kProbe = false;
+#endif
 
 struct LnGemmParams {
   Fs2GemmLn g;
   int M, m_tiles, kb;
   int* err;
+  long long* dbg;
 };
 
 // what the epilogue needs to know about one output row
@@ -78,14 +96,78 @@ __device__ __forceinline__ RowInfo row_info(int r, int M, int T, int halo) {
   return ri;
 }
 
+// ---- CTA-pair plumbing (same protocol as tcx_gemm_kernel in gemm_tc.cu)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_pair(uint32_t dst, const CUtensorMap* tm, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// MMA-completion arrive on the same barrier offset in both CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+// bulk-tensor store shared -> global of one box (coordinates: column in the map's element type, row)
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %4}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(0)
+               : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+template <bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmF,
+                                                               const __grid_constant__ CUtensorMap tmH,
                                                                const LnGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint8_t* out_stage = smem + STAGES * STAGE_BYTES;                       // 1024-aligned, 6 KB per epilogue warp
+  uint64_t* full_bar = (uint64_t*)(out_stage + NUM_EPI_WARPS * 2 * OUT_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;      // accumulator ready
   uint64_t* tempty_bar = tfull_bar + 1;          // accumulator drained
@@ -94,30 +176,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Fs2GemmLn& g = p.g;
   int* err = p.err;
+  const uint32_t rank = cluster_ctarank();
+  const int unit = (int)cluster_id_x(), nunits = (int)cluster_count_x();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), 1);      // the leader's producer arrives once (+ the pair's transaction bytes)
+      mbar_init(smem_u32(&empty_bar[s]), 1);     // one MMA commit (multicast to both CTAs)
     }
     mbar_init(smem_u32(tfull_bar), 1);
-    mbar_init(smem_u32(tempty_bar), NUM_EPI_WARPS);
+    mbar_init(smem_u32(tempty_bar), NUM_EPI_WARPS * NCTA);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_wait();
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
+    // ---------------------------------------------------------------- TMA producer (both CTAs of the pair)
     if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -125,25 +209,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       uint32_t s = 0, ph = 0;
       bool ok = true;
-      for (int t = blockIdx.x; t < p.m_tiles && ok; t += gridDim.x) {
-        const int m0 = t * BM;
+      for (int t = unit; t < p.m_tiles && ok; t += nunits) {
+        const int m0 = t * (BM * NCTA) + (int)rank * BM;
         for (int kb = 0; kb < p.kb; ++kb) {
           if (!mbar_wait(empty0 + 8 * s, ph ^ 1, err)) { ok = false; break; }
-          const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t fb_local = full0 + 8 * s;
+          const uint32_t fb = mapa_rank(fb_local, 0);               // bytes of both CTAs are credited to the leader
+          if (rank == 0) mbar_expect_tx(fb_local, STAGE_BYTES * NCTA);
           const uint32_t sa = smem0 + s * STAGE_BYTES;
-          tma_load_4d(sa, &tmA, fb, kb * BK, m0, 0, 0);
-          tma_load_4d(sa + A_BYTES, &tmB, fb, kb * BK, 0, 0, 0);
-          tma_load_4d(sa + A_BYTES + BSUB_BYTES, &tmB, fb, kb * BK, BNS, 0, 0);
+          tma_load_pair(sa, &tmA, fb, kb * BK, m0);
+          tma_load_pair(sa + A_BYTES, &tmB, fb, kb * BK, (int)rank * BSUB_ROWS);
+          tma_load_pair(sa + A_BYTES + BSUB_BYTES, &tmB, fb, kb * BK, BNS + (int)rank * BSUB_ROWS);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (elect_one()) {
-      // instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3, M >> 4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNS >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // ---------------------------------------------------------------- MMA issuer (leader CTA, one thread)
+    if (rank == 0 && elect_one()) {
+      // instruction descriptor: D = f32, A = B = bf16, both K-major, N >> 3, M >> 4 (M = 256 across the pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNS >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
       const uint32_t smem0 = smem_u32(smem);
       const uint64_t adesc0 = smem_desc(smem0, 16, 1024);
       const uint64_t bdesc0 = smem_desc(smem0 + A_BYTES, 16, 1024);
@@ -153,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       uint32_t s = 0, ph = 0, tc = 0;
       bool ok = true;
-      for (int t = blockIdx.x; t < p.m_tiles && ok; t += gridDim.x, ++tc) {
+      for (int t = unit; t < p.m_tiles && ok; t += nunits, ++tc) {
         if (!mbar_wait(smem_u32(tempty_bar), (tc & 1) ^ 1, err)) { ok = false; break; }
         tc_fence_after();
         uint32_t acc = 0;
@@ -163,14 +248,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
           const uint64_t ad = adesc0 + (uint64_t)s * STAGE_STEP, bd = bdesc0 + (uint64_t)s * STAGE_STEP;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(tmem_base, ad + k * KSTEP, bd + k * KSTEP, idesc, acc);
-            umma_bf16(tmem_base + BNS, ad + k * KSTEP, bd + SUB_STEP + k * KSTEP, idesc, acc);
+            umma_bf16_pair(tmem_base, ad + k * KSTEP, bd + k * KSTEP, idesc, acc);
+            umma_bf16_pair(tmem_base + BNS, ad + k * KSTEP, bd + SUB_STEP + k * KSTEP, idesc, acc);
             acc = 1;
           }
-          umma_commit(empty0 + 8 * s);
+          umma_commit_pair(empty0 + 8 * s);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (ok) umma_commit(smem_u32(tfull_bar));
+        if (ok) umma_commit_pair(smem_u32(tfull_bar));
       }
     }
   } else {
@@ -184,14 +269,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
     // branch dropout: the mask of fs2_ln_fwd / fs2_ln_bwd (common.cuh:drop_scale4) -- one 64-bit mix per group of four
     // consecutive elements.  A lane holds two consecutive columns of rows tr and tr + 8; the even lane of a pair mixes the
     // group of row tr, the odd lane the group of row tr + 8, and one shuffle hands each the half it lacks.
-    const bool drop = g.drop_p > 0.f;
     const uint64_t dseed = g.drop_seed ^ (g.seed_dev ? mix64(*g.seed_dev) : 0ull);
     const uint32_t dthr = (uint32_t)(g.drop_p * 65536.0f);
-    const float dks = drop ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    const float dks = DROP ? 1.0f / (1.0f - g.drop_p) : 1.0f;
     uint32_t tc = 0;
     bool ok = true;
-    for (int t = blockIdx.x; t < p.m_tiles && ok; t += gridDim.x, ++tc) {
-      const int row0 = t * BM + q * 32 + hf * 16;
+    const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 5 && lane == 0;
+    long long pt[6] = {0, 0, 0, 0, 0, 0};
+    const uint32_t tempty_leader = mapa_rank(smem_u32(tempty_bar), 0);
+    for (int t = unit; t < p.m_tiles && ok; t += nunits, ++tc) {
+      if (prof) pt[0] = clock64();
+      const int row0 = t * (BM * NCTA) + (int)rank * BM + q * 32 + hf * 16;
       const RowInfo ra = row_info(row0 + tr, p.M, g.T, g.halo), rb = row_info(row0 + tr + 8, p.M, g.T, g.halo);
       // residual rows of this warp (16 x 1536 B, contiguous): into L2 while the tile's MMAs run
       {
@@ -204,15 +292,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
       }
       const float* xa = g.x + ra.off + 2 * tq;
       const float* xb_ = g.x + rb.off + 2 * tq;
-      // CH chunks (32 columns each) per step: CH tensor-memory loads in flight before one wait, residual loads one step ahead
+      // CH chunks (32 columns each) per step.  Everything a step needs from memory (residual of the NEXT step, bias or
+      // gamma / beta of this one) and the step's dropout words are requested / computed as one unrolled batch BEFORE the
+      // wait on the tensor-memory load: with two epilogue warps per scheduler there is no other latency hiding, and a
+      // load-use pair or a 64-bit mix per 8-column group in program order made a step ~4 k cycles instead of ~1 k.
       float2 xc[8 * CH], xn[8 * CH];
 #pragma unroll
       for (int i = 0; i < 4 * CH; ++i) {
         xc[2 * i] = ra.ok ? ldg2(xa + 8 * i) : make_float2(0.f, 0.f);
         xc[2 * i + 1] = rb.ok ? ldg2(xb_ + 8 * i) : make_float2(0.f, 0.f);
       }
+      if (prof) pt[1] = clock64();
       if (!mbar_wait(smem_u32(tfull_bar), tc & 1, err)) { ok = false; break; }
       tc_fence_after();
+      if (prof) pt[2] = clock64();
       // ---- pass 1: z = x + keep * (acc + bias) -> tensor memory; row sums
       float sa = 0.f, sb = 0.f;
       const uint64_t ga0 = (uint64_t)((tq & 1) ? rb.r : ra.r) * (LN_N / 4) + (uint64_t)(tq >> 1);
@@ -228,30 +321,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
             xn[2 * i + 1] = rb.ok ? ldg2(xb_ + (c + CH) * 32 + 8 * i) : make_float2(0.f, 0.f);
           }
         }
+        float2 b2[4 * CH];
+#pragma unroll
+        for (int i = 0; i < 4 * CH; ++i) b2[i] = ldg2(g.bias + c * 32 + 8 * i + 2 * tq);
+        const bool pp = prof && tc == 0 && c == 4;
+        if (pp) p.dbg[8] = clock64();
+        uint32_t bits_a[4 * CH], bits_b[4 * CH];
+        if (DROP) {
+#pragma unroll
+          for (int i = 0; i < 4 * CH; ++i) {
+            const uint64_t grp = ga0 + (uint64_t)(c * 8 + 2 * i);
+            const uint64_t rnd = mix64(dseed ^ (grp * 0xD6E8FEB86659FD93ull));
+            const uint32_t mine_lo = (uint32_t)rnd, mine_hi = (uint32_t)(rnd >> 32);
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, (tq & 1) ? mine_lo : mine_hi, 1);
+            bits_a[i] = (tq & 1) ? got : mine_lo;       // row tr:     the even lane owns the group's mix
+            bits_b[i] = (tq & 1) ? mine_hi : got;       // row tr + 8: the odd lane owns it
+          }
+        }
+        if (pp) p.dbg[9] = clock64();
         tmem_wait_ld();
+        if (pp) p.dbg[10] = clock64();
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
 #pragma unroll
           for (int n = 0; n < 4; ++n) {
-            const float2 b2 = ldg2(g.bias + (c + j) * 32 + 8 * n + 2 * tq);
+            const int i = 4 * j + n;
             float ka0 = 1.f, ka1 = 1.f, kb0 = 1.f, kb1 = 1.f;
-            if (drop) {
-              const uint64_t grp = ga0 + (uint64_t)((c + j) * 8 + 2 * n);
-              const uint64_t rnd = mix64(dseed ^ (grp * 0xD6E8FEB86659FD93ull));
-              const uint32_t mine_lo = (uint32_t)rnd, mine_hi = (uint32_t)(rnd >> 32);
-              const uint32_t got = __shfl_xor_sync(0xffffffffu, (tq & 1) ? mine_lo : mine_hi, 1);
-              const uint32_t bits_a = (tq & 1) ? got : mine_lo;       // row tr:     the even lane owns the group's mix
-              const uint32_t bits_b = (tq & 1) ? mine_hi : got;       // row tr + 8: the odd lane owns it
-              ka0 = ((bits_a & 0xFFFFu) >= dthr) ? dks : 0.f;
-              ka1 = ((bits_a >> 16) >= dthr) ? dks : 0.f;
-              kb0 = ((bits_b & 0xFFFFu) >= dthr) ? dks : 0.f;
-              kb1 = ((bits_b >> 16) >= dthr) ? dks : 0.f;
+            if (DROP) {
+              ka0 = ((bits_a[i] & 0xFFFFu) >= dthr) ? dks : 0.f;
+              ka1 = ((bits_a[i] >> 16) >= dthr) ? dks : 0.f;
+              kb0 = ((bits_b[i] & 0xFFFFu) >= dthr) ? dks : 0.f;
+              kb1 = ((bits_b[i] >> 16) >= dthr) ? dks : 0.f;
             }
-            const float2 xa2 = xc[2 * (4 * j + n)], xb2 = xc[2 * (4 * j + n) + 1];
-            const float za0 = xa2.x + (__uint_as_float(r[j][4 * n]) + b2.x) * ka0;
-            const float za1 = xa2.y + (__uint_as_float(r[j][4 * n + 1]) + b2.y) * ka1;
-            const float zb0 = xb2.x + (__uint_as_float(r[j][4 * n + 2]) + b2.x) * kb0;
-            const float zb1 = xb2.y + (__uint_as_float(r[j][4 * n + 3]) + b2.y) * kb1;
+            const float za0 = xc[2 * i].x + (__uint_as_float(r[j][4 * n]) + b2[i].x) * ka0;
+            const float za1 = xc[2 * i].y + (__uint_as_float(r[j][4 * n + 1]) + b2[i].y) * ka1;
+            const float zb0 = xc[2 * i + 1].x + (__uint_as_float(r[j][4 * n + 2]) + b2[i].x) * kb0;
+            const float zb1 = xc[2 * i + 1].y + (__uint_as_float(r[j][4 * n + 3]) + b2[i].y) * kb1;
             sa += za0 + za1;
             sb += zb0 + zb1;
             r[j][4 * n] = __float_as_uint(za0);
@@ -261,10 +366,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
           }
           tmem_st_16x256b_x4(tw + (uint32_t)((c + j) * 32), r[j]);
         }
+        if (pp) p.dbg[11] = clock64();
 #pragma unroll
         for (int i = 0; i < 8 * CH; ++i) xc[i] = xn[i];
+        if (pp) { p.dbg[12] = (long long)__float_as_uint(xc[0].x + xc[15].y); p.dbg[13] = clock64(); }
       }
       tmem_wait_st();
+      if (prof) pt[3] = clock64();
       sa += __shfl_xor_sync(0xffffffffu, sa, 1);
       sa += __shfl_xor_sync(0xffffffffu, sa, 2);
       sb += __shfl_xor_sync(0xffffffffu, sb, 1);
@@ -304,116 +412,240 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
           if (g.rstd) g.rstd[rb.r] = rstd_b;
         }
       }
+      if (prof) pt[4] = clock64();
       // ---- pass 3: normalise, scale / shift, store
+      // A warp whose 16 rows are all rectangle rows without halo mirrors (all but ~5 % at mel-frame lengths) writes each
+      // 64-column step into its swizzled staging tile and lets the bulk-tensor engine store the three boxes: the
+      // load/store unit sees two shared-memory wavefronts per instruction where the same registers stored to global
+      // memory cost eight (one per row: 32 or 16 bytes of a 128-byte line each) -- that was the epilogue's bound.
+      const bool fast = __all_sync(0xffffffffu, ra.ok && rb.ok && (ra.m1 | ra.m2 | rb.m1 | rb.m2) == 0);
+      if (fast) {
+        const uint32_t stw = smem_u32(out_stage) + (uint32_t)(warp - 2) * (2 * OUT_STAGE_BYTES);
+        // 128B swizzle: 16-byte chunk k of row r sits at r * 128 + ((k ^ (r & 7)) << 4); rows tr and tr + 8 share r & 7
+        const uint32_t tsw = (uint32_t)tr;
+        const int row0w = row0;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; c += CH) {
+          uint32_t r[CH][16];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) tmem_ld_16x256b_x4(tw + (uint32_t)((c + j) * 32), r[j]);
+          float2 g2[4 * CH], be2[4 * CH];
+#pragma unroll
+          for (int i = 0; i < 4 * CH; ++i) {
+            g2[i] = ldg2(g.gamma + c * 32 + 8 * i + 2 * tq);
+            be2[i] = ldg2(g.beta + c * 32 + 8 * i + 2 * tq);
+          }
+          const bool pp = prof && tc == 0 && c == 4;
+          if (pp) p.dbg[16] = clock64();
+          tmem_wait_ld();
+          if (pp) p.dbg[17] = clock64();
+          if (c + CH >= NCHUNK) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader);
+          }
+          // two staging tiles in turn: the engine must have read the step before the previous one (bulk groups belong to lane 0)
+          const uint32_t st0 = stw + (uint32_t)((c / CH) & 1) * OUT_STAGE_BYTES;
+          const uint32_t rowa = st0 + (uint32_t)tr * 128u;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          if (pp) p.dbg[18] = clock64();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              const int i = 4 * j + n;
+              const float ya0 = (__uint_as_float(r[j][4 * n]) - mean_a) * rstd_a * g2[i].x + be2[i].x;
+              const float ya1 = (__uint_as_float(r[j][4 * n + 1]) - mean_a) * rstd_a * g2[i].y + be2[i].y;
+              const float yb0 = (__uint_as_float(r[j][4 * n + 2]) - mean_b) * rstd_b * g2[i].x + be2[i].x;
+              const float yb1 = (__uint_as_float(r[j][4 * n + 3]) - mean_b) * rstd_b * g2[i].y + be2[i].y;
+              const __nv_bfloat162 pa = __floats2bfloat162_rn(ya0, ya1), pb = __floats2bfloat162_rn(yb0, yb1);
+              // fp32 box j: byte 32 n + 8 tq of the row -> chunk 2n + tq/2
+              const uint32_t fo = (uint32_t)j * OUT_BOX_BYTES + ((((uint32_t)(2 * n) + (uint32_t)(tq >> 1)) ^ tsw) << 4) + 8u * (uint32_t)(tq & 1);
+              sts64(rowa + fo, ya0, ya1);
+              sts64(rowa + fo + 8u * 128u, yb0, yb1);
+              // bf16 box: byte 64 j + 16 n + 4 tq of the row -> chunk 4j + n
+              const uint32_t ho = 2u * OUT_BOX_BYTES + (((uint32_t)(4 * j + n) ^ tsw) << 4) + 4u * (uint32_t)tq;
+              sts32(rowa + ho, *reinterpret_cast<const uint32_t*>(&pa));
+              sts32(rowa + ho + 8u * 128u, *reinterpret_cast<const uint32_t*>(&pb));
+            }
+          }
+          if (pp) p.dbg[19] = clock64();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (pp) p.dbg[20] = clock64();
+          if (lane == 0) {
+            tma_store_box(&tmF, st0, c * 64, row0w);                       // fp32 tensor addressed as 768 16-bit columns
+            tma_store_box(&tmF, st0 + OUT_BOX_BYTES, (c + 1) * 64, row0w);
+            tma_store_box(&tmH, st0 + 2 * OUT_BOX_BYTES, c * 32, row0w);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (pp) p.dbg[21] = clock64();
+        }
+      } else {
+      // rows outside the rectangle: zeros or nothing; reflect-halo mirror rows: plain stores from the registers
       const bool wa = ra.ok || ra.zero, wb = rb.ok || rb.zero;
       const bool mirrors = __any_sync(0xffffffffu, (ra.m1 | ra.m2 | rb.m1 | rb.m2) != 0);
-      float* fa = g.out_f32 ? g.out_f32 + ra.off + 2 * tq : nullptr;
-      float* fb = g.out_f32 ? g.out_f32 + rb.off + 2 * tq : nullptr;
-      bf16* ha = oa ? oa + ra.off + 2 * tq : nullptr;
-      bf16* hb = oa ? oa + rb.off + 2 * tq : nullptr;
+      float* fa = g.out_f32 + ra.off + 2 * tq;
+      float* fb = g.out_f32 + rb.off + 2 * tq;
+      bf16* ha = oa + ra.off + 2 * tq;
+      bf16* hb = oa + rb.off + 2 * tq;
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; c += CH) {
         uint32_t r[CH][16];
 #pragma unroll
         for (int j = 0; j < CH; ++j) tmem_ld_16x256b_x4(tw + (uint32_t)((c + j) * 32), r[j]);
+        float2 g2[4 * CH], be2[4 * CH];
+#pragma unroll
+        for (int i = 0; i < 4 * CH; ++i) {
+          g2[i] = ldg2(g.gamma + c * 32 + 8 * i + 2 * tq);
+          be2[i] = ldg2(g.beta + c * 32 + 8 * i + 2 * tq);
+        }
         tmem_wait_ld();
         if (c + CH >= NCHUNK) {
           // last tensor-memory read of this warp: hand the accumulator back to the MMA thread
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(tempty_bar));
+          if (lane == 0) mbar_arrive_cluster(tempty_leader);
         }
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
 #pragma unroll
           for (int n = 0; n < 4; ++n) {
+            const int i = 4 * j + n;
             const int col = (c + j) * 32 + 8 * n;
-            const float2 g2 = ldg2(g.gamma + col + 2 * tq), be2 = ldg2(g.beta + col + 2 * tq);
             float2 ya, yb;
-            ya.x = (__uint_as_float(r[j][4 * n]) - mean_a) * rstd_a * g2.x + be2.x;
-            ya.y = (__uint_as_float(r[j][4 * n + 1]) - mean_a) * rstd_a * g2.y + be2.y;
-            yb.x = (__uint_as_float(r[j][4 * n + 2]) - mean_b) * rstd_b * g2.x + be2.x;
-            yb.y = (__uint_as_float(r[j][4 * n + 3]) - mean_b) * rstd_b * g2.y + be2.y;
-            if (!ra.ok) ya = make_float2(0.f, 0.f);
-            if (!rb.ok) yb = make_float2(0.f, 0.f);
+            ya.x = (__uint_as_float(r[j][4 * n]) - mean_a) * rstd_a * g2[i].x + be2[i].x;
+            ya.y = (__uint_as_float(r[j][4 * n + 1]) - mean_a) * rstd_a * g2[i].y + be2[i].y;
+            yb.x = (__uint_as_float(r[j][4 * n + 2]) - mean_b) * rstd_b * g2[i].x + be2[i].x;
+            yb.y = (__uint_as_float(r[j][4 * n + 3]) - mean_b) * rstd_b * g2[i].y + be2[i].y;
+            ya.x = ra.ok ? ya.x : 0.f;           // halo rows no mirror reaches get zeros
+            ya.y = ra.ok ? ya.y : 0.f;
+            yb.x = rb.ok ? yb.x : 0.f;
+            yb.y = rb.ok ? yb.y : 0.f;
             const __nv_bfloat162 pa = __floats2bfloat162_rn(ya.x, ya.y), pb = __floats2bfloat162_rn(yb.x, yb.y);
             if (wa) {
-              if (fa) *reinterpret_cast<float2*>(fa + col) = ya;
-              if (ha) *reinterpret_cast<__nv_bfloat162*>(ha + col) = pa;
+              *reinterpret_cast<float2*>(fa + col) = ya;
+              *reinterpret_cast<__nv_bfloat162*>(ha + col) = pa;
             }
             if (wb) {
-              if (fb) *reinterpret_cast<float2*>(fb + col) = yb;
-              if (hb) *reinterpret_cast<__nv_bfloat162*>(hb + col) = pb;
+              *reinterpret_cast<float2*>(fb + col) = yb;
+              *reinterpret_cast<__nv_bfloat162*>(hb + col) = pb;
             }
             if (mirrors) {                       // warp-uniform: only the first / last rows of an item (halo > 0)
               if (ra.m1) {
-                if (fa) *reinterpret_cast<float2*>(fa + ra.m1 + col) = ya;
-                if (ha) *reinterpret_cast<__nv_bfloat162*>(ha + ra.m1 + col) = pa;
+                *reinterpret_cast<float2*>(fa + ra.m1 + col) = ya;
+                *reinterpret_cast<__nv_bfloat162*>(ha + ra.m1 + col) = pa;
               }
               if (ra.m2) {
-                if (fa) *reinterpret_cast<float2*>(fa + ra.m2 + col) = ya;
-                if (ha) *reinterpret_cast<__nv_bfloat162*>(ha + ra.m2 + col) = pa;
+                *reinterpret_cast<float2*>(fa + ra.m2 + col) = ya;
+                *reinterpret_cast<__nv_bfloat162*>(ha + ra.m2 + col) = pa;
               }
               if (rb.m1) {
-                if (fb) *reinterpret_cast<float2*>(fb + rb.m1 + col) = yb;
-                if (hb) *reinterpret_cast<__nv_bfloat162*>(hb + rb.m1 + col) = pb;
+                *reinterpret_cast<float2*>(fb + rb.m1 + col) = yb;
+                *reinterpret_cast<__nv_bfloat162*>(hb + rb.m1 + col) = pb;
               }
               if (rb.m2) {
-                if (fb) *reinterpret_cast<float2*>(fb + rb.m2 + col) = yb;
-                if (hb) *reinterpret_cast<__nv_bfloat162*>(hb + rb.m2 + col) = pb;
+                *reinterpret_cast<float2*>(fb + rb.m2 + col) = yb;
+                *reinterpret_cast<__nv_bfloat162*>(hb + rb.m2 + col) = pb;
               }
             }
           }
         }
       }
+      }
+      if (prof && tc == 0) {
+        pt[5] = clock64();
+        p.dbg[0] = pt[1] - pt[0];      // row setup, L2 prefetch, first residual loads issued
+        p.dbg[1] = pt[2] - pt[1];      // wait for the tile's MMAs
+        p.dbg[2] = pt[3] - pt[2];      // pass 1
+        p.dbg[3] = pt[4] - pt[3];      // pass 2
+        p.dbg[4] = pt[5] - pt[4];      // pass 3
+      }
     }
+    // the staging tile must outlive the engine's reads; the stores themselves complete before the grid does
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
   }
 
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();          // nobody leaves while the peer can still signal its barriers
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
-int g_ln_gemm_sms = 0;
+long long* g_ln_gemm_dbg = nullptr;
 
 }  // namespace
+
+extern "C" int fs2_gemm_ln_set_debug(long long* dev_buf) {
+  g_ln_gemm_dbg = dev_buf;
+  return FS2_OK;
+}
 
 #define REQUIRE(cond, msg) do { if (!(cond)) { fs2_set_error(msg); return FS2_ERR_ARG; } } while (0)
 
 extern "C" int fs2_gemm_ln_tc(const Fs2GemmLn* gp, void* stream) {
   REQUIRE(gp && gp->A && gp->W && gp->bias && gp->x && gp->gamma && gp->beta, "fs2_gemm_ln_tc: null pointer");
-  REQUIRE(gp->out_f32 || gp->out_act, "fs2_gemm_ln_tc: no output");
+  REQUIRE(gp->out_f32 && gp->out_act, "fs2_gemm_ln_tc: both outputs (fp32 and bf16) are required");
   const Fs2GemmLn& g = *gp;
   REQUIRE(g.B > 0 && g.T > 0 && g.K > 0 && g.K % 8 == 0, "fs2_gemm_ln_tc: bad shape (K must be a multiple of 8)");
   REQUIRE(g.halo >= 0 && g.halo <= FS2_PAD && (g.halo == 0 || g.T > g.halo), "fs2_gemm_ln_tc: halo too wide for T");
   REQUIRE(g.drop_p >= 0.f && g.drop_p < 1.f, "fs2_gemm_ln_tc: bad dropout probability");
-  REQUIRE((((uintptr_t)g.x | (uintptr_t)g.out_f32 | (uintptr_t)g.bias | (uintptr_t)g.gamma | (uintptr_t)g.beta) % 8) == 0 &&
-              ((uintptr_t)g.out_act % 4) == 0,
-          "fs2_gemm_ln_tc: fp32 operands must be 8-byte aligned");
+  REQUIRE((((uintptr_t)g.x | (uintptr_t)g.bias | (uintptr_t)g.gamma | (uintptr_t)g.beta) % 8) == 0 &&
+              (((uintptr_t)g.out_f32 | (uintptr_t)g.out_act) % 16) == 0,
+          "fs2_gemm_ln_tc: fp32 operands must be 8-byte aligned, outputs 16-byte aligned");
   const long long Ml = (long long)g.B * (g.T + 2 * FS2_PAD);
   REQUIRE(Ml * LN_N < (1LL << 40) && Ml < 0x7FFFFFFF, "fs2_gemm_ln_tc: too many rows");
   LnGemmParams p;
   memset(&p, 0, sizeof p);
   p.g = g;
   p.M = (int)Ml;
-  p.m_tiles = (p.M + BM - 1) / BM;
+  p.m_tiles = (p.M + BM * NCTA - 1) / (BM * NCTA);
   p.kb = (g.K + BK - 1) / BK;
+  p.dbg = g_ln_gemm_dbg;
   int rc = fs2_tc_error_ptr(&p.err);
   if (rc) return rc;
   CUtensorMap ta, tb;
   if ((rc = fs2_tc_make_map_2d(g.A, g.K, p.M, g.lda, BK, BM, &ta))) return rc;
-  if ((rc = fs2_tc_make_map_2d(g.W, g.K, LN_N, g.ldw, BK, BNS, &tb))) return rc;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_CHECK_RET(cudaFuncSetAttribute(gemm_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    int dev = 0;
+  if ((rc = fs2_tc_make_map_2d(g.W, g.K, LN_N, g.ldw, BK, BSUB_ROWS, &tb))) return rc;
+  // output maps for the epilogue's bulk-tensor stores: 16-row boxes of 128 bytes; the fp32 tensor is described as
+  // (M, 768) 16-bit elements (the engine moves bytes)
+  CUtensorMap tf, th;
+  if ((rc = fs2_tc_make_map_2d(g.out_f32, 2 * LN_N, p.M, 2 * LN_N, 64, 16, &tf))) return rc;
+  if ((rc = fs2_tc_make_map_2d(g.out_act, LN_N, p.M, LN_N, 64, 16, &th))) return rc;
+  auto kern = g.drop_p > 0.f ? gemm_ln_kernel<true> : gemm_ln_kernel<false>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.blockDim = dim3(NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = (cudaStream_t)stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_fs2_pdl ? 2 : 1;
+  static int units = 0;       // CTA pairs that can be resident at once
+  if (units == 0) {
+    CUDA_CHECK_RET(cudaFuncSetAttribute(gemm_ln_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CUDA_CHECK_RET(cudaFuncSetAttribute(gemm_ln_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int dev = 0, sms = 0, nc = 0;
     CUDA_CHECK_RET(cudaGetDevice(&dev));
-    CUDA_CHECK_RET(cudaDeviceGetAttribute(&g_ln_gemm_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
+    CUDA_CHECK_RET(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cfg.gridDim = dim3(sms / NCTA * NCTA, 1, 1);
+    CUDA_CHECK_RET(cudaOccupancyMaxActiveClusters(&nc, gemm_ln_kernel<true>, &cfg));
+    if (nc <= 0) { fs2_set_error("fs2_gemm_ln_tc: no resident CTA pair possible"); return FS2_ERR_CUDA; }
+    units = nc < sms / NCTA ? nc : sms / NCTA;
   }
-  const int grid = p.m_tiles < g_ln_gemm_sms ? p.m_tiles : g_ln_gemm_sms;
-  FS2_LAUNCH(gemm_ln_kernel, grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream, ta, tb, p);
+  const int nunits = p.m_tiles < units ? p.m_tiles : units;
+  cfg.gridDim = dim3(nunits * NCTA, 1, 1);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tf, th, p);
+  if (e != cudaSuccess) { fs2_set_error(cudaGetErrorString(e)); return FS2_ERR_CUDA; }
   return fs2_check_launch();
 }

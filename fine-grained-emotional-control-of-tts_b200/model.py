@@ -178,6 +178,9 @@ class FastSpeech2(nn.Module):
         self._seen = set()
         self._pre = None
         self.fused_attention = True   # bf16, head_dim 192: fs2_flash_attn_fwd / _bwd instead of GEMM + softmax + GEMM
+        # bf16, model width 384, k = 1 second FFN conv: out-projection -> norm1 and FFN conv 2 -> norm2 each run as ONE kernel
+        # (fs2_gemm_ln_tc: the fp32 branch never reaches HBM); the backward takes x_hat from the saved LayerNorm output
+        self.fused_ln = os.environ.get("FS2_FUSED_LN", "1") != "0"
         self.async_mel_lens = False   # opt-in: no host sync; Tm is taken from pitch.shape[1], mel_lens arrives in pinned memory
         # opt-in, inference with predicted durations in precision="bf16": frame counts are trunc(pace * expm1(pred)), which is
         # discontinuous -- a bf16 encoder moves ~1 % of the phonemes across an integer boundary (tests/
@@ -390,9 +393,29 @@ class FastSpeech2(nn.Module):
         p.seed_dev = self._ctr.data_ptr()
         L.call("fs2_ln_fwd", L.C.addressof(p))
 
+    def _fused_ln(self):
+        """fs2_gemm_ln_tc covers the reference geometry (width 384, second FFN conv k = 1) on the bf16 path."""
+        return self.fused_ln and self._bf16 and self.D == 384 and self.k1 == 1
+
+    def _gemm_ln(self, a, B, T, wname, bias, x, gamma, beta, eps, *, drop=(0.0, 0), out_f32, out_act, halo, mean, rstd):
+        """out = LN(x + dropout(a . W^T + bias)) in one kernel (speechbrain's post-norm residual step)."""
+        w = self.store.pw(wname)
+        wbuf, woff, wld = self.store.operand(wname, True)
+        q = L.Fs2GemmLn()
+        q.B, q.T, q.K, q.lda, q.ldw = B, T, w.cin, w.cin, wld
+        q.A, q.W = a.data_ptr(), wbuf.data_ptr() + 2 * woff
+        q.bias, q.x = bias.data_ptr(), x.data_ptr()
+        q.drop_p, q.drop_seed = drop
+        q.seed_dev = self._ctr.data_ptr()
+        q.gamma, q.beta, q.eps = gamma.data_ptr(), beta.data_ptr(), eps
+        q.out_f32, q.out_act, q.halo = out_f32.data_ptr(), out_act.data_ptr(), halo
+        q.mean, q.rstd = mean.data_ptr(), rstd.data_ptr()
+        L.call("fs2_gemm_ln_tc", L.C.addressof(q))
+
     def _ln_bwd(self, B, T, C, x, gamma, beta, eps, mean, rstd, *, dy=None, dy2=None, dy3=None, dy2_fold=0, dhead=None,
                 head_w=None, head_scale=1.0, branch=None, drop_b=(0.0, 0), tanh=0, drop_a=(0.0, 0), lens=None,
-                relu_x=0, dx_f32=None, dact=None, dgamma=None, dbeta=None, dhead_w=None, dhead_b=None, dact_colsum=None):
+                relu_x=0, dx_f32=None, dact=None, dgamma=None, dbeta=None, dhead_w=None, dhead_b=None, dact_colsum=None,
+                y=None):
         self._wait_side(dact)
         p = L.Fs2LnBwd()
         p.B, p.T, p.C = B, T, C
@@ -403,13 +426,14 @@ class FastSpeech2(nn.Module):
         p.dhead = dhead.data_ptr() if dhead is not None else None
         p.head_w = head_w.data_ptr() if head_w is not None else None
         p.head_scale = head_scale
-        p.x = x.data_ptr()
+        p.x = x.data_ptr() if x is not None else None
+        p.y = y.data_ptr() if y is not None else None
         p.branch = branch.data_ptr() if branch is not None else None
         p.drop_b_p, p.drop_b_seed = drop_b
         p.gamma, p.beta, p.eps, p.tanh_act = gamma.data_ptr(), beta.data_ptr(), eps, tanh
         p.drop_a_p, p.drop_a_seed = drop_a
         p.lens = lens.data_ptr() if lens is not None else None
-        p.mean, p.rstd = mean.data_ptr(), rstd.data_ptr()
+        p.mean, p.rstd = mean.data_ptr() if mean is not None else None, rstd.data_ptr()
         p.relu_x = relu_x
         p.dx_f32 = dx_f32.data_ptr() if dx_f32 is not None else None
         p.dact = dact.data_ptr() if dact is not None else None
@@ -454,6 +478,7 @@ class FastSpeech2(nn.Module):
         bf = self._bf16
         p = cfg["p"] if training else 0.0
         fused = self._fused_attn(H)
+        fuse_ln = self._fused_ln()
         S = None if fused else self._f32(B * H, T, ldk)          # scratch, shared by all layers of this stack
         saves = []
         h1, h2 = (self.k0 - 1) // 2, (self.k1 - 1) // 2
@@ -474,25 +499,40 @@ class FastSpeech2(nn.Module):
                 sv.Pd = self._act(B * H, T, ldk) if p > 0 else sv.P
             sv.O = self._act(rows, D)
             self._attn_gemms_fwd(sv.qkv, B, T, H, S, lens, sv.P, sv.Pd, sv.O, p, sv.seeds[0])
-            sv.proj = self._f32(rows, D)
-            self._conv(sv.O, B, T, f"{pre}.self_att.att.out_proj.weight", sv.proj, c_bf16=False,
-                       bias=self._P(f"{pre}.self_att.att.out_proj.bias"))
             sv.x1_f32, sv.x1_act = self._f32(rows, D), self._act(rows, D)
             sv.mean1, sv.rstd1 = self._f32(rows), self._f32(rows)
-            self._ln_fwd(B, T, D, x_f32, self._P(f"{pre}.norm1.norm.weight"), self._P(f"{pre}.norm1.norm.bias"), 1e-6,
-                         branch=sv.proj, drop_b=(p, sv.seeds[1]), out_f32=sv.x1_f32, out_act=sv.x1_act, halo=h1,
-                         mean=sv.mean1, rstd=sv.rstd1)
+            if fuse_ln:
+                # out-projection + bias + dropout + residual + norm1 in one kernel: the fp32 branch stays in tensor memory
+                sv.proj = None
+                self._gemm_ln(sv.O, B, T, f"{pre}.self_att.att.out_proj.weight", self._P(f"{pre}.self_att.att.out_proj.bias"),
+                              x_f32, self._P(f"{pre}.norm1.norm.weight"), self._P(f"{pre}.norm1.norm.bias"), 1e-6,
+                              drop=(p, sv.seeds[1]), out_f32=sv.x1_f32, out_act=sv.x1_act, halo=h1, mean=sv.mean1,
+                              rstd=sv.rstd1)
+            else:
+                sv.proj = self._f32(rows, D)
+                self._conv(sv.O, B, T, f"{pre}.self_att.att.out_proj.weight", sv.proj, c_bf16=False,
+                           bias=self._P(f"{pre}.self_att.att.out_proj.bias"))
+                self._ln_fwd(B, T, D, x_f32, self._P(f"{pre}.norm1.norm.weight"), self._P(f"{pre}.norm1.norm.bias"), 1e-6,
+                             branch=sv.proj, drop_b=(p, sv.seeds[1]), out_f32=sv.x1_f32, out_act=sv.x1_act, halo=h1,
+                             mean=sv.mean1, rstd=sv.rstd1)
             sv.Hh = self._act(rows, F)
             self._conv(sv.x1_act, B, T, f"{pre}.pos_ffn.0.conv.weight", sv.Hh, c_bf16=bf,
                        bias=self._P(f"{pre}.pos_ffn.0.conv.bias"), relu=1, halo=h2)
-            sv.Fo = self._f32(rows, D)
-            self._conv(sv.Hh, B, T, f"{pre}.pos_ffn.2.conv.weight", sv.Fo, c_bf16=False,
-                       bias=self._P(f"{pre}.pos_ffn.2.conv.bias"))
             y_f32, y_act = self._f32(rows, D), self._act(rows, D)
             sv.mean2, sv.rstd2 = self._f32(rows), self._f32(rows)
-            self._ln_fwd(B, T, D, sv.x1_f32, self._P(f"{pre}.norm2.norm.weight"), self._P(f"{pre}.norm2.norm.bias"), 1e-6,
-                         branch=sv.Fo, drop_b=(p, sv.seeds[2]), out_f32=y_f32, out_act=y_act, mean=sv.mean2,
-                         rstd=sv.rstd2)
+            if fuse_ln:
+                sv.Fo = None
+                self._gemm_ln(sv.Hh, B, T, f"{pre}.pos_ffn.2.conv.weight", self._P(f"{pre}.pos_ffn.2.conv.bias"),
+                              sv.x1_f32, self._P(f"{pre}.norm2.norm.weight"), self._P(f"{pre}.norm2.norm.bias"), 1e-6,
+                              drop=(p, sv.seeds[2]), out_f32=y_f32, out_act=y_act, halo=0, mean=sv.mean2, rstd=sv.rstd2)
+            else:
+                sv.Fo = self._f32(rows, D)
+                self._conv(sv.Hh, B, T, f"{pre}.pos_ffn.2.conv.weight", sv.Fo, c_bf16=False,
+                           bias=self._P(f"{pre}.pos_ffn.2.conv.bias"))
+                self._ln_fwd(B, T, D, sv.x1_f32, self._P(f"{pre}.norm2.norm.weight"), self._P(f"{pre}.norm2.norm.bias"), 1e-6,
+                             branch=sv.Fo, drop_b=(p, sv.seeds[2]), out_f32=y_f32, out_act=y_act, mean=sv.mean2,
+                             rstd=sv.rstd2)
+            sv.y_f32 = y_f32
             saves.append(sv)
             x_f32, x_act = y_f32, y_act
             self._tr(f"{name}.layer{l}", y_f32, B, T, D)
@@ -546,8 +586,11 @@ class FastSpeech2(nn.Module):
             pre = f"{name}.layers.{l}"
             sv = saves[l]
             # ---- LN2 + FFN
-            self._ln_bwd(B, T, D, sv.x1_f32, self._P(f"{pre}.norm2.norm.weight"), self._P(f"{pre}.norm2.norm.bias"), 1e-6,
-                         sv.mean2, sv.rstd2, dy=dy_a, dy2=dy_b, branch=sv.Fo, drop_b=(p, sv.seeds[2]),
+            # (a forward through fs2_gemm_ln_tc kept no branch: x_hat comes from the saved LayerNorm output instead)
+            self._ln_bwd(B, T, D, sv.x1_f32 if sv.Fo is not None else None, self._P(f"{pre}.norm2.norm.weight"),
+                         self._P(f"{pre}.norm2.norm.bias"), 1e-6,
+                         sv.mean2, sv.rstd2, dy=dy_a, dy2=dy_b, branch=sv.Fo, y=sv.y_f32 if sv.Fo is None else None,
+                         drop_b=(p, sv.seeds[2]),
                          dx_f32=dz2, dact=dF_act, dgamma=self._G(f"{pre}.norm2.norm.weight"),
                          dbeta=self._G(f"{pre}.norm2.norm.bias"),
                          dact_colsum=self._G(f"{pre}.pos_ffn.2.conv.bias") if fuse_bias else None)
@@ -562,9 +605,10 @@ class FastSpeech2(nn.Module):
                              f"{pre}.pos_ffn.0.conv.bias")
             self._conv_dgrad(dH_act, B, T, f"{pre}.pos_ffn.0.conv.weight", dX1c, split=ksplit)
             # ---- LN1 + attention
-            self._ln_bwd(B, T, D, sv.x_f32, self._P(f"{pre}.norm1.norm.weight"), self._P(f"{pre}.norm1.norm.bias"), 1e-6,
+            self._ln_bwd(B, T, D, sv.x_f32 if sv.proj is not None else None, self._P(f"{pre}.norm1.norm.weight"),
+                         self._P(f"{pre}.norm1.norm.bias"), 1e-6,
                          sv.mean1, sv.rstd1, dy=dz2, dy2=dX1c[0], dy3=dX1c[1] if ksplit > 1 else None, dy2_fold=h1,
-                         branch=sv.proj, drop_b=(p, sv.seeds[1]),
+                         branch=sv.proj, y=sv.x1_f32 if sv.proj is None else None, drop_b=(p, sv.seeds[1]),
                          dx_f32=dz1, dact=dProj_act, dgamma=self._G(f"{pre}.norm1.norm.weight"),
                          dbeta=self._G(f"{pre}.norm1.norm.bias"),
                          dact_colsum=self._G(f"{pre}.self_att.att.out_proj.bias") if fuse_bias else None)

@@ -155,6 +155,9 @@ typedef struct {
   float* mean; float* rstd; /* optional [M] */
 } Fs2GemmLn;
 int fs2_gemm_ln_tc(const Fs2GemmLn* g, void* stream);
+/* measurement hook: when non-NULL, CTA 0 of every fs2_gemm_ln_tc launch writes the cycle breakdown of its first tile's
+ * epilogue (library built with -DFS2_TC_PROBE only; tools/gemm_ln_bench.py GEMM_LN_DBG=1) */
+int fs2_gemm_ln_set_debug(long long* dev_buf);
 
 /* softmax over keys with the reference's attn_mask quirk (model.py:338-343, 414-419):
  * keys valid for (b,h) are [0, min(len[b], len[(b*H+h) % B])).  S (B*H, T, ldk) fp32 -> P (and Pd = dropout(P)
