@@ -43,7 +43,12 @@ constexpr int STAGE_BYTES = A_BYTES + 2 * BSUB_BYTES;     // 40 KB per CTA
 // two fp32 boxes (16 x 128 B each) and one bf16 box (16 x 128 B), 128B-swizzled
 constexpr int OUT_BOX_BYTES = 16 * 128;
 constexpr int OUT_STAGE_BYTES = 3 * OUT_BOX_BYTES;                 // 6 KB, double-buffered
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * 2 * OUT_STAGE_BYTES + 1024 + 256;
+// the same 12 KB per warp serve pass 1 as a ring of XSLOTS residual slots (one step = two fp32 boxes = 4 KB each) filled by
+// bulk-tensor loads; pass 1 is over before pass 3 writes the first staging tile
+constexpr int XSLOTS = 3;
+constexpr int XSLOT_BYTES = 2 * OUT_BOX_BYTES;
+static_assert(XSLOTS * XSLOT_BYTES == 2 * OUT_STAGE_BYTES, "residual ring and output staging share one buffer");
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_EPI_WARPS * 2 * OUT_STAGE_BYTES + 1024 + 512;
 constexpr int NCHUNK = LN_N / 32;             // 32-column chunks per row
 constexpr int CH = 2;                         // chunks per epilogue step
 static_assert(NCHUNK % CH == 0, "chunks per step");
@@ -156,6 +161,11 @@ __device__ __forceinline__ void tma_store_box(const CUtensorMap* tm, uint32_t sr
 __device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 template <bool DROP>
@@ -163,6 +173,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmF,
                                                                const __grid_constant__ CUtensorMap tmH,
+                                                               const __grid_constant__ CUtensorMap tmX,
                                                                const LnGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -172,6 +183,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
   uint64_t* tfull_bar = empty_bar + STAGES;      // accumulator ready
   uint64_t* tempty_bar = tfull_bar + 1;          // accumulator drained
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 1);
+  uint64_t* xbar = (uint64_t*)(tmem_slot + 2);   // [NUM_EPI_WARPS][XSLOTS] residual slot filled
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Fs2GemmLn& g = p.g;
@@ -186,6 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
     }
     mbar_init(smem_u32(tfull_bar), 1);
     mbar_init(smem_u32(tempty_bar), NUM_EPI_WARPS * NCTA);
+    for (int i = 0; i < NUM_EPI_WARPS * XSLOTS; ++i) mbar_init(smem_u32(&xbar[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -266,12 +279,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
     const uint32_t tw = tmem_base + ((uint32_t)(q * 32 + hf * 16) << 16);
     const float invC = 1.0f / (float)LN_N;
     bf16* oa = (bf16*)g.out_act;
-    // branch dropout: the mask of fs2_ln_fwd / fs2_ln_bwd (common.cuh:drop_scale4) -- one 64-bit mix per group of four
-    // consecutive elements.  A lane holds two consecutive columns of rows tr and tr + 8; the even lane of a pair mixes the
-    // group of row tr, the odd lane the group of row tr + 8, and one shuffle hands each the half it lacks.
-    const uint64_t dseed = g.drop_seed ^ (g.seed_dev ? mix64(*g.seed_dev) : 0ull);
-    const uint32_t dthr = (uint32_t)(g.drop_p * 65536.0f);
-    const float dks = DROP ? 1.0f / (1.0f - g.drop_p) : 1.0f;
+    // branch dropout: the mask of fs2_ln_fwd / fs2_ln_bwd (common.cuh:drop_bits2) -- one 32-bit hash per pair of
+    // consecutive elements, which is exactly what a lane holds per row and 8-column group
+    const DropKey dk = drop_key(g.drop_p, g.drop_seed ^ (g.seed_dev ? mix64(*g.seed_dev) : 0ull));
+    const uint32_t dthr = dk.thr;
+    const float dks = dk.ks;
     uint32_t tc = 0;
     bool ok = true;
     const bool prof = kProbe && p.dbg != nullptr && blockIdx.x == 0 && warp == 5 && lane == 0;
@@ -281,46 +293,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
       if (prof) pt[0] = clock64();
       const int row0 = t * (BM * NCTA) + (int)rank * BM + q * 32 + hf * 16;
       const RowInfo ra = row_info(row0 + tr, p.M, g.T, g.halo), rb = row_info(row0 + tr + 8, p.M, g.T, g.halo);
-      // residual rows of this warp (16 x 1536 B, contiguous): into L2 while the tile's MMAs run
-      {
-        const char* xb = reinterpret_cast<const char*>(g.x + (long long)row0 * LN_N);
+      // Residual rows of this warp: bulk-tensor loads (16 rows x 32 fp32 columns per box, 128B-swizzled) into the warp's
+      // ring while the tile's MMAs run; the lanes read them back in the accumulator layout with conflict-free ld.shared.
+      // As plain global loads in that layout they cost eight load/store-unit wavefronts per instruction (32 bytes of eight
+      // different lines) -- ~1 k cycles per step for the SM's eight warps, the bound of pass 1 -- and had to live in
+      // registers a step ahead.
+      const uint32_t wbuf = smem_u32(out_stage) + (uint32_t)(warp - 2) * (2 * OUT_STAGE_BYTES);
+      const uint32_t xb0 = smem_u32(&xbar[(warp - 2) * XSLOTS]);
+      if (elect_one()) {
+        // the previous tile's bulk stores read the bytes the ring occupies
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const int line = i * 32 + lane;
-          if (row0 + line / 12 < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + line * 128));
+        for (int k = 0; k < XSLOTS; ++k) {
+          mbar_expect_tx(xb0 + 8 * k, XSLOT_BYTES);
+          tma_load_4d(wbuf + k * XSLOT_BYTES, &tmX, xb0 + 8 * k, (2 * k) * 64, row0, 0, 0);
+          tma_load_4d(wbuf + k * XSLOT_BYTES + OUT_BOX_BYTES, &tmX, xb0 + 8 * k, (2 * k + 1) * 64, row0, 0, 0);
         }
       }
-      const float* xa = g.x + ra.off + 2 * tq;
-      const float* xb_ = g.x + rb.off + 2 * tq;
-      // CH chunks (32 columns each) per step.  Everything a step needs from memory (residual of the NEXT step, bias or
-      // gamma / beta of this one) and the step's dropout words are requested / computed as one unrolled batch BEFORE the
-      // wait on the tensor-memory load: with two epilogue warps per scheduler there is no other latency hiding, and a
-      // load-use pair or a 64-bit mix per 8-column group in program order made a step ~4 k cycles instead of ~1 k.
-      float2 xc[8 * CH], xn[8 * CH];
-#pragma unroll
-      for (int i = 0; i < 4 * CH; ++i) {
-        xc[2 * i] = ra.ok ? ldg2(xa + 8 * i) : make_float2(0.f, 0.f);
-        xc[2 * i + 1] = rb.ok ? ldg2(xb_ + 8 * i) : make_float2(0.f, 0.f);
-      }
+      __syncwarp();
+      // CH chunks (32 columns each) per step.  Everything a step needs from memory (bias or gamma / beta) and the step's
+      // dropout words are requested / computed as one unrolled batch BEFORE the wait on the tensor-memory load: with two
+      // epilogue warps per scheduler there is no other latency hiding.
+      const uint32_t xlane = (uint32_t)tr * 128u + 8u * (uint32_t)(tq & 1);
       if (prof) pt[1] = clock64();
       if (!mbar_wait(smem_u32(tfull_bar), tc & 1, err)) { ok = false; break; }
       tc_fence_after();
       if (prof) pt[2] = clock64();
       // ---- pass 1: z = x + keep * (acc + bias) -> tensor memory; row sums
       float sa = 0.f, sb = 0.f;
-      const uint64_t ga0 = (uint64_t)((tq & 1) ? rb.r : ra.r) * (LN_N / 4) + (uint64_t)(tq >> 1);
+      // element pair index of (row, column 8n + 2tq): row * 192 + 4n + tq
+      const uint32_t pa0 = (uint32_t)ra.r * (LN_N / 2) + (uint32_t)tq, pb0 = (uint32_t)rb.r * (LN_N / 2) + (uint32_t)tq;
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; c += CH) {
         uint32_t r[CH][16];
 #pragma unroll
         for (int j = 0; j < CH; ++j) tmem_ld_16x256b_x4(tw + (uint32_t)((c + j) * 32), r[j]);
-        if (c + CH < NCHUNK) {
-#pragma unroll
-          for (int i = 0; i < 4 * CH; ++i) {
-            xn[2 * i] = ra.ok ? ldg2(xa + (c + CH) * 32 + 8 * i) : make_float2(0.f, 0.f);
-            xn[2 * i + 1] = rb.ok ? ldg2(xb_ + (c + CH) * 32 + 8 * i) : make_float2(0.f, 0.f);
-          }
-        }
         float2 b2[4 * CH];
 #pragma unroll
         for (int i = 0; i < 4 * CH; ++i) b2[i] = ldg2(g.bias + c * 32 + 8 * i + 2 * tq);
@@ -330,15 +338,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
         if (DROP) {
 #pragma unroll
           for (int i = 0; i < 4 * CH; ++i) {
-            const uint64_t grp = ga0 + (uint64_t)(c * 8 + 2 * i);
-            const uint64_t rnd = mix64(dseed ^ (grp * 0xD6E8FEB86659FD93ull));
-            const uint32_t mine_lo = (uint32_t)rnd, mine_hi = (uint32_t)(rnd >> 32);
-            const uint32_t got = __shfl_xor_sync(0xffffffffu, (tq & 1) ? mine_lo : mine_hi, 1);
-            bits_a[i] = (tq & 1) ? got : mine_lo;       // row tr:     the even lane owns the group's mix
-            bits_b[i] = (tq & 1) ? mine_hi : got;       // row tr + 8: the odd lane owns it
+            bits_a[i] = drop_bits2(dk, pa0 + (uint32_t)(c * 16 + 4 * i));
+            bits_b[i] = drop_bits2(dk, pb0 + (uint32_t)(c * 16 + 4 * i));
           }
         }
         if (pp) p.dbg[9] = clock64();
+        // this step's residual: slot (step % 3), filled for the (step / 3)-th time in this tile
+        const int step = c / CH;
+        const uint32_t xslot = wbuf + (uint32_t)(step % XSLOTS) * XSLOT_BYTES;
+        if (!mbar_wait(xb0 + 8 * (step % XSLOTS), (uint32_t)(step / XSLOTS) & 1u, err)) { ok = false; break; }
+        float2 xc[8 * CH];
+#pragma unroll
+        for (int i = 0; i < 4 * CH; ++i) {
+          const uint32_t a = xslot + (uint32_t)(i >> 2) * OUT_BOX_BYTES + xlane + ((((uint32_t)(2 * (i & 3)) + (uint32_t)(tq >> 1)) ^ (uint32_t)tr) << 4);
+          xc[2 * i] = lds64(a);
+          xc[2 * i + 1] = lds64(a + 8u * 128u);
+        }
         tmem_wait_ld();
         if (pp) p.dbg[10] = clock64();
 #pragma unroll
@@ -367,10 +382,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
           tmem_st_16x256b_x4(tw + (uint32_t)((c + j) * 32), r[j]);
         }
         if (pp) p.dbg[11] = clock64();
-#pragma unroll
-        for (int i = 0; i < 8 * CH; ++i) xc[i] = xn[i];
-        if (pp) { p.dbg[12] = (long long)__float_as_uint(xc[0].x + xc[15].y); p.dbg[13] = clock64(); }
+        // every lane has consumed the slot (its values went into the tensor-memory store above): refill it
+        __syncwarp();
+        if (step + XSLOTS < NCHUNK / CH && elect_one()) {
+          const int k = step % XSLOTS, s2 = step + XSLOTS;
+          mbar_expect_tx(xb0 + 8 * k, XSLOT_BYTES);
+          tma_load_4d(xslot, &tmX, xb0 + 8 * k, (2 * s2) * 64, row0, 0, 0);
+          tma_load_4d(xslot + OUT_BOX_BYTES, &tmX, xb0 + 8 * k, (2 * s2 + 1) * 64, row0, 0, 0);
+        }
+        if (pp) p.dbg[13] = clock64();
       }
+      if (!ok) break;
       tmem_wait_st();
       if (prof) pt[3] = clock64();
       sa += __shfl_xor_sync(0xffffffffu, sa, 1);
@@ -444,10 +466,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader);
           }
-          // two staging tiles in turn: the engine must have read the step before the previous one (bulk groups belong to lane 0)
+          // two staging tiles in turn: the engine must have read the step before the previous one (bulk groups belong to the elected lane)
           const uint32_t st0 = stw + (uint32_t)((c / CH) & 1) * OUT_STAGE_BYTES;
           const uint32_t rowa = st0 + (uint32_t)tr * 128u;
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
           if (pp) p.dbg[18] = clock64();
 #pragma unroll
@@ -474,7 +496,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (pp) p.dbg[20] = clock64();
-          if (lane == 0) {
+          if (elect_one()) {                 // the same lane every time (lowest of the full mask): bulk groups are per thread
             tma_store_box(&tmF, st0, c * 64, row0w);                       // fp32 tensor addressed as 768 16-bit columns
             tma_store_box(&tmF, st0 + OUT_BOX_BYTES, (c + 1) * 64, row0w);
             tma_store_box(&tmH, st0 + 2 * OUT_BOX_BYTES, c * 32, row0w);
@@ -564,7 +586,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
       }
     }
     // the staging tile must outlive the engine's reads; the stores themselves complete before the grid does
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
   }
 
@@ -594,9 +616,9 @@ extern "C" int fs2_gemm_ln_tc(const Fs2GemmLn* gp, void* stream) {
   REQUIRE(g.B > 0 && g.T > 0 && g.K > 0 && g.K % 8 == 0, "fs2_gemm_ln_tc: bad shape (K must be a multiple of 8)");
   REQUIRE(g.halo >= 0 && g.halo <= FS2_PAD && (g.halo == 0 || g.T > g.halo), "fs2_gemm_ln_tc: halo too wide for T");
   REQUIRE(g.drop_p >= 0.f && g.drop_p < 1.f, "fs2_gemm_ln_tc: bad dropout probability");
-  REQUIRE((((uintptr_t)g.x | (uintptr_t)g.bias | (uintptr_t)g.gamma | (uintptr_t)g.beta) % 8) == 0 &&
-              (((uintptr_t)g.out_f32 | (uintptr_t)g.out_act) % 16) == 0,
-          "fs2_gemm_ln_tc: fp32 operands must be 8-byte aligned, outputs 16-byte aligned");
+  REQUIRE((((uintptr_t)g.bias | (uintptr_t)g.gamma | (uintptr_t)g.beta) % 8) == 0 &&
+              (((uintptr_t)g.x | (uintptr_t)g.out_f32 | (uintptr_t)g.out_act) % 16) == 0,
+          "fs2_gemm_ln_tc: parameter vectors must be 8-byte aligned, residual and outputs 16-byte aligned");
   const long long Ml = (long long)g.B * (g.T + 2 * FS2_PAD);
   REQUIRE(Ml * LN_N < (1LL << 40) && Ml < 0x7FFFFFFF, "fs2_gemm_ln_tc: too many rows");
   LnGemmParams p;
@@ -616,6 +638,8 @@ extern "C" int fs2_gemm_ln_tc(const Fs2GemmLn* gp, void* stream) {
   CUtensorMap tf, th;
   if ((rc = fs2_tc_make_map_2d(g.out_f32, 2 * LN_N, p.M, 2 * LN_N, 64, 16, &tf))) return rc;
   if ((rc = fs2_tc_make_map_2d(g.out_act, LN_N, p.M, LN_N, 64, 16, &th))) return rc;
+  CUtensorMap tx;              // the residual, read the same way
+  if ((rc = fs2_tc_make_map_2d(g.x, 2 * LN_N, p.M, 2 * LN_N, 64, 16, &tx))) return rc;
   auto kern = g.drop_p > 0.f ? gemm_ln_kernel<true> : gemm_ln_kernel<false>;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -645,7 +669,7 @@ extern "C" int fs2_gemm_ln_tc(const Fs2GemmLn* gp, void* stream) {
   }
   const int nunits = p.m_tiles < units ? p.m_tiles : units;
   cfg.gridDim = dim3(nunits * NCTA, 1, 1);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tf, th, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tf, th, tx, p);
   if (e != cudaSuccess) { fs2_set_error(cudaGetErrorString(e)); return FS2_ERR_CUDA; }
   return fs2_check_launch();
 }

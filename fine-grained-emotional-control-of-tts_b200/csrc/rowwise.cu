@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(THREADS) ln_fwd_kernel(Fs2LnFwd p, int pf) {
   const float invC = 1.0f / (float)C;
   TA* oa = (TA*)p.out_act;
   const unsigned long long bump = p.seed_dev ? mix64(*p.seed_dev) : 0ull;
-  const DropCfg db{p.drop_b_p, p.drop_b_seed ^ bump}, da{p.drop_a_p, p.drop_a_seed ^ bump};
+  const DropKey db = drop_key(p.drop_b_p, p.drop_b_seed ^ bump), da = drop_key(p.drop_a_p, p.drop_a_seed ^ bump);
   int pf_first = 1;                                           // the first live row also asks for the rows in between
   for (long long r = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * WARPS) {
     int b = (int)(r / TP), t = (int)(r - (long long)b * TP) - FS2_PAD;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, (NV <= 3 && !HEAD) ? 3 : 2) ln_bwd_ke
     if (CS_OK) *reinterpret_cast<float4*>(&acc_d[CS_OK ? warp : 0][lane * 4 + i * 128]) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const unsigned long long bump = p.seed_dev ? mix64(*p.seed_dev) : 0ull;
-  const DropCfg db{p.drop_b_p, p.drop_b_seed ^ bump}, da{p.drop_a_p, p.drop_a_seed ^ bump};
+  const DropKey db = drop_key(p.drop_b_p, p.drop_b_seed ^ bump), da = drop_key(p.drop_a_p, p.drop_a_seed ^ bump);
   float4 dhw[HEAD ? NV : 1];
 #pragma unroll
   for (int i = 0; i < (HEAD ? NV : 1); ++i) dhw[i] = make_float4(0.f, 0.f, 0.f, 0.f);

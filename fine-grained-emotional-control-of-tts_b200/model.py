@@ -520,7 +520,9 @@ class FastSpeech2(nn.Module):
                        bias=self._P(f"{pre}.pos_ffn.0.conv.bias"), relu=1, halo=h2)
             y_f32, y_act = self._f32(rows, D), self._act(rows, D)
             sv.mean2, sv.rstd2 = self._f32(rows), self._f32(rows)
-            if fuse_ln:
+            # (at phoneme-length row counts the K = 1536 form loses: 17 CTA pairs walk 24 k-blocks each where the plain GEMM
+            #  spreads 128 x 192 tiles over 68 SMs -- 30.8 vs 26.3 us at 4352 rows, profiles/r02_gemm_ln_bench.txt)
+            if fuse_ln and rows >= 8192:
                 sv.Fo = None
                 self._gemm_ln(sv.Hh, B, T, f"{pre}.pos_ffn.2.conv.weight", self._P(f"{pre}.pos_ffn.2.conv.bias"),
                               sv.x1_f32, self._P(f"{pre}.norm2.norm.weight"), self._P(f"{pre}.norm2.norm.bias"), 1e-6,
