@@ -299,6 +299,25 @@ def memory_kernels(peaks):
              "alg_bytes": r["alg_bytes"]} for r in rows]
 
 
+def gemm_ln_pairs():
+    """fs2_gemm_ln_tc (out-projection / FFN conv 2 + residual + LayerNorm as one kernel) against the two launches it
+    replaces, batch 32 at 800 and 488 frames (tools/gemm_ln_bench.py); `fused_alg_GB/s` = operand + residual + both
+    outputs over the launch time (HBM peak: MEASURED_PEAKS.json)."""
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ.setdefault("GEMM_LN_T", "800,488")
+    gb = importlib.import_module("gemm_ln_bench")
+    argv, sys.argv = sys.argv, sys.argv[:1]
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            rows = gb.main()
+    finally:
+        sys.argv = argv
+    torch.cuda.empty_cache()
+    return rows
+
+
 def inference_b256():
     """BASELINE configs[4] in the same run: batch 256, predicted durations, pace 0.8 / 1.0 / 1.2 (tools/infer_bench.py)."""
     import contextlib
@@ -524,7 +543,8 @@ def main():
     }
     line.update(extras)
     if world == 1 and not args.no_extras:
-        for key, fn in (("memory_kernels", lambda: memory_kernels(peaks)), ("inference_b256", inference_b256)):
+        for key, fn in (("memory_kernels", lambda: memory_kernels(peaks)), ("gemm_ln", gemm_ln_pairs),
+                        ("inference_b256", inference_b256)):
             try:
                 line[key] = fn()
             except Exception as e:                   # an evidence leg must never take the product number down with it

@@ -16,6 +16,7 @@ PAD, C = 4, 384
 
 
 def timeit(fn, ring, iters=30, warm=4):
+    iters, warm = int(os.environ.get("GEMM_LN_ITERS", iters)), int(os.environ.get("GEMM_LN_WARM", warm))   # 1 / 1 under ncu
     for i in range(warm):
         fn(i % ring)
     torch.cuda.synchronize()
@@ -30,8 +31,9 @@ def timeit(fn, ring, iters=30, warm=4):
 
 def main():
     L = importlib.import_module(PKG + "._lib")
-    Ts = [int(a) for a in sys.argv[1:]] or [800, 632, 488, 376, 128]
+    Ts = [int(a) for a in sys.argv[1:] if a.isdigit()] or [int(a) for a in os.environ.get("GEMM_LN_T", "800,632,488,376,128").split(",")]
     B = 32
+    out = []
     dbg = None
     if os.environ.get("GEMM_LN_DBG"):          # probe build: FS2_B200_LIB=<pkg>/libfs2_b200_probe.so
         dbg = torch.zeros(32, dtype=torch.int64, device="cuda")
@@ -77,9 +79,10 @@ def main():
 
             t2, t1 = timeit(two, ring), timeit(one, ring)
             alg = rows * (K * 2 + C * (4 + 4 + 2))            # A + residual in, fp32 + bf16 out
-            print(json.dumps({"K": K, "T": T, "rows": rows, "two_launches_us": round(t2, 1), "fused_us": round(t1, 1),
-                              "fused_alg_GB/s": round(alg / t1 * 1e-3, 1), "fused_TFLOP/s": round(2.0 * rows * C * K / t1 * 1e-6, 1)}),
-                  flush=True)
+            out.append({"K": K, "T": T, "rows": rows, "two_launches_us": round(t2, 1), "fused_us": round(t1, 1),
+                        "alg_bytes": alg, "fused_alg_GB/s": round(alg / t1 * 1e-3, 1),
+                        "fused_TFLOP/s": round(2.0 * rows * C * K / t1 * 1e-6, 1)})
+            print(json.dumps(out[-1]), flush=True)
             if dbg is not None:
                 torch.cuda.synchronize()
                 print("   epilogue of CTA 0, first tile [cycles]: setup %d, wait for MMAs %d, pass 1 %d, pass 2 %d, pass 3 %d"
@@ -91,6 +94,7 @@ def main():
                       % (d[17] - d[16], d[18] - d[17], d[19] - d[18], d[20] - d[19], d[21] - d[20]), flush=True)
             del A, x, proj, of, oa
     assert L.gemm_tc_error_flag() == 0
+    return out
 
 
 if __name__ == "__main__":

@@ -204,6 +204,12 @@ def main():
                                             drop_b=(0.1, 11), dx_f32=dx[i], dact=da[i], dgamma=dg, dbeta=db), R4)
         report("ln_bwd (B=32,Tm=800,C=384)" + (f" [L2 prefetch distance {pf}]" if pf else " [no L2 prefetch]"), rows * C * (4 + 4 + 4 + 4 + 2) + rows * 8, us,
                "read dy fp32 + x fp32 + branch fp32, write dx fp32 + dbranch bf16")
+    # the form the FFT blocks use since fs2_gemm_ln_tc: x_hat from the saved LayerNorm output (no x, no branch)
+    raw.fs2_ln_tune(PFS[-1])
+    us = timeit(lambda i: model._ln_bwd(B3, Tm3, C, None, gam, bet, 1e-6, None, rstd, dy=dys[i], y=o32[i],
+                                        drop_b=(0.1, 11), dx_f32=dx[i], dact=da[i], dgamma=dg, dbeta=db), R4)
+    report("ln_bwd, x_hat from the forward output (B=32,Tm=800,C=384)", rows * C * (4 + 4 + 4 + 2) + rows * 4, us,
+           "read dy fp32 + y fp32, write dx fp32 + dbranch bf16")
     cs = torch.zeros(1536, device=dev)
     big = [torch.randn(rows, 1536, device=dev).bfloat16() for _ in range(3)]
     us = timeit(lambda i: L.call("fs2_colsum", big[i], 1, rows, 1536, 1536, cs), 3)
