@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/fs2_b200.h"
 #include "tc_ptx.cuh"
@@ -67,6 +68,7 @@ struct LnGemmParams {
   int M, m_tiles, kb;
   int* err;
   long long* dbg;
+  int dbg_mode;      // probe build only (results incomplete): pass-3 experiments, see fs2_gemm_ln_set_debug
 };
 
 // what the epilogue needs to know about one output row
@@ -149,6 +151,10 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3)
                : "memory");
 }
+
+// two accumulator columns of one row as a float2 (the 16x256b layout hands a lane pairs of consecutive columns), for the
+// packed fp32x2 arithmetic of sm_100 (FADD2 / FMUL2 / FFMA2: one instruction per column pair, IEEE-identical per element)
+__device__ __forceinline__ float2 f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
@@ -316,14 +322,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
       // dropout words are requested / computed as one unrolled batch BEFORE the wait on the tensor-memory load: with two
       // epilogue warps per scheduler there is no other latency hiding.
       const uint32_t xlane = (uint32_t)tr * 128u + 8u * (uint32_t)(tq & 1);
+      // Dropout keep bits of this lane's 2 x 96 elements, computed NOW -- while the tile's MMAs run and the epilogue warps
+      // have nothing else to do -- and packed into six words: the hashes are ~210 integer instructions per lane and
+      // 64-column step, and the integer pipe (half rate) made them ~1 k cycles per step when they sat inside pass 1.
+      // Word w of a row covers steps 2w and 2w + 1; bit 16 (step & 1) + 2 i + e is column 64 step + 8 i + 2 tq + e.
+      uint32_t km_a0 = 0u, km_a1 = 0u, km_a2 = 0u, km_b0 = 0u, km_b1 = 0u, km_b2 = 0u;
+      if (DROP) {
+        const uint32_t pa0 = (uint32_t)ra.r * (LN_N / 2) + (uint32_t)tq, pb0 = (uint32_t)rb.r * (LN_N / 2) + (uint32_t)tq;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          uint32_t ma = 0u, mb = 0u;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {           // k = 8 (step & 1) + i: element pair index 32 step + 4 i + tq of the row
+            const uint32_t ha = drop_bits2(dk, pa0 + (uint32_t)(64 * w + 4 * k));
+            const uint32_t hb = drop_bits2(dk, pb0 + (uint32_t)(64 * w + 4 * k));
+            ma |= ((ha & 0xFFFFu) >= dthr ? 1u : 0u) << (2 * k);
+            ma |= ((ha >> 16) >= dthr ? 1u : 0u) << (2 * k + 1);
+            mb |= ((hb & 0xFFFFu) >= dthr ? 1u : 0u) << (2 * k);
+            mb |= ((hb >> 16) >= dthr ? 1u : 0u) << (2 * k + 1);
+          }
+          if (w == 0) { km_a0 = ma; km_b0 = mb; }
+          if (w == 1) { km_a1 = ma; km_b1 = mb; }
+          if (w == 2) { km_a2 = ma; km_b2 = mb; }
+        }
+        // pin the computation here: without a use before the wait below the compiler sinks it behind the wait
+        asm volatile("" ::"r"(km_a0), "r"(km_a1), "r"(km_a2), "r"(km_b0), "r"(km_b1), "r"(km_b2));
+      }
       if (prof) pt[1] = clock64();
       if (!mbar_wait(smem_u32(tfull_bar), tc & 1, err)) { ok = false; break; }
       tc_fence_after();
       if (prof) pt[2] = clock64();
       // ---- pass 1: z = x + keep * (acc + bias) -> tensor memory; row sums
-      float sa = 0.f, sb = 0.f;
-      // element pair index of (row, column 8n + 2tq): row * 192 + 4n + tq
-      const uint32_t pa0 = (uint32_t)ra.r * (LN_N / 2) + (uint32_t)tq, pb0 = (uint32_t)rb.r * (LN_N / 2) + (uint32_t)tq;
+      float2 sa2 = make_float2(0.f, 0.f), sb2 = make_float2(0.f, 0.f);     // even / odd column partial sums
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; c += CH) {
         uint32_t r[CH][16];
@@ -331,22 +361,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
         for (int j = 0; j < CH; ++j) tmem_ld_16x256b_x4(tw + (uint32_t)((c + j) * 32), r[j]);
         float2 b2[4 * CH];
 #pragma unroll
-        for (int i = 0; i < 4 * CH; ++i) b2[i] = ldg2(g.bias + c * 32 + 8 * i + 2 * tq);
+        for (int i = 0; i < 4 * CH; ++i) b2[i] = (kProbe && (p.dbg_mode & 8)) ? make_float2(0.f, 0.f) : ldg2(g.bias + c * 32 + 8 * i + 2 * tq);
         const bool pp = prof && tc == 0 && c == 4;
+        if (prof && tc == 0) p.dbg[22 + c / CH] = clock64();       // start of every pass-1 step
         if (pp) p.dbg[8] = clock64();
-        uint32_t bits_a[4 * CH], bits_b[4 * CH];
-        if (DROP) {
-#pragma unroll
-          for (int i = 0; i < 4 * CH; ++i) {
-            bits_a[i] = drop_bits2(dk, pa0 + (uint32_t)(c * 16 + 4 * i));
-            bits_b[i] = drop_bits2(dk, pb0 + (uint32_t)(c * 16 + 4 * i));
-          }
-        }
+        // this step's keep bits: 16 per row
+        const int stp = c / CH;
+        const uint32_t wa_ = (stp < 2 ? km_a0 : stp < 4 ? km_a1 : km_a2) >> ((stp & 1) * 16);
+        const uint32_t wb_ = (stp < 2 ? km_b0 : stp < 4 ? km_b1 : km_b2) >> ((stp & 1) * 16);
         if (pp) p.dbg[9] = clock64();
         // this step's residual: slot (step % 3), filled for the (step / 3)-th time in this tile
         const int step = c / CH;
         const uint32_t xslot = wbuf + (uint32_t)(step % XSLOTS) * XSLOT_BYTES;
-        if (!mbar_wait(xb0 + 8 * (step % XSLOTS), (uint32_t)(step / XSLOTS) & 1u, err)) { ok = false; break; }
+        if (!(kProbe && (p.dbg_mode & 32) && step >= XSLOTS) &&
+            !mbar_wait(xb0 + 8 * (step % XSLOTS), (uint32_t)(step / XSLOTS) & 1u, err)) { ok = false; break; }
         float2 xc[8 * CH];
 #pragma unroll
         for (int i = 0; i < 4 * CH; ++i) {
@@ -363,28 +391,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
             const int i = 4 * j + n;
             float ka0 = 1.f, ka1 = 1.f, kb0 = 1.f, kb1 = 1.f;
             if (DROP) {
-              ka0 = ((bits_a[i] & 0xFFFFu) >= dthr) ? dks : 0.f;
-              ka1 = ((bits_a[i] >> 16) >= dthr) ? dks : 0.f;
-              kb0 = ((bits_b[i] & 0xFFFFu) >= dthr) ? dks : 0.f;
-              kb1 = ((bits_b[i] >> 16) >= dthr) ? dks : 0.f;
+              ka0 = (wa_ & (1u << (2 * i))) ? dks : 0.f;
+              ka1 = (wa_ & (2u << (2 * i))) ? dks : 0.f;
+              kb0 = (wb_ & (1u << (2 * i))) ? dks : 0.f;
+              kb1 = (wb_ & (2u << (2 * i))) ? dks : 0.f;
             }
-            const float za0 = xc[2 * i].x + (__uint_as_float(r[j][4 * n]) + b2[i].x) * ka0;
-            const float za1 = xc[2 * i].y + (__uint_as_float(r[j][4 * n + 1]) + b2[i].y) * ka1;
-            const float zb0 = xc[2 * i + 1].x + (__uint_as_float(r[j][4 * n + 2]) + b2[i].x) * kb0;
-            const float zb1 = xc[2 * i + 1].y + (__uint_as_float(r[j][4 * n + 3]) + b2[i].y) * kb1;
-            sa += za0 + za1;
-            sb += zb0 + zb1;
-            r[j][4 * n] = __float_as_uint(za0);
-            r[j][4 * n + 1] = __float_as_uint(za1);
-            r[j][4 * n + 2] = __float_as_uint(zb0);
-            r[j][4 * n + 3] = __float_as_uint(zb1);
+            const float2 za = __ffma2_rn(__fadd2_rn(f2(r[j][4 * n], r[j][4 * n + 1]), b2[i]), make_float2(ka0, ka1), xc[2 * i]);
+            const float2 zb = __ffma2_rn(__fadd2_rn(f2(r[j][4 * n + 2], r[j][4 * n + 3]), b2[i]), make_float2(kb0, kb1), xc[2 * i + 1]);
+            sa2 = __fadd2_rn(sa2, za);
+            sb2 = __fadd2_rn(sb2, zb);
+            r[j][4 * n] = __float_as_uint(za.x);
+            r[j][4 * n + 1] = __float_as_uint(za.y);
+            r[j][4 * n + 2] = __float_as_uint(zb.x);
+            r[j][4 * n + 3] = __float_as_uint(zb.y);
           }
           tmem_st_16x256b_x4(tw + (uint32_t)((c + j) * 32), r[j]);
         }
         if (pp) p.dbg[11] = clock64();
         // every lane has consumed the slot (its values went into the tensor-memory store above): refill it
         __syncwarp();
-        if (step + XSLOTS < NCHUNK / CH && elect_one()) {
+        if (step + XSLOTS < NCHUNK / CH && !(kProbe && (p.dbg_mode & 32)) && elect_one()) {
           const int k = step % XSLOTS, s2 = step + XSLOTS;
           mbar_expect_tx(xb0 + 8 * k, XSLOT_BYTES);
           tma_load_4d(xslot, &tmX, xb0 + 8 * k, (2 * s2) * 64, row0, 0, 0);
@@ -393,15 +419,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
         if (pp) p.dbg[13] = clock64();
       }
       if (!ok) break;
+      if (prof && tc == 0) p.dbg[28] = clock64();
       tmem_wait_st();
       if (prof) pt[3] = clock64();
+      if (prof && tc == 0) p.dbg[29] = pt[3];
+      float sa = sa2.x + sa2.y, sb = sb2.x + sb2.y;
       sa += __shfl_xor_sync(0xffffffffu, sa, 1);
       sa += __shfl_xor_sync(0xffffffffu, sa, 2);
       sb += __shfl_xor_sync(0xffffffffu, sb, 1);
       sb += __shfl_xor_sync(0xffffffffu, sb, 2);
       const float mean_a = sa * invC, mean_b = sb * invC;
       // ---- pass 2: centred sum of squares
-      float qa = 0.f, qb = 0.f;
+      float2 qa2 = make_float2(0.f, 0.f), qb2 = make_float2(0.f, 0.f);
+      const float2 nma = make_float2(-mean_a, -mean_a), nmb = make_float2(-mean_b, -mean_b);
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; c += CH) {
         uint32_t r[CH][16];
@@ -412,13 +442,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
         for (int j = 0; j < CH; ++j) {
 #pragma unroll
           for (int n = 0; n < 4; ++n) {
-            const float a0 = __uint_as_float(r[j][4 * n]) - mean_a, a1 = __uint_as_float(r[j][4 * n + 1]) - mean_a;
-            const float b0 = __uint_as_float(r[j][4 * n + 2]) - mean_b, b1 = __uint_as_float(r[j][4 * n + 3]) - mean_b;
-            qa += a0 * a0 + a1 * a1;
-            qb += b0 * b0 + b1 * b1;
+            const float2 da = __fadd2_rn(f2(r[j][4 * n], r[j][4 * n + 1]), nma), db = __fadd2_rn(f2(r[j][4 * n + 2], r[j][4 * n + 3]), nmb);
+            qa2 = __ffma2_rn(da, da, qa2);
+            qb2 = __ffma2_rn(db, db, qb2);
           }
         }
       }
+      float qa = qa2.x + qa2.y, qb = qb2.x + qb2.y;
       qa += __shfl_xor_sync(0xffffffffu, qa, 1);
       qa += __shfl_xor_sync(0xffffffffu, qa, 2);
       qb += __shfl_xor_sync(0xffffffffu, qb, 1);
@@ -440,6 +470,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
       // 64-column step into its swizzled staging tile and lets the bulk-tensor engine store the three boxes: the
       // load/store unit sees two shared-memory wavefronts per instruction where the same registers stored to global
       // memory cost eight (one per row: 32 or 16 bytes of a 128-byte line each) -- that was the epilogue's bound.
+      const float2 rsa = make_float2(rstd_a, rstd_a), rsb = make_float2(rstd_b, rstd_b);
       const bool fast = __all_sync(0xffffffffu, ra.ok && rb.ok && (ra.m1 | ra.m2 | rb.m1 | rb.m2) == 0);
       if (fast) {
         const uint32_t stw = smem_u32(out_stage) + (uint32_t)(warp - 2) * (2 * OUT_STAGE_BYTES);
@@ -454,8 +485,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
           float2 g2[4 * CH], be2[4 * CH];
 #pragma unroll
           for (int i = 0; i < 4 * CH; ++i) {
-            g2[i] = ldg2(g.gamma + c * 32 + 8 * i + 2 * tq);
-            be2[i] = ldg2(g.beta + c * 32 + 8 * i + 2 * tq);
+            g2[i] = (kProbe && (p.dbg_mode & 8)) ? make_float2(1.f, 1.f) : ldg2(g.gamma + c * 32 + 8 * i + 2 * tq);
+            be2[i] = (kProbe && (p.dbg_mode & 8)) ? make_float2(0.f, 0.f) : ldg2(g.beta + c * 32 + 8 * i + 2 * tq);
           }
           const bool pp = prof && tc == 0 && c == 4;
           if (pp) p.dbg[16] = clock64();
@@ -469,18 +500,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
           // two staging tiles in turn: the engine must have read the step before the previous one (bulk groups belong to the elected lane)
           const uint32_t st0 = stw + (uint32_t)((c / CH) & 1) * OUT_STAGE_BYTES;
           const uint32_t rowa = st0 + (uint32_t)tr * 128u;
-          if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          __syncwarp();
+          // (nothing is pending in the first two steps: the tile began with wait_group.read 0)
+          if (c >= 2 * CH) {
+            if (!(kProbe && (p.dbg_mode & 4)) && elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+          }
           if (pp) p.dbg[18] = clock64();
 #pragma unroll
           for (int j = 0; j < CH; ++j) {
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
               const int i = 4 * j + n;
-              const float ya0 = (__uint_as_float(r[j][4 * n]) - mean_a) * rstd_a * g2[i].x + be2[i].x;
-              const float ya1 = (__uint_as_float(r[j][4 * n + 1]) - mean_a) * rstd_a * g2[i].y + be2[i].y;
-              const float yb0 = (__uint_as_float(r[j][4 * n + 2]) - mean_b) * rstd_b * g2[i].x + be2[i].x;
-              const float yb1 = (__uint_as_float(r[j][4 * n + 3]) - mean_b) * rstd_b * g2[i].y + be2[i].y;
+              // (z - mean) * rstd * gamma + beta, the expression order of fs2_ln_fwd
+              const float2 ya = __ffma2_rn(__fmul2_rn(__fadd2_rn(f2(r[j][4 * n], r[j][4 * n + 1]), nma), rsa), g2[i], be2[i]);
+              const float2 yb = __ffma2_rn(__fmul2_rn(__fadd2_rn(f2(r[j][4 * n + 2], r[j][4 * n + 3]), nmb), rsb), g2[i], be2[i]);
+              const float ya0 = ya.x, ya1 = ya.y, yb0 = yb.x, yb1 = yb.y;
               const __nv_bfloat162 pa = __floats2bfloat162_rn(ya0, ya1), pb = __floats2bfloat162_rn(yb0, yb1);
               // fp32 box j: byte 32 n + 8 tq of the row -> chunk 2n + tq/2
               const uint32_t fo = (uint32_t)j * OUT_BOX_BYTES + ((((uint32_t)(2 * n) + (uint32_t)(tq >> 1)) ^ tsw) << 4) + 8u * (uint32_t)(tq & 1);
@@ -493,10 +527,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
             }
           }
           if (pp) p.dbg[19] = clock64();
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (!(kProbe && (p.dbg_mode & 16))) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (pp) p.dbg[20] = clock64();
-          if (elect_one()) {                 // the same lane every time (lowest of the full mask): bulk groups are per thread
+          if (!(kProbe && (p.dbg_mode & 1)) && elect_one()) {   // the same lane every time (lowest of the full mask): bulk groups are per thread
             tma_store_box(&tmF, st0, c * 64, row0w);                       // fp32 tensor addressed as 768 16-bit columns
             tma_store_box(&tmF, st0 + OUT_BOX_BYTES, (c + 1) * 64, row0w);
             tma_store_box(&tmH, st0 + 2 * OUT_BOX_BYTES, c * 32, row0w);
@@ -537,10 +571,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
             const int i = 4 * j + n;
             const int col = (c + j) * 32 + 8 * n;
             float2 ya, yb;
-            ya.x = (__uint_as_float(r[j][4 * n]) - mean_a) * rstd_a * g2[i].x + be2[i].x;
-            ya.y = (__uint_as_float(r[j][4 * n + 1]) - mean_a) * rstd_a * g2[i].y + be2[i].y;
-            yb.x = (__uint_as_float(r[j][4 * n + 2]) - mean_b) * rstd_b * g2[i].x + be2[i].x;
-            yb.y = (__uint_as_float(r[j][4 * n + 3]) - mean_b) * rstd_b * g2[i].y + be2[i].y;
+            ya = __ffma2_rn(__fmul2_rn(__fadd2_rn(f2(r[j][4 * n], r[j][4 * n + 1]), nma), rsa), g2[i], be2[i]);
+            yb = __ffma2_rn(__fmul2_rn(__fadd2_rn(f2(r[j][4 * n + 2], r[j][4 * n + 3]), nmb), rsb), g2[i], be2[i]);
             ya.x = ra.ok ? ya.x : 0.f;           // halo rows no mirror reaches get zeros
             ya.y = ra.ok ? ya.y : 0.f;
             yb.x = rb.ok ? yb.x : 0.f;
@@ -599,11 +631,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_ln_kernel(const __grid_const
 }
 
 long long* g_ln_gemm_dbg = nullptr;
+int g_ln_gemm_dbg_mode = 0;
 
 }  // namespace
 
 extern "C" int fs2_gemm_ln_set_debug(long long* dev_buf) {
   g_ln_gemm_dbg = dev_buf;
+  const char* e = getenv("GEMM_LN_DBG_MODE");     // bit 0: no bulk stores, bit 1: no staging writes, bit 2: no staging-reuse wait
+  g_ln_gemm_dbg_mode = e ? atoi(e) : 0;
   return FS2_OK;
 }
 
@@ -628,6 +663,7 @@ extern "C" int fs2_gemm_ln_tc(const Fs2GemmLn* gp, void* stream) {
   p.m_tiles = (p.M + BM * NCTA - 1) / (BM * NCTA);
   p.kb = (g.K + BK - 1) / BK;
   p.dbg = g_ln_gemm_dbg;
+  p.dbg_mode = g_ln_gemm_dbg_mode;
   int rc = fs2_tc_error_ptr(&p.err);
   if (rc) return rc;
   CUtensorMap ta, tb;

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 PKG = "fine-grained-emotional-control-of-tts_b200"
 PAD, C = 4, 384
+PDROP = float(os.environ.get("GEMM_LN_P", "0.1"))      # branch dropout (0 selects the kernel instantiation without it)
 
 
 def timeit(fn, ring, iters=30, warm=4):
@@ -61,7 +62,7 @@ def main():
                 p = L.Fs2LnFwd()
                 p.B, p.T, p.C = B, T, C
                 p.x, p.branch = x[i].data_ptr(), proj[i].data_ptr()
-                p.drop_b_p, p.drop_b_seed = 0.1, 1234
+                p.drop_b_p, p.drop_b_seed = PDROP, 1234
                 p.gamma, p.beta, p.eps = gamma.data_ptr(), beta.data_ptr(), 1e-6
                 p.out_f32, p.out_act, p.act_bf16, p.halo = of[i].data_ptr(), oa[i].data_ptr(), 1, 4
                 p.mean, p.rstd, p.seed_dev = mean.data_ptr(), rstd.data_ptr(), ctr.data_ptr()
@@ -71,7 +72,7 @@ def main():
                 q = L.Fs2GemmLn()
                 q.B, q.T, q.K, q.lda, q.ldw = B, T, K, K, K
                 q.A, q.W, q.bias, q.x = A[i].data_ptr(), W.data_ptr(), bias.data_ptr(), x[i].data_ptr()
-                q.drop_p, q.drop_seed, q.seed_dev = 0.1, 1234, ctr.data_ptr()
+                q.drop_p, q.drop_seed, q.seed_dev = PDROP, 1234, ctr.data_ptr()
                 q.gamma, q.beta, q.eps = gamma.data_ptr(), beta.data_ptr(), 1e-6
                 q.out_f32, q.out_act, q.halo = of[i].data_ptr(), oa[i].data_ptr(), 4
                 q.mean, q.rstd = mean.data_ptr(), rstd.data_ptr()
@@ -90,6 +91,8 @@ def main():
                 d = dbg.tolist()
                 print("   pass 1, third step: loads + dropout words issued %d, wait TMEM %d, math + TMEM store %d, residual of the next step arrived %d"
                       % (d[9] - d[8], d[10] - d[9], d[11] - d[10], d[13] - d[11]), flush=True)
+                print("   pass 1, cycles per step: %s, loop end -> tensor-memory stores complete %d"
+                      % (" ".join(str(d[23 + k] - d[22 + k]) for k in range(5)) + " " + str(d[28] - d[27]), d[29] - d[28]), flush=True)
                 print("   pass 3, third step: wait TMEM (+ gamma / beta) %d, staging tile free %d, math + st.shared %d, proxy fence %d, 3 bulk stores issued %d"
                       % (d[17] - d[16], d[18] - d[17], d[19] - d[18], d[20] - d[19], d[21] - d[20]), flush=True)
             del A, x, proj, of, oa
