@@ -181,6 +181,7 @@ class FastSpeech2(nn.Module):
         # bf16, model width 384, k = 1 second FFN conv: out-projection -> norm1 and FFN conv 2 -> norm2 each run as ONE kernel
         # (fs2_gemm_ln_tc: the fp32 branch never reaches HBM); the backward takes x_hat from the saved LayerNorm output
         self.fused_ln = os.environ.get("FS2_FUSED_LN", "1") != "0"
+        self.fused_ln_min_rows_ffn = int(os.environ.get("FS2_FUSED_LN_MIN_ROWS_FFN", "8192"))
         self.async_mel_lens = False   # opt-in: no host sync; Tm is taken from pitch.shape[1], mel_lens arrives in pinned memory
         # opt-in, inference with predicted durations in precision="bf16": frame counts are trunc(pace * expm1(pred)), which is
         # discontinuous -- a bf16 encoder moves ~1 % of the phonemes across an integer boundary (tests/
@@ -520,9 +521,10 @@ class FastSpeech2(nn.Module):
                        bias=self._P(f"{pre}.pos_ffn.0.conv.bias"), relu=1, halo=h2)
             y_f32, y_act = self._f32(rows, D), self._act(rows, D)
             sv.mean2, sv.rstd2 = self._f32(rows), self._f32(rows)
-            # (at phoneme-length row counts the K = 1536 form loses: 17 CTA pairs walk 24 k-blocks each where the plain GEMM
-            #  spreads 128 x 192 tiles over 68 SMs -- 30.8 vs 26.3 us at 4352 rows, profiles/r02_gemm_ln_bench.txt)
-            if fuse_ln and rows >= 8192:
+            # (at phoneme-length row counts the K = 1536 form is on par at best: 17 CTA pairs walk 24 k-blocks each where the
+            #  plain GEMM spreads 128 x 192 tiles over 68 SMs -- 28.0 vs 26.9 us at 4352 rows, profiles/r02_gemm_ln_bench_final.txt;
+            #  step A/B on one box: 8.52 / 8.55 ms with the default fused_ln_min_rows_ffn = 8192, 8.58 / 8.58 ms with 0)
+            if fuse_ln and rows >= self.fused_ln_min_rows_ffn:
                 sv.Fo = None
                 self._gemm_ln(sv.Hh, B, T, f"{pre}.pos_ffn.2.conv.weight", self._P(f"{pre}.pos_ffn.2.conv.bias"),
                               sv.x1_f32, self._P(f"{pre}.norm2.norm.weight"), self._P(f"{pre}.norm2.norm.bias"), 1e-6,
