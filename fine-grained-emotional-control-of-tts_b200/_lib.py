@@ -83,7 +83,7 @@ class Fs2Gemm(C.Structure):
         ("bias", C.c_void_p), ("alpha", C.c_float), ("relu", C.c_int),
         ("relu_aux", C.c_void_p), ("aux_bf16", C.c_int),
         ("rs_T", C.c_int), ("rs_Tp", C.c_int), ("lens", C.c_void_p), ("halo", C.c_int),
-        ("ab_bf16", C.c_int), ("c_split_stride", C.c_longlong),
+        ("ab_bf16", C.c_int), ("c_split_stride", C.c_longlong), ("a_colsum", C.c_void_p),
     ]
 
 
@@ -200,7 +200,8 @@ def gemm(*, mode, M, N, K, A, lda, a_rows, a_inner, B, ldb, b_rows, b_inner, Cou
          ab_bf16, taps=1, batch1=1, batch2=1, a_s1=0, a_s2=0, a_row_off=0, a_tap_step=0,
          b_s1=0, b_s2=0, b_row_off=0, b_tap_step=0, c_tap_stride=0, c_col_stride=0, c_s1=0, c_s2=0, c_row_off=0,
          c_col_off=0, accumulate=0, split_k=1, bias=None, alpha=1.0, relu=0, relu_aux=None,
-         aux_bf16=0, rs_T=0, rs_Tp=0, lens=None, halo=0, use_tc=None, A_off=0, B_off=0, C_off=0, c_split_stride=0):
+         aux_bf16=0, rs_T=0, rs_Tp=0, lens=None, halo=0, use_tc=None, A_off=0, B_off=0, C_off=0, c_split_stride=0,
+         a_colsum=None):
     """Thin wrapper over fs2_gemm_tc / fs2_gemm_simt.  A_off/B_off/C_off are element offsets
     added to the base pointers (in the operand's own element size)."""
     g = Fs2Gemm()
@@ -226,6 +227,7 @@ def gemm(*, mode, M, N, K, A, lda, a_rows, a_inner, B, ldb, b_rows, b_inner, Cou
     g.lens = lens.data_ptr() if lens is not None else None
     g.halo, g.ab_bf16 = halo, int(ab_bf16)
     g.c_split_stride = c_split_stride
+    g.a_colsum = a_colsum.data_ptr() if a_colsum is not None else None
     if use_tc is None:
         use_tc = bool(ab_bf16)
     fn = "fs2_gemm_tc" if use_tc else "fs2_gemm_simt"

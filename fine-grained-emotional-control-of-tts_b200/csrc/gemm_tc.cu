@@ -194,6 +194,12 @@ __device__ __forceinline__ void epi_chunk(const Fs2Gemm& g, const EpiRow& er, co
 // caller): full 32-column chunk, unit column stride, no atomics, no halo mirrors in this warp's rows.
 constexpr int EPI_STAGE_BYTES = 2048;                      // per epilogue warp
 constexpr int EPI_STAGE_TOTAL = NUM_EPI_WARPS * EPI_STAGE_BYTES;
+// Weight-gradient kernels (mode 2) with 128 x 192 tiles can fold the bias gradient in (Fs2Gemm.a_colsum): a 2 KB tile of
+// bf16 ones serves as a second B operand -- one extra N = 16 MMA per K step gives the column sums of the A tile (dy) in 16
+// spare tensor-memory columns per accumulator buffer.  All elements are equal, so layout and swizzle of the tile do not matter.
+constexpr int ONES_OFF = 256 + EPI_STAGE_TOTAL + 768;      // after the barriers and the staging tiles, 1024-aligned
+constexpr int ONES_BYTES = 2048;
+constexpr int CS_COLS = 16;
 
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
@@ -432,6 +438,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // bias-gradient fold (see ONES_OFF): possible where two accumulator buffers leave 2 x 16 tensor-memory columns free
+  constexpr bool CS_OK = (MODE == 2) && (2 * BN + 2 * CS_COLS <= TMEM_COLS);
+  const bool cs_on = CS_OK && g.a_colsum != nullptr;
+  if (cs_on) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + STAGES * STAGE_BYTES + ONES_OFF);
+    for (int i = threadIdx.x; i < ONES_BYTES / 4; i += NTHREADS) ones[i] = 0x3F803F80u;      // bf16 1.0 pairs
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -529,6 +543,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       constexpr uint64_t STAGE_STEP = STAGE_BYTES >> 4;
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       uint32_t s = 0, ph = 0;
+      // bias-gradient fold: the tile of ones as a second (MN-major) B operand, N = 16
+      const uint64_t ones_desc = smem_desc(smem0 + STAGES * STAGE_BYTES + ONES_OFF, BK * 128, 1024);
+      const uint32_t idesc_cs = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(CS_COLS >> 3) << 17);
       for (int t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x, ++tc) {
         const int z = (t / p.n_tiles_total) / p.m_tiles;
         const int zs = z % p.nsplit;
@@ -540,6 +557,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         if (prof) w_acc += clock64() - tq0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
+        const bool cs_tile = CS_OK && cs_on && (t % p.n_tiles_total) == 0;      // first column tile (tap 0) of this row block
+        const uint32_t tmem_cs = tmem_base + 2 * BN + as * CS_COLS;
         uint32_t acc = 0;
         for (int i = 0; i < nkb; ++i) {
           const long long tq1 = prof ? clock64() : 0;
@@ -552,6 +571,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             // K-major: 16 elements = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
             // MN-major: 16 k-rows = 2 groups of 8 rows (1024 B each); 64-wide MN blocks 8192 B apart.
             umma_bf16(tmem_d, ad + k * A_STEP, bd + k * B_STEP, idesc, acc);
+            if (CS_OK && cs_tile) umma_bf16(tmem_cs, ad + k * A_STEP, ones_desc, idesc_cs, acc);
             acc = 1;
           }
           umma_commit(empty0 + 8 * s);
@@ -625,6 +645,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       const long long tq3 = prof ? clock64() : 0;
       if (prof) w_tfull += tq3 - tq2;
       tc_fence_after();
+      if (CS_OK && cs_on && nt == 0 && half == 0) {
+        // column sums of this row block's A tiles over the tile's K range: every thread holds the sum of its row m
+        uint32_t cs[8];
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * BN + as * CS_COLS), cs);
+        if (row_ok) atomicAdd(g.a_colsum + m, __uint_as_float(cs[0]) * g.alpha);
+      }
 #pragma unroll 1
       for (int ci = 0; ci < CHUNKS_PER_HALF; ++ci) {
         const int c = half * CHUNKS_PER_HALF + ci;
@@ -1038,7 +1064,7 @@ int g_num_sms = 0;
 
 template <int MODE, int BN, int STAGES>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, TcParams& p, cudaStream_t st) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256 + EPI_STAGE_TOTAL;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256 + EPI_STAGE_TOTAL + (MODE == 2 ? 768 + ONES_BYTES : 0);
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
@@ -1254,6 +1280,14 @@ extern "C" int fs2_gemm_tc_error_flag(void) {
   return v;
 }
 
+// Fs2Gemm.a_colsum where the chosen GEMM kernel cannot fold it in: the stand-alone column-sum kernel on the same stream
+static int colsum_fallback(const Fs2Gemm& g, cudaStream_t st) {
+  if (g.mode != 2 || g.batch1 * g.batch2 != 1) { fs2_set_error("fs2_gemm_tc: a_colsum needs mode 2 without batching"); return FS2_ERR_ARG; }
+  if (g.alpha != 1.f) { fs2_set_error("fs2_gemm_tc: a_colsum with alpha != 1 needs the 128 x 192-tile kernel"); return FS2_ERR_UNSUPPORTED; }
+  const bf16* a = (const bf16*)g.A + (long long)g.a_row_off * g.lda;
+  return fs2_colsum(a, 1, (long long)g.K, g.M, g.lda, g.a_colsum, (void*)st);
+}
+
 extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
   if (!gp || !gp->A || !gp->B || !gp->C) { fs2_set_error("fs2_gemm_tc: null pointer"); return FS2_ERR_ARG; }
   const Fs2Gemm& g = *gp;
@@ -1346,6 +1380,11 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
     }
   }
   if (use_pair) {
+    if (g.a_colsum) {                      // the pair kernel does not fold the bias gradient
+      rc = colsum_fallback(g, st);
+      if (rc) return rc;
+      p.g.a_colsum = nullptr;
+    }
     const int ncta = g_use_pair == 3 ? 1 : 2;
     if (g_num_sms == 0) {
       int dev = 0;
@@ -1374,6 +1413,12 @@ extern "C" int fs2_gemm_tc(const Fs2Gemm* gp, void* stream) {
     if (g.mode == 2) return dispatch_x<2>(cfg, ta, tb, p, st);
     fs2_set_error("fs2_gemm_tc: bad mode");
     return FS2_ERR_ARG;
+  }
+  // bias-gradient fold: only the 128 x 192-tile weight-gradient kernel has the spare tensor-memory columns
+  if (g.a_colsum && !(g.mode == 2 && BN == 192 && g.batch1 * g.batch2 == 1)) {
+    rc = colsum_fallback(g, st);
+    if (rc) return rc;
+    p.g.a_colsum = nullptr;
   }
   CUtensorMap ta, tb;
   // A: mode 0/1 K-major box (64 k, 128 rows); mode 2 MN-major box (64 m, 64 k-rows)

@@ -180,6 +180,8 @@ class FastSpeech2(nn.Module):
         self.fused_attention = True   # bf16, head_dim 192: fs2_flash_attn_fwd / _bwd instead of GEMM + softmax + GEMM
         # bf16, model width 384, k = 1 second FFN conv: out-projection -> norm1 and FFN conv 2 -> norm2 each run as ONE kernel
         # (fs2_gemm_ln_tc: the fp32 branch never reaches HBM); the backward takes x_hat from the saved LayerNorm output
+        # bf16 path: bias gradients ride inside the weight-gradient GEMMs (Fs2Gemm.a_colsum) instead of separate column-sum launches
+        self.fold_bias_grad = os.environ.get("FS2_FOLD_BIAS_GRAD", "1") != "0"
         self.fused_ln = os.environ.get("FS2_FUSED_LN", "1") != "0"
         self.fused_ln_min_rows_ffn = int(os.environ.get("FS2_FUSED_LN_MIN_ROWS_FFN", "8192"))
         self.async_mel_lens = False   # opt-in: no host sync; Tm is taken from pitch.shape[1], mel_lens arrives in pinned memory
@@ -359,6 +361,7 @@ class FastSpeech2(nn.Module):
         rows = B * (T + 2 * PAD)
         p = (w.k - 1) // 2
         split = 0            # auto: chosen by fs2_gemm_tc from the tile count and the SM count
+        fold = self._bf16 and self.fold_bias_grad
         o, _ = self.store.offsets[wkey]
         if w.gather:         # a column block of a wider (Cout, src_ld) matrix
             c_off, ldc, tap_stride = o + w.src_col0, w.src_ld, 1
@@ -367,8 +370,10 @@ class FastSpeech2(nn.Module):
         L.gemm(mode=2, M=w.cout, N=w.cin, K=rows, taps=w.k, A=dy, lda=w.cout, a_rows=rows, a_inner=w.cout,
                B=x, ldb=w.cin, b_rows=rows, b_inner=w.cin, b_row_off=-p, b_tap_step=1,
                Cout=self.store.flat_grad, C_off=c_off, ldc=ldc, c_tap_stride=tap_stride, c_col_stride=1,
-               c_bf16=False, ab_bf16=self._bf16, accumulate=1, split_k=split)
-        if bkey is not None:
+               c_bf16=False, ab_bf16=self._bf16, accumulate=1, split_k=split,
+               a_colsum=self._G(bkey) if (bkey is not None and fold) else None)
+        # bf16 path: the bias gradient (column sums of dy) rides along with the weight-gradient GEMM (Fs2Gemm.a_colsum)
+        if bkey is not None and not fold:
             L.call("fs2_colsum", dy, int(self._bf16), rows, w.cout, w.cout, self._G(bkey))
 
     def _ln_fwd(self, B, T, C, x, gamma, beta, eps, *, branch=None, drop_b=(0.0, 0), tanh=0, drop_a=(0.0, 0),

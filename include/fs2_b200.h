@@ -61,6 +61,10 @@ typedef struct {
   long long c_split_stride; /* modes 0/1, fs2_gemm_tc: with split_k = s > 1, split i of the reduction is STORED (no atomics) to
                               C + i * c_split_stride -- s partial results the consumer adds up (deterministic split-K for
                               short grids; fp32 C, plain epilogue).  0: not used. */
+  float* a_colsum;          /* fs2_gemm_tc, mode 2 only, optional: a_colsum[m] += alpha * sum_k A[a_row_off+k, m] -- the bias gradient
+                              that belongs to a weight gradient (db = column sums of dy).  Folded into the GEMM where the kernel
+                              has room for it (128 x 192 tiles: one extra N = 16 MMA per K step against a shared-memory tile of
+                              ones, in the first column tile only); otherwise the library launches its column-sum kernel. */
 } Fs2Gemm;
 
 int fs2_gemm_simt(const Fs2Gemm* g, void* stream);

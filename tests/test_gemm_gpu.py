@@ -185,3 +185,30 @@ def test_dgrad_deterministic_split_k(lib, M, rows):
     got = outs[0].double().sum(0)
     assert (got - ref).abs().max().item() <= 2e-4 * max(ref.abs().max().item(), 1.0)
     assert outs[0][0].abs().max() > 0 and outs[0][1].abs().max() > 0           # both halves carry a partial sum
+
+
+@pytest.mark.parametrize("name,M,N,K,taps,split", [
+    ("ffn_conv9_fold", 1536, 384, 2100, 9, 0),      # 128 x 192 tiles: the bias gradient rides inside the GEMM (ones-tile MMA), auto split-K
+    ("in_proj_fold", 1152, 384, 900, 1, 0),
+    ("ragged_m_fold", 200, 384, 777, 1, 3),         # M not a multiple of 128, fixed split
+    ("postnet_fallback", 512, 512, 1500, 5, 0),     # 256-wide tiles have no spare tensor-memory columns: separate column-sum kernel
+    ("n80_fallback", 512, 80, 1300, 5, 0),
+])
+def test_wgrad_bias_gradient_column_sums(lib, name, M, N, K, taps, split):
+    """Fs2Gemm.a_colsum: db[m] += sum_k dy[k, m] next to dW = dy^T x (mode 2) -- the bias gradient of a Conv1d / Linear
+    (reference: autograd of speechbrain Conv1d / nn.Linear biases, train.py:80)."""
+    p = (taps - 1) // 2
+    dy = _rand((K, M), 11, torch.bfloat16)
+    x = _rand((K, N), 12, torch.bfloat16)
+    dW = torch.zeros(M, taps * N, device="cuda")
+    db = torch.full((M,), 0.5, device="cuda")                      # accumulates (+=) like the flat gradient buffer
+    lib.gemm(mode=2, M=M, N=N, K=K, taps=taps, A=dy, lda=M, a_rows=K, a_inner=M, B=x, ldb=N, b_rows=K, b_inner=N,
+             b_row_off=-p, b_tap_step=1, Cout=dW, ldc=taps * N, c_tap_stride=N, c_col_stride=1, c_bf16=False, ab_bf16=True,
+             accumulate=1, split_k=split, a_colsum=db)
+    torch.cuda.synchronize()
+    assert lib.gemm_tc_error_flag() == 0
+    ref_db = 0.5 + dy.double().sum(0)
+    assert (db.double() - ref_db).abs().max().item() <= 2e-4 * max(1.0, ref_db.abs().max().item()), name
+    ref = ref_gemm(2, M, N, K, taps, dy.float(), x.float(), b_row_off=-p, b_tap_step=1)
+    err = (dW.double().view(ref.shape) - ref).abs().max().item()
+    assert err <= 2e-4 * max(ref.abs().max().item(), 1.0), name    # the weight gradient itself is unchanged
