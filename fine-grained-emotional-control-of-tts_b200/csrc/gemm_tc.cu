@@ -571,8 +571,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             // K-major: 16 elements = 32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
             // MN-major: 16 k-rows = 2 groups of 8 rows (1024 B each); 64-wide MN blocks 8192 B apart.
             umma_bf16(tmem_d, ad + k * A_STEP, bd + k * B_STEP, idesc, acc);
-            if (CS_OK && cs_tile) umma_bf16(tmem_cs, ad + k * A_STEP, ones_desc, idesc_cs, acc);
             acc = 1;
+          }
+          if (CS_OK && cs_tile) {
+            // column sums of the same A tile (one branch per k-block, outside the back-to-back MMA sequence above: the
+            // issue loop of this thread is the kernel's critical path)
+            const uint32_t acc_cs = (i != 0) ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_cs, ad + k * A_STEP, ones_desc, idesc_cs, (k != 0) ? 1u : acc_cs);
           }
           umma_commit(empty0 + 8 * s);
           if (++s == STAGES) { s = 0; ph ^= 1; }
