@@ -69,6 +69,28 @@ def test_struct_sizes_match_c(built, tmp_path):
                      ctypes.sizeof(built.Fs2PackItem), ctypes.sizeof(built.Fs2GemmLn)]
 
 
+def test_struct_field_offsets_match_c(built, tmp_path):
+    """Every field of every ctypes descriptor mirror sits at the offset the C compiler gives it in include/fs2_b200.h
+    (a size check alone would miss two swapped fields of the same type)."""
+    structs = {"Fs2Gemm": built.Fs2Gemm, "Fs2LnFwd": built.Fs2LnFwd, "Fs2LnBwd": built.Fs2LnBwd, "Fs2PackItem": built.Fs2PackItem,
+               "Fs2GemmLn": built.Fs2GemmLn}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fs2_b200.h"', 'int main(){']
+    names = []
+    for sn, cls in structs.items():
+        for fn, _ in cls._fields_:
+            lines.append(f'printf("%zu\\n", offsetof({sn}, {fn}));')
+            names.append((sn, fn, getattr(cls, fn).offset))
+    lines.append('return 0;}')
+    src = tmp_path / "off.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "off"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)   # unknown field = compile error
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert len(got) == len(names)
+    for (sn, fn, off), g in zip(names, got):
+        assert off == g, f"{sn}.{fn}: ctypes offset {off}, C offset {g}"
+
+
 def test_no_cpu_fallback(built):
     import torch
     pkg = importlib.import_module("fine-grained-emotional-control-of-tts_b200")
