@@ -10,14 +10,19 @@
 //   warp 1   : TMEM allocator; in the leader CTA the single-thread tcgen05.mma issuer (two M = 256, N = 192 MMAs per
 //              K = 16 step, completion multicast to both CTAs)
 //   warps 2-9: epilogue.  Each warp owns 16 rows (its TMEM lane quadrant, upper or lower half) and reads them in the
-//              16x256b register layout: a quad of lanes holds 32 contiguous bytes of a row, so residual loads and output
-//              stores are full-sector accesses straight from / to registers, and row statistics are quad shuffles.
+//              16x256b register layout: a quad of lanes holds 8 consecutive columns of a row (row statistics = quad shuffles,
+//              a lane's column pairs suit the packed fp32x2 instructions).  Nothing goes through the load/store unit to
+//              global memory on the fast path -- in this layout an instruction touches 8 lines x 32 bytes, which bounded
+//              the first versions: the residual arrives through a per-warp bulk-tensor ring (3 slots x 4 KB, 128B swizzle)
+//              and is read back with conflict-free ld.shared; the outputs go through per-warp swizzled staging tiles and
+//              bulk-tensor stores (warps that hold halo / mirror rows store from registers).
+//              While the tile's MMAs run: ring loads + the dropout keep bits of the lane's 2 x 96 elements (six words).
 //              pass 1: z = x + keep * (acc + bias) written back to tensor memory, row sums;  pass 2: centred squares;
 //              pass 3: normalise, scale / shift, store fp32 + bf16 (+ reflect-halo mirror rows).
-// While the MMAs of a tile run, the epilogue warps ask L2 for the tile's residual rows; the accumulator is handed back to
-// the MMA thread after the last tensor-memory read of pass 3, so the next tile's MMAs overlap the final stores.
-// The accumulator cannot be double-buffered (2 x 384 columns > 512): what overlaps a tile's epilogue is the TMA ring
-// (the next tile's first 3 k-blocks) and the other SMs' main loops.
+// The accumulator is handed back to the MMA thread after the last tensor-memory read of pass 3, so the next tile's MMAs
+// overlap the final stores.  It cannot be double-buffered (2 x 384 columns > 512): what overlaps a tile's epilogue is the
+// TMA ring (the next tile's first 3 k-blocks) and the other SMs' main loops.  History and cycle breakdown:
+// profiles/r02_summary.md section 6.
 #include <cuda.h>
 #include <cstdio>
 #include <cstring>
