@@ -557,8 +557,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         if (prof) w_acc += clock64() - tq0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        const bool cs_tile = CS_OK && cs_on && (t % p.n_tiles_total) == 0;      // first column tile (tap 0) of this row block
+        // bias-gradient fold: the column tiles of a row block (n_tiles_total of them walk the same A tiles) share the work --
+        // tile nt sums the k-blocks with (kb + nt) % n_tiles_total == 0, every tile adds its partial sums in the epilogue.
+        // (All of it in the first column tile made that tile twice as long as its neighbours: 182 -> 208 us for the k = 9
+        // FFN weight gradient; a countdown instead of a modulo keeps the issue loop short.)
         const uint32_t tmem_cs = tmem_base + 2 * BN + as * CS_COLS;
+        int cs_ctr = 0x7FFFFFFF;
+        if (CS_OK && cs_on) {
+            const int ntt = p.n_tiles_total;
+            cs_ctr = (ntt - (kb_begin + t % ntt) % ntt) % ntt;
+        }
+        uint32_t acc_cs = 0;
         uint32_t acc = 0;
         for (int i = 0; i < nkb; ++i) {
           const long long tq1 = prof ? clock64() : 0;
@@ -573,12 +582,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             umma_bf16(tmem_d, ad + k * A_STEP, bd + k * B_STEP, idesc, acc);
             acc = 1;
           }
-          if (CS_OK && cs_tile) {
+          if (CS_OK && cs_ctr-- == 0) {
             // column sums of the same A tile (one branch per k-block, outside the back-to-back MMA sequence above: the
             // issue loop of this thread is the kernel's critical path)
-            const uint32_t acc_cs = (i != 0) ? 1u : 0u;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_cs, ad + k * A_STEP, ones_desc, idesc_cs, (k != 0) ? 1u : acc_cs);
+            acc_cs = 1;
+            cs_ctr = p.n_tiles_total - 1;
           }
           umma_commit(empty0 + 8 * s);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -651,8 +661,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
       const long long tq3 = prof ? clock64() : 0;
       if (prof) w_tfull += tq3 - tq2;
       tc_fence_after();
-      if (CS_OK && cs_on && nt == 0 && half == 0) {
-        // column sums of this row block's A tiles over the tile's K range: every thread holds the sum of its row m
+      bool cs_have = false;
+      if (CS_OK && cs_on && half == 0) {
+        // did this tile's share of the k-blocks ((kb + nt) % n_tiles_total == 0) contain any?
+        const int zs_ = z % p.nsplit, kb0_ = zs_ * p.kb_per_split, kb1_ = min(p.total_kb, kb0_ + p.kb_per_split);
+        const int ntt = p.n_tiles_total;
+        cs_have = kb0_ + (ntt - (kb0_ + nt) % ntt) % ntt < kb1_;
+      }
+      if (CS_OK && cs_have) {
+        // partial column sums of this row block's A tiles: every thread holds the sum of its row m
         uint32_t cs[8];
         tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * BN + as * CS_COLS), cs);
         if (row_ok) atomicAdd(g.a_colsum + m, __uint_as_float(cs[0]) * g.alpha);
