@@ -63,8 +63,9 @@ typedef struct {
                               short grids; fp32 C, plain epilogue).  0: not used. */
   float* a_colsum;          /* fs2_gemm_tc, mode 2 only, optional: a_colsum[m] += alpha * sum_k A[a_row_off+k, m] -- the bias gradient
                               that belongs to a weight gradient (db = column sums of dy).  Folded into the GEMM where the kernel
-                              has room for it (128 x 192 tiles: one extra N = 16 MMA per K step against a shared-memory tile of
-                              ones, in the first column tile only); otherwise the library launches its column-sum kernel. */
+                              has room for it (128 x 192 tiles: extra N = 16 MMAs against a shared-memory tile of ones, the
+                              k-blocks shared out over the column tiles of a row block); otherwise the library launches its
+                              column-sum kernel. */
 } Fs2Gemm;
 
 int fs2_gemm_simt(const Fs2Gemm* g, void* stream);
